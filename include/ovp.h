@@ -1,0 +1,223 @@
+/*
+ * ovp.h — C ABI of the B200-native ov_plane hot path (MSCKF / point-on-plane EKF update + IMU covariance propagation).
+ *
+ * Drop-in boundary: the reference has no FFI seam — its updaters are C++ classes calling the all-static
+ * `StateHelper` (ov_plane/src/state/StateHelper.h) on a `State` whose covariance is private (State.h:123-133).  This library
+ * replaces what sits behind that seam.  An `ovp_ctx` owns, on ONE GPU, the covariance `_Cov` (fp64, column-major, symmetric,
+ * full storage), the variable table `_variables` (id / size / kind, same id semantics as ov_type::Type::id()) and the
+ * mean + first-estimate values of every variable (so that a chain of dependent updates never returns to the host).
+ * Every entry point below cites the reference function it replaces.  INTEGRATION.md shows the adapter a maintainer adds on
+ * the reference side (thin C++ shims with the reference's own signatures).
+ *
+ * Conventions: all matrices are column-major IEEE double; `handle` = stable integer naming one variable (what a
+ * std::shared_ptr<ov_type::Type> is in the reference); `id` = its offset in the covariance (-1 when not in the state).
+ * All functions return an ovp_status (0 = OK).  The reference prints and calls std::exit(EXIT_FAILURE) on the conditions
+ * mapped to OVP_ERR_* (StateHelper.cpp:46-49,55-59,116-118,185-187,279-283,387-391,403-407); an adapter maps non-zero
+ * status to the same print + exit.  One in-flight call per ctx; distinct ctxs are independent (State is unsynchronised in
+ * the reference too, SURVEY §8(b) "Threading").  There is NO CPU fallback: every entry point needs a CUDA device.
+ */
+#ifndef OVP_H
+#define OVP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ovp_ctx ovp_ctx;
+
+typedef enum ovp_status {
+  OVP_OK = 0,
+  OVP_ERR_BAD_ARGS = 1,          /* shape / handle errors (reference: assert, StateHelper.cpp:70-73,127-128) */
+  OVP_ERR_NEGATIVE_DIAGONAL = 2, /* StateHelper.cpp:107-118,176-187 */
+  OVP_ERR_NON_CONTIGUOUS = 3,    /* StateHelper.cpp:52-61 */
+  OVP_ERR_NON_ISOTROPIC = 4,     /* StateHelper.cpp:413-425 */
+  OVP_ERR_NOT_IN_STATE = 5,      /* StateHelper.cpp:279-283,387-391 */
+  OVP_ERR_ALREADY_IN_STATE = 6,  /* StateHelper.cpp:403-407 */
+  OVP_ERR_CAPACITY = 7,          /* state / measurement capacity given to ovp_create exceeded */
+  OVP_ERR_CUDA = 8,              /* CUDA runtime failure; see ovp_last_error */
+  OVP_ERR_NOT_POSITIVE_DEFINITE = 9,
+  OVP_ERR_TIME = 10              /* Propagator.cpp:41-51 (same / backwards timestamp), StateHelper.cpp:591-594 */
+} ovp_status;
+
+/* ov_type kinds the path needs (error-state size / value size): Vec(n/n), PoseJPL(6/7: q_xyzw,p), IMU(15/16: q,p,v,bg,ba),
+ * Landmark GLOBAL_3D (3/3).  JPL quaternion, left-multiplicative update (ov_type::JPLQuat::update). */
+typedef enum ovp_kind { OVP_KIND_VEC = 0, OVP_KIND_POSE = 1, OVP_KIND_IMU = 2, OVP_KIND_LANDMARK = 3 } ovp_kind;
+
+/* Subset of ov_plane::StateOptions (state/StateOptions.h:41-153) the path reads. */
+typedef struct ovp_state_options {
+  int do_fej;
+  int imu_avg;
+  int use_rk4_integration;
+  int do_calib_camera_pose;
+  int do_calib_camera_intrinsics;
+  int do_calib_camera_timeoffset;
+  int max_clone_size;
+  int max_aruco_features;
+  double sigma_constraint;
+  double const_init_multi;
+  double const_init_chi2;
+  double sigma_plane_merge;
+  double plane_merge_chi2;
+  double plane_merge_deg_max;
+} ovp_state_options;
+
+/* ---- context / State (state/State.h, State.cpp:33-102) ------------------------------------------------------------ */
+/* Builds the State exactly like State::State(options): imu, [dt], [extrinsics], [intrinsics] and the prior diagonal.
+ * max_state: covariance capacity (rows); max_meas_rows: capacity of one stacked measurement system (rows of Hx_big). */
+int ovp_create(const ovp_state_options *opt, int device, int max_state, int max_meas_rows, ovp_ctx **out);
+void ovp_destroy(ovp_ctx *ctx);
+const char *ovp_last_error(ovp_ctx *ctx);
+const char *ovp_status_string(int status);
+int ovp_set_chi2_table(ovp_ctx *ctx, const double *quantile95, int n); /* chi_squared_table, UpdaterMSCKF.cpp:59-62 */
+
+int ovp_cov_rows(ovp_ctx *ctx);                                       /* State::max_covariance_size(), State.h:87 */
+int ovp_cov_download(ovp_ctx *ctx, double *out, int ld);              /* StateHelper::get_full_covariance, :261-274 */
+int ovp_cov_upload(ovp_ctx *ctx, const double *in, int n, int ld);    /* raw overwrite, n must equal ovp_cov_rows */
+int ovp_handle_imu(ovp_ctx *ctx);
+int ovp_handle_dt(ovp_ctx *ctx);
+int ovp_handle_calib(ovp_ctx *ctx);
+int ovp_handle_intrinsics(ovp_ctx *ctx);
+int ovp_var_id(ovp_ctx *ctx, int handle);                             /* Type::id() */
+int ovp_var_size(ovp_ctx *ctx, int handle);                           /* Type::size() */
+int ovp_var_value_size(ovp_ctx *ctx, int handle);
+int ovp_var_set(ovp_ctx *ctx, int handle, const double *value, const double *fej); /* Type::set_value / set_fej */
+int ovp_var_get(ovp_ctx *ctx, int handle, double *value, double *fej);             /* Type::value / fej */
+int ovp_num_variables(ovp_ctx *ctx);
+int ovp_variable_order(ovp_ctx *ctx, int *handles);                   /* State::_variables order */
+int ovp_set_timestamp(ovp_ctx *ctx, double t);
+double ovp_get_timestamp(ovp_ctx *ctx);
+/* Append a variable with zero covariance (used by initialize_with_gt-style set-up and by tests; the covariance is then
+ * written with ovp_set_initial_covariance / ovp_cov_upload). */
+int ovp_add_clone_raw(ovp_ctx *ctx, double timestamp, const double *value7, const double *fej7, int *handle);
+int ovp_add_plane_raw(ovp_ctx *ctx, int64_t planeid, const double *cp, const double *cp_fej, int *handle);
+int ovp_add_slam_raw(ovp_ctx *ctx, int64_t featid, const double *p, const double *p_fej, int *handle);
+int ovp_plane_handle(ovp_ctx *ctx, int64_t planeid); /* State::_features_PLANE lookup, -1 when absent */
+int ovp_clone_handle(ovp_ctx *ctx, double timestamp); /* State::_clones_IMU lookup, -1 when absent */
+
+/* ---- StateHelper (state/StateHelper.cpp) ---------------------------------------------------------------------------- */
+int ovp_set_initial_covariance(ovp_ctx *ctx, const double *cov, int n, const int *handles, int k);      /* :204-229 */
+int ovp_get_marginal_covariance(ovp_ctx *ctx, const int *handles, int k, double *out);                   /* :231-259 */
+int ovp_ekf_propagation(ovp_ctx *ctx, const int *new_handles, int k_new, const int *old_handles, int k_old, const double *Phi,
+                        int phi_rows, int phi_cols, const double *Q);                                     /* :41-119 */
+/* H: rows x n (n = sum of sizes of `handles`), ld = rows; Rdiag NULL => identity (every caller on the path) */
+int ovp_ekf_update(ovp_ctx *ctx, const int *handles, int k, const double *H, int rows, const double *res,
+                   const double *Rdiag);                                                                  /* :121-202 */
+int ovp_marginalize(ovp_ctx *ctx, int handle);                                                            /* :276-344 */
+int ovp_clone(ovp_ctx *ctx, int handle, int *new_handle);                                                 /* :346-396 */
+int ovp_augment_clone(ovp_ctx *ctx, double timestamp, const double last_w[3], int *new_handle);           /* :588-625 */
+int ovp_marginalize_old_clone(ovp_ctx *ctx);                                                              /* :627-636 */
+int ovp_marginalize_slam(ovp_ctx *ctx);                                                                   /* :638-652 */
+/* initialize a new Vec (plane CP, tag = plane id) or Landmark (tag = feature id) of size s; R = sigma2 * I (isotropic is
+ * required, :413-425).  H_R rows x n, H_L rows x s, col-major.  *accepted = 0 on chi2 failure (state untouched). */
+int ovp_initialize(ovp_ctx *ctx, int kind, int s, const double *value, const double *fej, int64_t tag, const int *handles, int k,
+                   const double *H_R, const double *H_L, const double *res, int rows, double sigma2, double chi2_mult,
+                   int do_update, int *accepted, int *new_handle);                                        /* :398-487 */
+int ovp_initialize_invertible(ovp_ctx *ctx, int kind, int s, const double *value, const double *fej, int64_t tag,
+                              const int *handles, int k, const double *H_R, const double *H_L, const double *res, double sigma2,
+                              int *new_handle);                                                           /* :489-586 */
+int ovp_merge_planes_and_marginalize(ovp_ctx *ctx, const int64_t *f2p_feat, const int64_t *f2p_plane, int nf,
+                                     const int64_t *merge_new, const int64_t *merge_old, int nm);         /* :654-758 */
+
+/* ---- UpdaterHelper / UpdaterPlane static helpers (stateless, host buffers in / out, computed on the GPU) ------------ */
+/* UpdaterHelper::get_feature_jacobian_full (UpdaterHelper.cpp:195-513), mono, GLOBAL_3D.  Outputs col-major with
+ * ld = *rows_out; buffers sized for 3*m(+1) rows and (14 + 6*m + 3) columns; x_order receives variable handles. */
+int ovp_feature_jacobian_full(ovp_ctx *ctx, int m, const int *clone_handles, const float *uv, const double *p_FinG,
+                              const double *p_FinG_fej, int64_t planeid, const double *cp, const double *cp_fej, double sigma_px,
+                              double sigma_c, double *H_f, int *hf_cols, double *H_x, int *hx_cols, double *res, int *rows_out,
+                              int *x_order, int *x_order_n);
+/* UpdaterHelper::nullspace_project_inplace (:515-546) / UpdaterPlane::nullspace_project_inplace (UpdaterPlane.cpp:483-517).
+ * Result is an orthogonal-equivalent left-nullspace projection (Householder instead of the reference's Givens order):
+ * identical H_o^T H_o, H_o^T r and chi2; rows of H_o differ by an orthogonal transform (SURVEY §7 hazard list). */
+int ovp_nullspace_project_inplace(ovp_ctx *ctx, double *H_f, int hf_cols, double *H_x, int hx_cols, double *res, int rows,
+                                  int *rows_out);
+int ovp_plane_nullspace_project_inplace(ovp_ctx *ctx, double *H_f, int hf_cols, double *H_x, int hx_cols, double *H_cp,
+                                        double *res, int rows, int *rows_out);
+/* UpdaterHelper::measurement_compress_inplace (:548-579) / UpdaterPlane::measurement_compress_inplace
+ * (UpdaterPlane.cpp:519-552).  Q-less Cholesky-QR on tensor cores: returns upper-trapezoidal R with R^T R = H^T H and
+ * z = R^-T H^T res (equal to the Givens result up to row signs when H has full column rank; rank-deficient pivots give
+ * zero rows).  The plane variant carries H_cp and keeps only the first min(rows, cols) rows like the reference. */
+int ovp_measurement_compress_inplace(ovp_ctx *ctx, double *H_x, int cols, double *res, int rows, int *rows_out);
+int ovp_plane_measurement_compress_inplace(ovp_ctx *ctx, double *H_x, int cols, double *H_cp, double *res, int rows,
+                                           int *rows_out);
+
+/* ---- UpdaterMSCKF::update from "features triangulated, plane CPs known" on (UpdaterMSCKF.cpp:407-828) --------------- */
+typedef struct ovp_feature_batch {
+  int F;                         /* number of features (feature_vec after triangulation, caller's order)               */
+  const int *meas_offset;        /* F+1 prefix offsets into the measurement arrays                                      */
+  const int *meas_clone;         /* per measurement: handle of the clone it was taken at (Feature::timestamps)          */
+  const float *uv;               /* per measurement: raw pixel (u,v) as float, like Feature::uvs (Eigen::VectorXf)       */
+  const double *p_FinG;          /* 3F: triangulated (and, for on-plane features, plane-refined) position               */
+  const double *p_FinG_original; /* 3F: position before plane refinement (UpdaterMSCKF.cpp:160,663); may alias p_FinG   */
+  const int64_t *featid;         /* F                                                                                   */
+  const int64_t *planeid;        /* F: feat2plane value, 0 = not on a plane                                             */
+  int nplanes;                   /* planes that obtained a linearisation point (plane_estimates_cp_inG, :198-404)       */
+  const int64_t *plane_ids;      /* nplanes, any order (visited ascending like the std::map)                            */
+  const double *plane_cp;        /* 3*nplanes: CP estimate for planes NOT in the state (in-state planes use the state)  */
+} ovp_feature_batch;
+
+typedef struct ovp_updater_options { /* UpdaterOptions.h:38-54 */
+  double sigma_pix;
+  double chi2_multipler;
+} ovp_updater_options;
+
+/* Outputs: feat_status[F]: 1 accepted in the point update, 0 chi2-rejected, 2 consumed by a passed plane update;
+ * feat_chi2[F] (NaN when not gated individually); plane_status[nplanes]: 1 pass, 0 chi2 fail, -1 not visited;
+ * plane_chi2[nplanes]; hx_order: Hx_order_big of the final point update as variable handles (first-seen order over the
+ * accepted features, UpdaterMSCKF.cpp:768-775).  Any output pointer may be NULL. */
+int ovp_msckf_update(ovp_ctx *ctx, const ovp_feature_batch *batch, const ovp_updater_options *opt, int *feat_status,
+                     double *feat_chi2, int *plane_status, double *plane_chi2, int *hx_order, int *hx_order_n);
+
+/* ---- Multi-GPU sharding of one large update ----------------------------------------------------------- */
+/* Rank-local half: Jacobians, nullspace, chi2 gates and compression of THIS rank's point features against the replicated
+ * state; writes the (n+1) x (n+1) lower-triangular factor block [R^T ; z^T] in the canonical column order of the FULL batch
+ * described by all_clone_handles (every rank passes the same list) to d_out (DEVICE pointer, (n+1)*(n+1) doubles).
+ * Global half: stacks G gathered blocks (device pointer, G*(n+1)*(n+1) doubles, e.g. the output of ncclAllGather),
+ * re-compresses and runs the EKF update on this ctx. */
+int ovp_msckf_shard_columns(ovp_ctx *ctx, const int *all_clone_handles, int n_clones, int *n_cols);
+int ovp_msckf_shard_compress(ovp_ctx *ctx, const ovp_feature_batch *batch, const ovp_updater_options *opt,
+                             const int *all_clone_handles, int n_clones, double *d_out, int *feat_status, double *feat_chi2);
+int ovp_msckf_update_gathered(ovp_ctx *ctx, const double *d_blocks, int G, const int *all_clone_handles, int n_clones);
+
+/* ---- Propagator (state/Propagator.cpp) ------------------------------------------------------------------------------- */
+int ovp_propagator_set_noise(ovp_ctx *ctx, double sigma_w, double sigma_wb, double sigma_a, double sigma_ab,
+                             double gravity_mag);                       /* NoiseManager.h:41-63, Propagator.h:57-64 */
+int ovp_propagator_feed_imu(ovp_ctx *ctx, double timestamp, const double wm[3], const double am[3]); /* Propagator.h:71-88 */
+/* propagate_and_clone (:37-126): IMU selection + mean (RK4 / discrete) + summed Phi, Qd on the host, then ONE device pass:
+ * EKFPropagation + augment_clone.  Phi15 / Q15 (optional, 15x15 col-major) return the summed transition for parity tests. */
+int ovp_propagate_and_clone(ovp_ctx *ctx, double timestamp, double *Phi15, double *Q15, int *new_handle);
+
+/* Split form of ovp_msckf_update for callers that keep one feature batch resident on the device: prepare = validation,
+ * planning and the single host->device copy; launch = kernels only (asynchronous, repeatable: the state changes, the plan
+ * does not); finish = device->host read of the gates and Hx_order.  ovp_msckf_update == prepare + launch + finish. */
+int ovp_msckf_prepare(ovp_ctx *ctx, const ovp_feature_batch *batch, const ovp_updater_options *opt);
+int ovp_msckf_launch(ovp_ctx *ctx);
+int ovp_msckf_finish(ovp_ctx *ctx, int *feat_status, double *feat_chi2, int *plane_status, double *plane_chi2, int *hx_order,
+                     int *hx_order_n);
+/* device-side copy of (covariance, values, first-estimates) and its restore; the variable table must be unchanged */
+int ovp_snapshot(ovp_ctx *ctx);
+int ovp_restore(ovp_ctx *ctx);
+
+/* ---- instrumentation -------------------------------------------------------------------------------------------------- */
+/* number of kernel launches issued by this ctx since creation (bench.py's gpu_launches) */
+int64_t ovp_launch_count(ovp_ctx *ctx);
+/* CUDA stream the ctx launches on (as an opaque pointer) so that callers can time with events on the right stream */
+void *ovp_stream(ovp_ctx *ctx);
+/* device-resident timing of the last ovp_msckf_update, ms: [0] total, [1] feature kernels, [2] gram+compress, [3] ekf update */
+int ovp_last_timing(ovp_ctx *ctx, double *ms4);
+int ovp_synchronize(ovp_ctx *ctx);
+/* per-kernel timing with CUDA events on the launch stream: classes [0] DMMA gemm, [1] gram, [2] diagonal-block Cholesky,
+ * [3] feature kernel, [4] other; report = total ms, launch count and algorithmic work (flops; bytes for [3]) since enabled */
+int ovp_set_profiling(ovp_ctx *ctx, int on);
+int ovp_profile_report(ovp_ctx *ctx, double *ms5, int64_t *count5, double *work5);
+/* bytes this ctx copied host->device / device->host since creation */
+int ovp_transfer_bytes(ovp_ctx *ctx, int64_t *h2d, int64_t *d2h);
+/* measured FP64 tensor-core (DMMA) throughput of this device with the library's own GEMM kernel: returns TFLOP/s */
+int ovp_selftest_dgemm_tflops(ovp_ctx *ctx, int n, int iters, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVP_H */

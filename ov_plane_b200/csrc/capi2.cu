@@ -1,0 +1,1168 @@
+// Second half of the extern "C" surface: EKFUpdate / clone / marginalize / initialize entry points, the stateless
+// UpdaterHelper / UpdaterPlane helpers, UpdaterMSCKF::update, the multi-GPU shard halves, the Propagator and instrumentation.
+// (compiled as part of the unity build ovp_unity.cu, after capi.cu)
+#include "host_math.h"
+
+using namespace ovp;
+
+namespace ovp {
+
+__global__ void transpose_stack_kernel(const double *blocks, int G, int n, double *Hs, int ld) {
+  // Hs[(g*n + i), j] = L_g[j, i]   for i < n, j <= n ; block g is (n+1) x (n+1) col-major
+  size_t total = (size_t)G * n * (n + 1);
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    int j = (int)(t % (n + 1));
+    size_t r = t / (n + 1);
+    int i = (int)(r % n), g = (int)(r / n);
+    const double *L = blocks + (size_t)g * (n + 1) * (n + 1);
+    Hs[(size_t)j * ld + (size_t)g * n + i] = L[(size_t)i * (n + 1) + j];
+  }
+}
+
+static int small_inverse(const double *A, int s, double *Ainv) { // col-major, Gauss-Jordan with partial pivoting
+  double M[9], I[9];
+  for (int i = 0; i < s * s; i++) {
+    M[i] = A[i];
+    I[i] = 0;
+  }
+  for (int i = 0; i < s; i++)
+    I[i * s + i] = 1;
+  for (int k = 0; k < s; k++) {
+    int p = k;
+    for (int i = k + 1; i < s; i++)
+      if (std::fabs(M[k * s + i]) > std::fabs(M[k * s + p]))
+        p = i;
+    if (M[k * s + p] == 0.0)
+      return 1;
+    if (p != k)
+      for (int j = 0; j < s; j++) {
+        std::swap(M[j * s + k], M[j * s + p]);
+        std::swap(I[j * s + k], I[j * s + p]);
+      }
+    double d = M[k * s + k];
+    for (int j = 0; j < s; j++) {
+      M[j * s + k] /= d;
+      I[j * s + k] /= d;
+    }
+    for (int i = 0; i < s; i++)
+      if (i != k) {
+        double f = M[k * s + i];
+        for (int j = 0; j < s; j++) {
+          M[j * s + i] -= f * M[j * s + k];
+          I[j * s + i] -= f * I[j * s + k];
+        }
+      }
+  }
+  for (int i = 0; i < s * s; i++)
+    Ainv[i] = I[i];
+  return 0;
+}
+
+// new variable bookkeeping after its covariance rows exist
+static void register_new(Ctx *c, int h, int kind, int64_t tag) {
+  c->vars[h].id = c->N;
+  c->order.push_back(h);
+  c->N += c->vars[h].size;
+  c->var_table_dirty = true;
+  if (kind == OVP_KIND_LANDMARK)
+    c->slam[tag] = h;
+  else
+    c->planes[tag] = h;
+}
+
+// StateHelper::initialize_invertible on device-staged operands (W = [H_L | H_R | res], top s rows), StateHelper.cpp:489-586
+static int init_invertible_core(Ctx *c, int kind, int s, const double *value, const double *fej, int64_t tag, const int *d_cols, int n,
+                                const double *W, int ldW, double sigma2, int *new_handle) {
+  const int N = c->N;
+  if (N + s > c->Nmax)
+    return fail(c, OVP_ERR_CAPACITY, "state capacity %d exceeded", c->Nmax);
+  // M_a = P[:, cols] * Hxinit^T (N x s);  Hxinit = W[0:s, s:s+n]
+  MatView HxT = mv(W + (size_t)s * ldW, ldW, 1); // logical n x s
+  launch_gemm1(c, make_problem(N, s, n, mv(c->dP, c->ldP, 0, nullptr, d_cols), HxT, c->dM, c->Nmax));
+  // Mm = Hxinit * M_a[cols,:] + sigma2 I  (s x s) -> dscal[16..]
+  double *dMm = c->dscal + 16;
+  {
+    MatView Hx = HxT;
+    Hx.trans ^= 1;
+    GemmProblem p = make_problem(s, s, n, Hx, mv(c->dM, c->Nmax, 0, d_cols, nullptr), dMm, s);
+    p.diag_const = sigma2;
+    p.b_kfast = 0;
+    launch_gemm1(c, p);
+  }
+  // bring the s x s pieces to the host: H_finit (upper-triangular top of H_L), Mm, resinit
+  double hHL[9], hMm[9], hres[3], hW[3 * 3 + 3];
+  OVP_CUDA(cudaMemcpy2DAsync(hHL, s * sizeof(double), W, (size_t)ldW * sizeof(double), s * sizeof(double), s, cudaMemcpyDeviceToHost, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(hMm, dMm, s * s * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(hres, W + (size_t)(s + n) * ldW, s * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
+  (void)hW;
+  for (int j = 0; j < s; j++)
+    for (int i = j + 1; i < s; i++)
+      hHL[j * s + i] = 0.0; // below-diagonal entries were annihilated by the reflectors
+  double Hinv[9];
+  if (small_inverse(hHL, s, Hinv))
+    return fail(c, OVP_ERR_BAD_ARGS, "initialize: H_L is singular");
+  // symmetric Mm from its upper part (M.selfadjointView<Upper>, :566)
+  for (int j = 0; j < s; j++)
+    for (int i = j + 1; i < s; i++)
+      hMm[j * s + i] = hMm[i * s + j];
+  double T[9], PLL[9];
+  for (int i = 0; i < s; i++)
+    for (int j = 0; j < s; j++) {
+      double v = 0;
+      for (int k = 0; k < s; k++)
+        v += Hinv[k * s + i] * hMm[j * s + k]; // (Hinv * Mm)(i,j)
+      T[j * s + i] = v;
+    }
+  for (int i = 0; i < s; i++)
+    for (int j = 0; j < s; j++) {
+      double v = 0;
+      for (int k = 0; k < s; k++)
+        v += T[k * s + i] * Hinv[k * s + j]; // (T * Hinv^T)(i,j) = sum_k T(i,k) Hinv(j,k)
+      PLL[j * s + i] = v;
+    }
+  double dxn[3];
+  for (int i = 0; i < s; i++) {
+    double v = 0;
+    for (int k = 0; k < s; k++)
+      v += Hinv[k * s + i] * hres[k];
+    dxn[i] = v;
+  }
+  double *dsm = c->dscal + 32; // Hinv (9) + PLL (9)
+  double pack[18];
+  std::memcpy(pack, Hinv, sizeof(double) * 9);
+  std::memcpy(pack + 9, PLL, sizeof(double) * 9);
+  OVP_CUDA(cudaMemcpyAsync(dsm, pack, sizeof(pack), cudaMemcpyHostToDevice, c->stream));
+  init_grow_kernel<<<((N + s) * s + 255) / 256, 256, 0, c->stream>>>(c->dP, c->ldP, N, s, c->dM, c->Nmax, dsm, dsm + 9);
+  c->launches++;
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
+  Var v;
+  v.kind = kind;
+  v.size = s;
+  v.nvalue = s;
+  v.tag = tag;
+  double nv[3], nf[3];
+  for (int i = 0; i < s; i++) {
+    nv[i] = value[i] + dxn[i]; // new_variable->update(H_Linv * res), :577
+    nf[i] = fej[i];
+  }
+  int st = state_append_variable(c, v, nv, nf, new_handle);
+  if (st)
+    return st;
+  register_new(c, *new_handle, kind, tag);
+  return OVP_OK;
+}
+
+// shared front half of initialize / initialize_invertible: stage W = [H_L | H_R | res] on the device
+static int stage_init_system(Ctx *c, const double *H_R, const double *H_L, const double *res, int rows, int n, int s, double **W) {
+  size_t e = (size_t)rows * (s + n + 1);
+  int st = ensure_stage(c, e + 64);
+  if (st)
+    return st;
+  *W = c->d_stage;
+  OVP_CUDA(cudaMemcpyAsync(*W, H_L, (size_t)rows * s * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(*W + (size_t)rows * s, H_R, (size_t)rows * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(*W + (size_t)rows * (s + n), res, (size_t)rows * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  return OVP_OK;
+}
+
+} // namespace ovp
+
+extern "C" {
+
+int ovp_ekf_update(ovp_ctx *h, const int *handles, int k, const double *H, int rows, const double *res, const double *Rdiag) {
+  Ctx *c = &h->c;
+  int n = 0;
+  int st = upload_cols(c, handles, k, 0, &n);
+  if (st)
+    return st;
+  if (rows <= 0 || n <= 0)
+    return fail(c, OVP_ERR_BAD_ARGS, "ekf_update: empty system");
+  if (rows > c->Rcap)
+    return fail(c, OVP_ERR_CAPACITY, "ekf_update: %d rows exceed capacity %d (compress first, like the reference's callers)", rows, c->Rcap);
+  st = ensure_stage(c, (size_t)rows * n + 2 * rows);
+  if (st)
+    return st;
+  double *dH = c->d_stage, *dres = c->d_stage + (size_t)rows * n, *dR = dres + rows;
+  OVP_CUDA(cudaMemcpyAsync(dH, H, (size_t)rows * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(dres, res, (size_t)rows * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (Rdiag)
+    OVP_CUDA(cudaMemcpyAsync(dR, Rdiag, (size_t)rows * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  st = ekf_update_core(c, c->dcols, n, mv(dH, rows, 1), rows, dres, Rdiag ? dR : nullptr, -1.0, nullptr, nullptr);
+  if (st)
+    return st;
+  return check_status_flags(c);
+}
+
+int ovp_marginalize(ovp_ctx *h, int handle) { return do_marginalize(&h->c, handle); }
+
+int ovp_clone(ovp_ctx *h, int handle, int *new_handle) {
+  Ctx *c = &h->c;
+  if (!valid_handle(c, handle) || c->vars[handle].id < 0)
+    return fail(c, OVP_ERR_NOT_IN_STATE, "clone: variable %d not in the state (StateHelper.cpp:387-391)", handle);
+  int st = sync_host_values(c);
+  if (st)
+    return st;
+  Var v = c->vars[handle];
+  const bool imu_pose = (v.kind == OVP_KIND_IMU); // the only sub-variable clone on the path: imu->pose() (StateHelper.cpp:598)
+  if (imu_pose) {
+    v.kind = OVP_KIND_POSE;
+    v.size = 6;
+    v.nvalue = 7;
+  }
+  if (c->N + v.size > c->Nmax)
+    return fail(c, OVP_ERR_CAPACITY, "state capacity %d exceeded", c->Nmax);
+  int old = c->vars[handle].id;
+  v.id = -1;
+  st = state_append_variable(c, v, &c->h_val[(size_t)handle * OVP_VAL_STRIDE], &c->h_fej[(size_t)handle * OVP_VAL_STRIDE], new_handle);
+  if (st)
+    return st;
+  clone_kernel<<<((c->N + v.size) * v.size + 255) / 256, 256, 0, c->stream>>>(c->dP, c->ldP, c->N, old, v.size);
+  c->launches++;
+  c->vars[*new_handle].id = c->N;
+  c->order.push_back(*new_handle);
+  c->N += v.size;
+  c->var_table_dirty = true;
+  return OVP_OK;
+}
+
+int ovp_augment_clone(ovp_ctx *h, double timestamp, const double last_w[3], int *new_handle) {
+  Ctx *c = &h->c;
+  if (c->clones.count(timestamp))
+    return fail(c, OVP_ERR_TIME, "augment_clone: a clone at this timestamp exists (StateHelper.cpp:591-594)");
+  c->timestamp = timestamp;
+  int nh = -1;
+  int st = ovp_clone(h, c->h_imu, &nh);
+  if (st)
+    return st;
+  c->clones[timestamp] = nh;
+  if (c->opt.do_calib_camera_timeoffset) {
+    double dnc[6] = {last_w[0], last_w[1], last_w[2], c->h_val[(size_t)c->h_imu * OVP_VAL_STRIDE + 7],
+                     c->h_val[(size_t)c->h_imu * OVP_VAL_STRIDE + 8], c->h_val[(size_t)c->h_imu * OVP_VAL_STRIDE + 9]};
+    double *dd = c->dscal + 64;
+    OVP_CUDA(cudaMemcpyAsync(dd, dnc, sizeof(dnc), cudaMemcpyHostToDevice, c->stream));
+    int rows = c->N, newid = c->vars[nh].id, dtid = c->vars[c->h_dt].id;
+    dt_col_kernel<<<(rows * 6 + 255) / 256, 256, 0, c->stream>>>(c->dP, c->ldP, rows, newid, dtid, dd);
+    dt_row_kernel<<<(rows * 6 + 255) / 256, 256, 0, c->stream>>>(c->dP, c->ldP, rows, newid, dtid, dd);
+    c->launches += 2;
+    OVP_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  if (new_handle)
+    *new_handle = nh;
+  return OVP_OK;
+}
+
+int ovp_marginalize_old_clone(ovp_ctx *h) {
+  Ctx *c = &h->c;
+  if ((int)c->clones.size() > c->opt.max_clone_size) {
+    int hh = c->clones.begin()->second; // State::margtimestep(): the oldest clone
+    return do_marginalize(c, hh);
+  }
+  return OVP_OK;
+}
+
+int ovp_marginalize_slam(ovp_ctx *h) {
+  Ctx *c = &h->c;
+  std::vector<int> todo;
+  for (auto &kv : c->slam)
+    if (c->vars[kv.second].should_marg && (int)kv.first > 4 * c->opt.max_aruco_features)
+      todo.push_back(kv.second);
+  for (int hh : todo) {
+    int st = do_marginalize(c, hh);
+    if (st)
+      return st;
+  }
+  return OVP_OK;
+}
+
+int ovp_initialize_invertible(ovp_ctx *h, int kind, int s, const double *value, const double *fej, int64_t tag, const int *handles, int k,
+                              const double *H_R, const double *H_L, const double *res, double sigma2, int *new_handle) {
+  Ctx *c = &h->c;
+  if (s < 1 || s > 3)
+    return fail(c, OVP_ERR_BAD_ARGS, "initialize_invertible: new variable size %d not in 1..3", s);
+  if ((kind == OVP_KIND_LANDMARK && c->slam.count(tag)) || (kind == OVP_KIND_VEC && c->planes.count(tag)))
+    return fail(c, OVP_ERR_ALREADY_IN_STATE, "initialize_invertible: variable already in the state (StateHelper.cpp:494-498)");
+  int n = 0;
+  int st = upload_cols(c, handles, k, 0, &n);
+  if (st)
+    return st;
+  double *W;
+  st = stage_init_system(c, H_R, H_L, res, s, n, s, &W);
+  if (st)
+    return st;
+  return init_invertible_core(c, kind, s, value, fej, tag, c->dcols, n, W, s, sigma2, new_handle);
+}
+
+int ovp_initialize(ovp_ctx *h, int kind, int s, const double *value, const double *fej, int64_t tag, const int *handles, int k,
+                   const double *H_R, const double *H_L, const double *res, int rows, double sigma2, double chi2_mult, int do_update,
+                   int *accepted, int *new_handle) {
+  Ctx *c = &h->c;
+  *accepted = 0;
+  *new_handle = -1;
+  if (s < 1 || s > 3 || rows < s)
+    return fail(c, OVP_ERR_BAD_ARGS, "initialize: bad sizes (s=%d rows=%d)", s, rows);
+  if ((kind == OVP_KIND_LANDMARK && c->slam.count(tag)) || (kind == OVP_KIND_VEC && c->planes.count(tag)))
+    return fail(c, OVP_ERR_ALREADY_IN_STATE, "initialize: variable already in the state (StateHelper.cpp:403-407)");
+  if (rows >= c->chi2_table_n)
+    return fail(c, OVP_ERR_BAD_ARGS, "initialize: chi2 table too short for %d rows", rows);
+  int n = 0;
+  int st = upload_cols(c, handles, k, 0, &n);
+  if (st)
+    return st;
+  if (rows - s > c->Rcap)
+    return fail(c, OVP_ERR_CAPACITY, "initialize: %d rows exceed capacity", rows);
+  double *W;
+  st = stage_init_system(c, H_R, H_L, res, rows, n, s, &W);
+  if (st)
+    return st;
+  // separate the system with s reflectors on H_L (Givens in the reference, StateHelper.cpp:434-446; orthogonal-equivalent)
+  householder_cols_kernel<<<1, 256, (size_t)rows * sizeof(double), c->stream>>>(W, rows, rows, s + n + 1, s);
+  c->launches++;
+  const int ru = rows - s;
+  double *dR = c->dvec + 3 * (size_t)c->Rcap;
+  if (ru > 0) {
+    launch_fill(c, dR, ru, sigma2);
+    // chi2 of the updating portion against the CURRENT covariance (dry run), :464-475
+    st = ekf_update_core(c, c->dcols, n, mv(W + (size_t)s * rows + s, rows, 1), ru, W + (size_t)(s + n) * rows + s, dR, -1.0, nullptr,
+                         c->dscal, false);
+    if (st)
+      return st;
+  }
+  double chi2 = 0.0;
+  if (ru > 0) {
+    OVP_CUDA(cudaMemcpyAsync(&chi2, c->dscal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    OVP_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  st = check_status_flags(c);
+  if (st)
+    return st;
+  double chi2_check = c->chi2_table[rows]; // dof = full rows, not rows - s (:471-472)
+  if (chi2 > chi2_mult * chi2_check)
+    return OVP_OK; // accepted = 0, state untouched
+  st = init_invertible_core(c, kind, s, value, fej, tag, c->dcols, n, W, rows, sigma2, new_handle);
+  if (st)
+    return st;
+  *accepted = 1;
+  if (ru > 0 && do_update) {
+    st = ekf_update_core(c, c->dcols, n, mv(W + (size_t)s * rows + s, rows, 1), ru, W + (size_t)(s + n) * rows + s, dR, -1.0, nullptr,
+                         nullptr);
+    if (st)
+      return st;
+    return check_status_flags(c);
+  }
+  return OVP_OK;
+}
+
+int ovp_merge_planes_and_marginalize(ovp_ctx *h, const int64_t *f2p_feat, const int64_t *f2p_plane, int nf, const int64_t *merge_new,
+                                     const int64_t *merge_old, int nm) {
+  Ctx *c = &h->c;
+  (void)f2p_feat;
+  if (c->planes.empty())
+    return OVP_OK;
+  if (3 >= c->chi2_table_n)
+    return fail(c, OVP_ERR_BAD_ARGS, "chi2 table not set");
+  // StateHelper.cpp:661-736
+  std::vector<int64_t> ids;
+  for (auto &kv : c->planes)
+    ids.push_back(kv.first);
+  for (int64_t planeid : ids) {
+    if (!c->planes.count(planeid))
+      continue;
+    int64_t planeid_new = -1;
+    bool in_state = false;
+    for (int i = 0; i < nm; i++)
+      if (merge_old[i] == planeid) {
+        planeid_new = merge_new[i];
+        in_state = c->planes.count(planeid_new) > 0;
+      }
+    if (planeid_new == -1 || planeid == planeid_new)
+      continue;
+    if (!in_state) {
+      int hh = c->planes[planeid];
+      c->planes.erase(planeid);
+      c->planes[planeid_new] = hh;
+      c->vars[hh].tag = planeid_new;
+      continue;
+    }
+    int st = sync_host_values(c);
+    if (st)
+      return st;
+    int hn = c->planes[planeid_new], ho = c->planes[planeid];
+    const double *cpn = &c->h_val[(size_t)hn * OVP_VAL_STRIDE], *cpo = &c->h_val[(size_t)ho * OVP_VAL_STRIDE];
+    double nn = std::sqrt(cpn[0] * cpn[0] + cpn[1] * cpn[1] + cpn[2] * cpn[2]);
+    double no = std::sqrt(cpo[0] * cpo[0] + cpo[1] * cpo[1] + cpo[2] * cpo[2]);
+    double norm_dist = (cpn[0] * cpo[0] + cpn[1] * cpo[1] + cpn[2] * cpo[2]) / (nn * no);
+    double norm_angle = (180.0 / M_PI) * std::acos(norm_dist);
+    double wc = 1.0 / c->opt.sigma_plane_merge;
+    double res[3], H[18];
+    std::memset(H, 0, sizeof(H));
+    for (int i = 0; i < 3; i++) {
+      res[i] = wc * (0.0 - (cpn[i] - cpo[i]));
+      H[i * 3 + i] = wc;
+      H[(3 + i) * 3 + i] = -wc;
+    }
+    int hs[2] = {hn, ho};
+    double Pm[36];
+    st = ovp_get_marginal_covariance(h, hs, 2, Pm);
+    if (st)
+      return st;
+    // S = H P H^T + I (3x3), chi2 = res^T S^-1 res on the host (6x6 problem; the EKF update itself runs on the device)
+    double HP[18], S[9];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 6; j++) {
+        double v = 0;
+        for (int k2 = 0; k2 < 6; k2++)
+          v += H[k2 * 3 + i] * Pm[j * 6 + k2];
+        HP[j * 3 + i] = v;
+      }
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double v = (i == j) ? 1.0 : 0.0;
+        for (int k2 = 0; k2 < 6; k2++)
+          v += HP[k2 * 3 + i] * H[k2 * 3 + j];
+        S[j * 3 + i] = v;
+      }
+    double Sinv[9];
+    if (small_inverse(S, 3, Sinv))
+      return fail(c, OVP_ERR_NOT_POSITIVE_DEFINITE, "plane merge: singular S");
+    double chi2 = 0;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+        chi2 += res[i] * Sinv[j * 3 + i] * res[j];
+    double chi2_check = c->opt.plane_merge_chi2 * c->chi2_table[3];
+    if (chi2 < chi2_check && norm_angle < c->opt.plane_merge_deg_max) {
+      st = ovp_ekf_update(h, hs, 2, H, 3, res, nullptr);
+      if (st)
+        return st;
+    }
+    st = do_marginalize(c, ho);
+    if (st)
+      return st;
+  }
+  // marginalise planes no active feature refers to (:738-757)
+  std::set<int64_t> active;
+  for (int i = 0; i < nf; i++)
+    active.insert(f2p_plane[i]);
+  ids.clear();
+  for (auto &kv : c->planes)
+    ids.push_back(kv.first);
+  for (int64_t pid : ids)
+    if (!active.count(pid)) {
+      int st = do_marginalize(c, c->planes[pid]);
+      if (st)
+        return st;
+    }
+  return OVP_OK;
+}
+
+// ---- stateless helpers -----------------------------------------------------------------------------------------------
+int ovp_feature_jacobian_full(ovp_ctx *h, int m, const int *clone_handles, const float *uv, const double *p_FinG, const double *p_FinG_fej,
+                              int64_t planeid, const double *cp, const double *cp_fej, double sigma_px, double sigma_c, double *H_f,
+                              int *hf_cols, double *H_x, int *hx_cols, double *res, int *rows_out, int *x_order, int *x_order_n) {
+  Ctx *c = &h->c;
+  if (m < 1 || m > 64)
+    return fail(c, OVP_ERR_BAD_ARGS, "feature_jacobian_full: m=%d not in 1..64", m);
+  for (int i = 0; i < m; i++) {
+    if (!valid_handle(c, clone_handles[i]) || c->vars[clone_handles[i]].kind != OVP_KIND_POSE)
+      return fail(c, OVP_ERR_BAD_ARGS, "feature_jacobian_full: handle %d is not a clone", clone_handles[i]);
+    for (int j = 0; j < i; j++)
+      if (clone_handles[j] == clone_handles[i])
+        return fail(c, OVP_ERR_BAD_ARGS, "feature_jacobian_full: duplicate clone (mono camera assumed)");
+  }
+  const bool has_plane = planeid != 0;
+  const bool in_state = has_plane && c->planes.count(planeid);
+  const int ncal = (c->opt.do_calib_camera_pose ? 6 : 0) + (c->opt.do_calib_camera_intrinsics ? 8 : 0);
+  const int rows = has_plane ? 3 * m : 2 * m;
+  const int hfc = 3 + ((has_plane && !in_state) ? 3 : 0);
+  const int hxc = ncal + 6 * m + (in_state ? 3 : 0);
+  size_t e = (size_t)rows * (hfc + hxc + 1) + 256;
+  int st = ensure_stage(c, e);
+  if (st)
+    return st;
+  OVP_CUDA(cudaMemsetAsync(c->d_stage, 0, e * sizeof(double), c->stream));
+  JacArgs a;
+  a.m = m;
+  int *dcl = c->dcols + (size_t)4 * c->Rcap;
+  float *duv = (float *)(c->d_stage + (size_t)rows * (hfc + hxc + 1));
+  OVP_CUDA(cudaMemcpyAsync(dcl, clone_handles, m * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(duv, uv, 2 * m * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  a.clone_handles = dcl;
+  a.uv = duv;
+  for (int i = 0; i < 3; i++) {
+    a.pf[i] = p_FinG[i];
+    a.pf_fej[i] = p_FinG_fej[i];
+    a.cp[i] = has_plane ? cp[i] : 0.0;
+    a.cp_fej[i] = has_plane ? cp_fej[i] : 0.0;
+  }
+  a.has_plane = has_plane;
+  a.plane_in_state = in_state;
+  a.val = c->d_val;
+  a.fej = c->d_fej;
+  a.h_calib = c->h_calib;
+  a.h_intr = c->h_intr;
+  a.do_fej = c->opt.do_fej;
+  a.do_calib_pose = c->opt.do_calib_camera_pose;
+  a.do_calib_intr = c->opt.do_calib_camera_intrinsics;
+  a.white_px = 1.0 / sigma_px;
+  a.white_c = 1.0 / sigma_c;
+  a.Hf = c->d_stage;
+  a.Hx = c->d_stage + (size_t)rows * hfc;
+  a.res = c->d_stage + (size_t)rows * (hfc + hxc);
+  a.rows = rows;
+  a.hf_cols = hfc;
+  a.hx_cols = hxc;
+  jacobian_only_kernel<<<1, 64, 0, c->stream>>>(a);
+  c->launches++;
+  OVP_CUDA(cudaMemcpyAsync(H_f, a.Hf, (size_t)rows * hfc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(H_x, a.Hx, (size_t)rows * hxc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(res, a.res, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
+  *hf_cols = hfc;
+  *hx_cols = hxc;
+  *rows_out = rows;
+  int no = 0;
+  if (c->opt.do_calib_camera_pose)
+    x_order[no++] = c->h_calib;
+  if (c->opt.do_calib_camera_intrinsics)
+    x_order[no++] = c->h_intr;
+  for (int i = 0; i < m; i++)
+    x_order[no++] = clone_handles[i];
+  if (in_state)
+    x_order[no++] = c->planes[planeid];
+  *x_order_n = no;
+  return OVP_OK;
+}
+
+static int nullspace_common(Ctx *c, double *H_f, int hf_cols, double *H_x, int hx_cols, double *H_cp, double *res, int rows, int *rows_out) {
+  if (rows < hf_cols || hf_cols < 1)
+    return fail(c, OVP_ERR_BAD_ARGS, "nullspace_project: need rows >= H_f.cols() (assert, UpdaterHelper.cpp:518)");
+  int ncp = H_cp ? 3 : 0;
+  int ncols = hf_cols + hx_cols + ncp + 1;
+  int st = ensure_stage(c, (size_t)rows * ncols);
+  if (st)
+    return st;
+  double *W = c->d_stage;
+  OVP_CUDA(cudaMemcpyAsync(W, H_f, (size_t)rows * hf_cols * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(W + (size_t)rows * hf_cols, H_x, (size_t)rows * hx_cols * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (H_cp)
+    OVP_CUDA(cudaMemcpyAsync(W + (size_t)rows * (hf_cols + hx_cols), H_cp, (size_t)rows * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(W + (size_t)rows * (hf_cols + hx_cols + ncp), res, (size_t)rows * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  householder_cols_kernel<<<1, 256, (size_t)rows * sizeof(double), c->stream>>>(W, rows, rows, ncols, hf_cols);
+  c->launches++;
+  int ro = rows - hf_cols;
+  // copy back rows [hf_cols, rows) compacted to ld = ro
+  OVP_CUDA(cudaMemcpy2DAsync(H_x, (size_t)ro * sizeof(double), W + (size_t)rows * hf_cols + hf_cols, (size_t)rows * sizeof(double),
+                             (size_t)ro * sizeof(double), hx_cols, cudaMemcpyDeviceToHost, c->stream));
+  if (H_cp)
+    OVP_CUDA(cudaMemcpy2DAsync(H_cp, (size_t)ro * sizeof(double), W + (size_t)rows * (hf_cols + hx_cols) + hf_cols, (size_t)rows * sizeof(double),
+                               (size_t)ro * sizeof(double), 3, cudaMemcpyDeviceToHost, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(res, W + (size_t)rows * (hf_cols + hx_cols + ncp) + hf_cols, (size_t)ro * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
+  *rows_out = ro;
+  return OVP_OK;
+}
+int ovp_nullspace_project_inplace(ovp_ctx *h, double *H_f, int hf_cols, double *H_x, int hx_cols, double *res, int rows, int *rows_out) {
+  return nullspace_common(&h->c, H_f, hf_cols, H_x, hx_cols, nullptr, res, rows, rows_out);
+}
+int ovp_plane_nullspace_project_inplace(ovp_ctx *h, double *H_f, int hf_cols, double *H_x, int hx_cols, double *H_cp, double *res, int rows,
+                                        int *rows_out) {
+  return nullspace_common(&h->c, H_f, hf_cols, H_x, hx_cols, H_cp, res, rows, rows_out);
+}
+
+static int compress_common(Ctx *c, double *H_x, int cols, double *H_cp, double *res, int rows, int *rows_out) {
+  *rows_out = rows;
+  if (rows <= cols)
+    return OVP_OK; // fat matrix: nothing to do (UpdaterHelper.cpp:551-552)
+  int ncp = H_cp ? 3 : 0;
+  int nc1 = cols + ncp + 1;
+  if (nc1 > c->Rcap)
+    return fail(c, OVP_ERR_CAPACITY, "measurement_compress: %d columns exceed capacity %d", nc1, c->Rcap);
+  if (rows > c->max_meas_rows)
+    return fail(c, OVP_ERR_CAPACITY, "measurement_compress: %d rows exceed capacity %d", rows, c->max_meas_rows);
+  int ld = (rows + 7) & ~7;
+  launch_fill(c, c->dHs, (size_t)ld * nc1, 0.0);
+  OVP_CUDA(cudaMemcpy2DAsync(c->dHs, (size_t)ld * sizeof(double), H_x, (size_t)rows * sizeof(double), (size_t)rows * sizeof(double), cols,
+                             cudaMemcpyHostToDevice, c->stream));
+  if (H_cp)
+    OVP_CUDA(cudaMemcpy2DAsync(c->dHs + (size_t)ld * cols, (size_t)ld * sizeof(double), H_cp, (size_t)rows * sizeof(double),
+                               (size_t)rows * sizeof(double), 3, cudaMemcpyHostToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(c->dHs + (size_t)ld * (cols + ncp), res, (size_t)rows * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  int st = gram_of_stacked(c, rows, nc1, ld);
+  if (st)
+    return st;
+  st = chol_partial(c, c->wsG, c->wsG.S, c->wsG.cap, nc1, cols, 1e-11, false);
+  if (st)
+    return st;
+  // R = L[0:cols,0:cols]^T ; carried columns = L[cols.., 0:cols]^T
+  std::vector<double> L((size_t)nc1 * cols);
+  OVP_CUDA(cudaMemcpy2DAsync(L.data(), (size_t)nc1 * sizeof(double), c->wsG.S, (size_t)c->wsG.cap * sizeof(double), (size_t)nc1 * sizeof(double),
+                             cols, cudaMemcpyDeviceToHost, c->stream));
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
+  const int r = cols; // min(rows, cols)
+  for (int j = 0; j < cols; j++)
+    for (int i = 0; i < r; i++)
+      H_x[(size_t)j * r + i] = (i <= j) ? L[(size_t)i * nc1 + j] : 0.0;
+  if (H_cp)
+    for (int j = 0; j < 3; j++)
+      for (int i = 0; i < r; i++)
+        H_cp[(size_t)j * r + i] = L[(size_t)i * nc1 + cols + j];
+  for (int i = 0; i < r; i++)
+    res[i] = L[(size_t)i * nc1 + cols + ncp];
+  *rows_out = r;
+  return OVP_OK;
+}
+int ovp_measurement_compress_inplace(ovp_ctx *h, double *H_x, int cols, double *res, int rows, int *rows_out) {
+  return compress_common(&h->c, H_x, cols, nullptr, res, rows, rows_out);
+}
+int ovp_plane_measurement_compress_inplace(ovp_ctx *h, double *H_x, int cols, double *H_cp, double *res, int rows, int *rows_out) {
+  return compress_common(&h->c, H_x, cols, H_cp, res, rows, rows_out);
+}
+
+// ---- UpdaterMSCKF ------------------------------------------------------------------------------------------------------
+int ovp_msckf_update(ovp_ctx *h, const ovp_feature_batch *batch, const ovp_updater_options *opt, int *feat_status, double *feat_chi2,
+                     int *plane_status, double *plane_chi2, int *hx_order, int *hx_order_n) {
+  Ctx *c = &h->c;
+  if (!batch || !opt)
+    return fail(c, OVP_ERR_BAD_ARGS, "null batch / options");
+  return msckf_update_impl(c, batch, opt, feat_status, feat_chi2, plane_status, plane_chi2, hx_order, hx_order_n, nullptr);
+}
+
+static int shard_cols(Ctx *c, const int *all_clone_handles, int n_clones, std::vector<int> &cols) {
+  std::vector<std::pair<int, int>> blocks;
+  if (c->opt.do_calib_camera_pose)
+    blocks.push_back({c->vars[c->h_calib].id, 6});
+  if (c->opt.do_calib_camera_intrinsics)
+    blocks.push_back({c->vars[c->h_intr].id, 8});
+  for (int i = 0; i < n_clones; i++) {
+    int hh = all_clone_handles[i];
+    if (!valid_handle(c, hh) || c->vars[hh].kind != OVP_KIND_POSE || c->vars[hh].id < 0)
+      return fail(c, OVP_ERR_BAD_ARGS, "shard: handle %d is not a clone in the state", hh);
+    blocks.push_back({c->vars[hh].id, 6});
+  }
+  std::sort(blocks.begin(), blocks.end());
+  cols.clear();
+  for (auto &b : blocks)
+    for (int j = 0; j < b.second; j++)
+      cols.push_back(b.first + j);
+  return OVP_OK;
+}
+int ovp_msckf_shard_columns(ovp_ctx *h, const int *all_clone_handles, int n_clones, int *n_cols) {
+  std::vector<int> cols;
+  int st = shard_cols(&h->c, all_clone_handles, n_clones, cols);
+  if (st)
+    return st;
+  *n_cols = (int)cols.size();
+  return OVP_OK;
+}
+int ovp_msckf_shard_compress(ovp_ctx *h, const ovp_feature_batch *batch, const ovp_updater_options *opt, const int *all_clone_handles,
+                             int n_clones, double *d_out, int *feat_status, double *feat_chi2) {
+  Ctx *c = &h->c;
+  std::vector<int> cols;
+  int st = shard_cols(c, all_clone_handles, n_clones, cols);
+  if (st)
+    return st;
+  MsckfExtra ex;
+  ex.forced_cols = &cols;
+  ex.d_export = d_out;
+  if (batch->F == 0) {
+    size_t n1 = cols.size() + 1;
+    OVP_CUDA(cudaMemsetAsync(d_out, 0, n1 * n1 * sizeof(double), c->stream));
+    OVP_CUDA(cudaStreamSynchronize(c->stream));
+    return OVP_OK;
+  }
+  return msckf_update_impl(c, batch, opt, feat_status, feat_chi2, nullptr, nullptr, nullptr, nullptr, &ex);
+}
+int ovp_msckf_update_gathered(ovp_ctx *h, const double *d_blocks, int G, const int *all_clone_handles, int n_clones) {
+  Ctx *c = &h->c;
+  std::vector<int> cols;
+  int st = shard_cols(c, all_clone_handles, n_clones, cols);
+  if (st)
+    return st;
+  const int n = (int)cols.size();
+  const int rows = G * n, nc1 = n + 1;
+  if (rows > c->max_meas_rows || nc1 > c->Rcap)
+    return fail(c, OVP_ERR_CAPACITY, "gathered system %d x %d exceeds capacity", rows, nc1);
+  OVP_CUDA(cudaMemcpyAsync(c->dcols, cols.data(), n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  int ld = (rows + 7) & ~7;
+  launch_fill(c, c->dHs, (size_t)ld * nc1, 0.0);
+  transpose_stack_kernel<<<148 * 4, 256, 0, c->stream>>>(d_blocks, G, n, c->dHs, ld);
+  c->launches++;
+  st = gram_of_stacked(c, rows, nc1, ld);
+  if (st)
+    return st;
+  st = chol_partial(c, c->wsG, c->wsG.S, c->wsG.cap, nc1, n, 1e-11, false);
+  if (st)
+    return st;
+  double *d_z = c->dvec + c->Rcap;
+  extract_row_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->wsG.S, c->wsG.cap, nc1 - 1, n, d_z);
+  c->launches++;
+  st = ekf_update_core(c, c->dcols, n, mv(c->wsG.S, c->wsG.cap), n, d_z, nullptr, -1.0, nullptr, nullptr);
+  if (st)
+    return st;
+  return check_status_flags(c);
+}
+
+// ---- Propagator ----------------------------------------------------------------------------------------------------------
+int ovp_propagator_set_noise(ovp_ctx *h, double sigma_w, double sigma_wb, double sigma_a, double sigma_ab, double gravity_mag) {
+  Ctx *c = &h->c;
+  c->sigma_w = sigma_w;
+  c->sigma_wb = sigma_wb;
+  c->sigma_a = sigma_a;
+  c->sigma_ab = sigma_ab;
+  c->gravity[0] = 0;
+  c->gravity[1] = 0;
+  c->gravity[2] = gravity_mag;
+  return OVP_OK;
+}
+int ovp_propagator_feed_imu(ovp_ctx *h, double timestamp, const double wm[3], const double am[3]) {
+  ImuSample s;
+  s.t = timestamp;
+  for (int i = 0; i < 3; i++) {
+    s.wm[i] = wm[i];
+    s.am[i] = am[i];
+  }
+  h->c.imu_data.push_back(s);
+  return OVP_OK;
+}
+
+} // extern "C"
+
+namespace ovp {
+using namespace hm;
+
+static ImuSample interpolate_data(const ImuSample &a, const ImuSample &b, double t) { // Propagator.h:146-156
+  double lambda = (t - a.t) / (b.t - a.t);
+  ImuSample d;
+  d.t = t;
+  for (int i = 0; i < 3; i++) {
+    d.am[i] = (1 - lambda) * a.am[i] + lambda * b.am[i];
+    d.wm[i] = (1 - lambda) * a.wm[i] + lambda * b.wm[i];
+  }
+  return d;
+}
+static std::vector<ImuSample> select_imu_readings(const std::vector<ImuSample> &imu, double time0, double time1) { // Propagator.cpp:226-341
+  std::vector<ImuSample> prop;
+  if (imu.empty())
+    return prop;
+  for (size_t i = 0; i + 1 < imu.size(); i++) {
+    if (imu[i + 1].t > time0 && imu[i].t < time0) {
+      prop.push_back(interpolate_data(imu[i], imu[i + 1], time0));
+      continue;
+    }
+    if (imu[i].t >= time0 && imu[i + 1].t <= time1) {
+      prop.push_back(imu[i]);
+      continue;
+    }
+    if (imu[i + 1].t > time1) {
+      if (imu[i].t > time1 && i == 0) {
+        break;
+      } else if (imu[i].t > time1) {
+        prop.push_back(interpolate_data(imu[i - 1], imu[i], time1));
+      } else {
+        prop.push_back(imu[i]);
+      }
+      if (prop.back().t != time1)
+        prop.push_back(interpolate_data(imu[i], imu[i + 1], time1));
+      break;
+    }
+  }
+  if (prop.empty())
+    return prop;
+  for (size_t i = 0; i + 1 < prop.size(); i++)
+    if (std::abs(prop[i + 1].t - prop[i].t) < 1e-12) {
+      prop.erase(prop.begin() + i);
+      i--;
+    }
+  return prop;
+}
+
+struct ImuMean {
+  V4 q;
+  V3 p, v, bg, ba;
+};
+
+// Propagator.cpp:490-569
+static void predict_mean_rk4(const ImuMean &x, const V3 &g, double dt, const V3 &w1, const V3 &a1, const V3 &w2, const V3 &a2, V4 &nq, V3 &nv,
+                             V3 &np) {
+  V3 w_hat = w1, a_hat = a1;
+  V3 w_alpha = (1.0 / dt) * (w2 - w1);
+  V3 a_jerk = (1.0 / dt) * (a2 - a1);
+  V4 q_0 = x.q;
+  V3 p_0 = x.p, v_0 = x.v;
+  V4 dq_0{{0, 0, 0, 1}};
+  auto add4 = [](const V4 &a, double s, const V4 &b) { return V4{{a[0] + s * b[0], a[1] + s * b[1], a[2] + s * b[2], a[3] + s * b[3]}}; };
+  V4 q0_dot = half_omega_times(w_hat, dq_0);
+  V3 p0_dot = v_0;
+  M3 R0 = quat_2_Rot(quat_multiply(dq_0, q_0));
+  V3 v0_dot = transpose(R0) * a_hat - g;
+  V4 k1_q{{dt * q0_dot[0], dt * q0_dot[1], dt * q0_dot[2], dt * q0_dot[3]}};
+  V3 k1_p = dt * p0_dot, k1_v = dt * v0_dot;
+  w_hat = w_hat + (0.5 * dt) * w_alpha;
+  a_hat = a_hat + (0.5 * dt) * a_jerk;
+  V4 dq_1 = quatnorm(add4(dq_0, 0.5, k1_q));
+  V3 v_1 = v_0 + 0.5 * k1_v;
+  V4 q1_dot = half_omega_times(w_hat, dq_1);
+  M3 R1 = quat_2_Rot(quat_multiply(dq_1, q_0));
+  V3 v1_dot = transpose(R1) * a_hat - g;
+  V4 k2_q{{dt * q1_dot[0], dt * q1_dot[1], dt * q1_dot[2], dt * q1_dot[3]}};
+  V3 k2_p = dt * v_1, k2_v = dt * v1_dot;
+  V4 dq_2 = quatnorm(add4(dq_0, 0.5, k2_q));
+  V3 v_2 = v_0 + 0.5 * k2_v;
+  V4 q2_dot = half_omega_times(w_hat, dq_2);
+  M3 R2 = quat_2_Rot(quat_multiply(dq_2, q_0));
+  V3 v2_dot = transpose(R2) * a_hat - g;
+  V4 k3_q{{dt * q2_dot[0], dt * q2_dot[1], dt * q2_dot[2], dt * q2_dot[3]}};
+  V3 k3_p = dt * v_2, k3_v = dt * v2_dot;
+  w_hat = w_hat + (0.5 * dt) * w_alpha;
+  a_hat = a_hat + (0.5 * dt) * a_jerk;
+  V4 dq_3 = quatnorm(add4(dq_0, 1.0, k3_q));
+  V3 v_3 = v_0 + k3_v;
+  V4 q3_dot = half_omega_times(w_hat, dq_3);
+  M3 R3 = quat_2_Rot(quat_multiply(dq_3, q_0));
+  V3 v3_dot = transpose(R3) * a_hat - g;
+  V4 k4_q{{dt * q3_dot[0], dt * q3_dot[1], dt * q3_dot[2], dt * q3_dot[3]}};
+  V3 k4_p = dt * v_3, k4_v = dt * v3_dot;
+  V4 s = dq_0;
+  s = add4(s, 1.0 / 6.0, k1_q);
+  s = add4(s, 1.0 / 3.0, k2_q);
+  s = add4(s, 1.0 / 3.0, k3_q);
+  s = add4(s, 1.0 / 6.0, k4_q);
+  V4 dq = quatnorm(s);
+  nq = quat_multiply(dq, q_0);
+  np = p_0 + (1.0 / 6.0) * k1_p + (1.0 / 3.0) * k2_p + (1.0 / 3.0) * k3_p + (1.0 / 6.0) * k4_p;
+  nv = v_0 + (1.0 / 6.0) * k1_v + (1.0 / 3.0) * k2_v + (1.0 / 3.0) * k3_v + (1.0 / 6.0) * k4_v;
+}
+// Propagator.cpp:456-488
+static void predict_mean_discrete(const ImuMean &x, const V3 &g, bool imu_avg, double dt, const V3 &w1, const V3 &a1, const V3 &w2, const V3 &a2,
+                                  V4 &nq, V3 &nv, V3 &np) {
+  V3 w_hat = w1, a_hat = a1;
+  if (imu_avg) {
+    w_hat = 0.5 * (w1 + w2);
+    a_hat = 0.5 * (a1 + a2);
+  }
+  double w_norm = norm(w_hat);
+  M3 R = quat_2_Rot(x.q);
+  V4 ho = half_omega_times(w_hat, x.q); // 0.5 * Omega(w) q
+  V4 q;
+  if (w_norm > 1e-20) {
+    double cs = std::cos(0.5 * w_norm * dt), sn = (1 / w_norm) * std::sin(0.5 * w_norm * dt);
+    for (int i = 0; i < 4; i++)
+      q[i] = cs * x.q[i] + sn * 2.0 * ho[i];
+  } else {
+    for (int i = 0; i < 4; i++)
+      q[i] = x.q[i] + dt * ho[i];
+  }
+  nq = quatnorm(q);
+  nv = x.v + dt * (transpose(R) * a_hat) - dt * g;
+  np = x.p + dt * x.v + (0.5 * dt * dt) * (transpose(R) * a_hat) - (0.5 * dt * dt) * g;
+}
+
+} // namespace ovp
+
+extern "C" {
+
+int ovp_propagate_and_clone(ovp_ctx *h, double timestamp, double *Phi15, double *Q15, int *new_handle) {
+  using namespace ovp::hm;
+  Ctx *c = &h->c;
+  if (c->timestamp == timestamp)
+    return fail(c, OVP_ERR_TIME, "propagate_and_clone: same timestep as the last update (Propagator.cpp:41-44)");
+  if (c->timestamp > timestamp)
+    return fail(c, OVP_ERR_TIME, "propagate_and_clone: backwards in time (Propagator.cpp:47-51)");
+  int st = sync_host_values(c);
+  if (st)
+    return st;
+  double *iv = &c->h_val[(size_t)c->h_imu * OVP_VAL_STRIDE];
+  double *ifej = &c->h_fej[(size_t)c->h_imu * OVP_VAL_STRIDE];
+  double t_off = c->h_val[(size_t)c->h_dt * OVP_VAL_STRIDE];
+  if (!c->have_last_prop_time_offset) {
+    c->last_prop_time_offset = t_off;
+    c->have_last_prop_time_offset = true;
+  }
+  double time0 = c->timestamp + c->last_prop_time_offset;
+  double time1 = timestamp + t_off;
+  std::vector<ImuSample> prop = select_imu_readings(c->imu_data, time0, time1);
+  M15 Phi, Qs;
+  for (int i = 0; i < 15; i++)
+    Phi(i, i) = 1.0;
+  V3 g = v3(c->gravity[0], c->gravity[1], c->gravity[2]);
+  const int th = 0, p_id = 3, v_id = 6, bg = 9, ba = 12;
+  if (prop.size() > 1) {
+    for (size_t i = 0; i + 1 < prop.size(); i++) {
+      // predict_and_compute, Propagator.cpp:343-454
+      ImuMean x;
+      ImuMean xf;
+      for (int k = 0; k < 4; k++) {
+        x.q[k] = iv[k];
+        xf.q[k] = ifej[k];
+      }
+      for (int k = 0; k < 3; k++) {
+        x.p[k] = iv[4 + k];
+        x.v[k] = iv[7 + k];
+        x.bg[k] = iv[10 + k];
+        x.ba[k] = iv[13 + k];
+        xf.p[k] = ifej[4 + k];
+        xf.v[k] = ifej[7 + k];
+      }
+      double dt = prop[i + 1].t - prop[i].t;
+      V3 w_hat = v3(prop[i].wm[0], prop[i].wm[1], prop[i].wm[2]) - x.bg;
+      V3 a_hat = v3(prop[i].am[0], prop[i].am[1], prop[i].am[2]) - x.ba;
+      V3 w_hat2 = v3(prop[i + 1].wm[0], prop[i + 1].wm[1], prop[i + 1].wm[2]) - x.bg;
+      V3 a_hat2 = v3(prop[i + 1].am[0], prop[i + 1].am[1], prop[i + 1].am[2]) - x.ba;
+      V4 nq;
+      V3 nv, np;
+      if (c->opt.use_rk4_integration)
+        predict_mean_rk4(x, g, dt, w_hat, a_hat, w_hat2, a_hat2, nq, nv, np);
+      else
+        predict_mean_discrete(x, g, c->opt.imu_avg != 0, dt, w_hat, a_hat, w_hat2, a_hat2, nq, nv, np);
+      M15 F;
+      double G[15][12];
+      std::memset(G, 0, sizeof(G));
+      auto setG = [&](int i0, int j0, const M3 &B) {
+        for (int a = 0; a < 3; a++)
+          for (int b = 0; b < 3; b++)
+            G[i0 + a][j0 + b] = B(a, b);
+      };
+      M3 I3 = eye3();
+      if (c->opt.do_fej) {
+        M3 Rfej = quat_2_Rot(xf.q);
+        M3 RfT = transpose(Rfej);
+        M3 dR = quat_2_Rot(nq) * RfT;
+        M3 Jr = Jr_so3((-dt) * w_hat);
+        M3 dRJ = (-dt) * (dR * Jr);
+        F.setBlock3(th, th, dR);
+        F.setBlock3(th, bg, dRJ);
+        F.setBlock3(bg, bg, I3);
+        F.setBlock3(v_id, th, (-1.0) * (skew(nv - xf.v + dt * g) * RfT));
+        F.setBlock3(v_id, v_id, I3);
+        F.setBlock3(v_id, ba, (-dt) * RfT);
+        F.setBlock3(ba, ba, I3);
+        F.setBlock3(p_id, th, (-1.0) * (skew(np - xf.p - dt * xf.v + (0.5 * dt * dt) * g) * RfT));
+        F.setBlock3(p_id, v_id, dt * I3);
+        F.setBlock3(p_id, ba, (-0.5 * dt * dt) * RfT);
+        F.setBlock3(p_id, p_id, I3);
+        setG(th, 0, dRJ);
+        setG(v_id, 3, (-dt) * RfT);
+        setG(p_id, 3, (-0.5 * dt * dt) * RfT);
+        setG(bg, 6, I3);
+        setG(ba, 9, I3);
+      } else {
+        M3 R = quat_2_Rot(x.q);
+        M3 RT = transpose(R);
+        M3 E = exp_so3((-dt) * w_hat);
+        M3 Jr = Jr_so3((-dt) * w_hat);
+        M3 EJ = (-dt) * (E * Jr);
+        F.setBlock3(th, th, E);
+        F.setBlock3(th, bg, EJ);
+        F.setBlock3(bg, bg, I3);
+        F.setBlock3(v_id, th, (-1.0) * (RT * skew(dt * a_hat)));
+        F.setBlock3(v_id, v_id, I3);
+        F.setBlock3(v_id, ba, (-dt) * RT);
+        F.setBlock3(ba, ba, I3);
+        F.setBlock3(p_id, th, (-0.5) * (RT * skew((dt * dt) * a_hat)));
+        F.setBlock3(p_id, v_id, dt * I3);
+        F.setBlock3(p_id, ba, (-0.5 * dt * dt) * RT);
+        F.setBlock3(p_id, p_id, I3);
+        setG(th, 0, EJ);
+        setG(v_id, 3, (-dt) * RT);
+        setG(p_id, 3, (-0.5 * dt * dt) * RT);
+        setG(bg, 6, I3);
+        setG(ba, 9, I3);
+      }
+      double qc[12];
+      for (int k = 0; k < 3; k++) {
+        qc[k] = c->sigma_w * c->sigma_w / dt;
+        qc[3 + k] = c->sigma_a * c->sigma_a / dt;
+        qc[6 + k] = c->sigma_wb * c->sigma_wb * dt;
+        qc[9 + k] = c->sigma_ab * c->sigma_ab * dt;
+      }
+      M15 Qd;
+      for (int a = 0; a < 15; a++)
+        for (int b = 0; b < 15; b++) {
+          double s = 0;
+          for (int k = 0; k < 12; k++)
+            s += G[a][k] * qc[k] * G[b][k];
+          Qd(a, b) = s;
+        }
+      for (int a = 0; a < 15; a++)
+        for (int b = a + 1; b < 15; b++) {
+          double m = 0.5 * (Qd(a, b) + Qd(b, a));
+          Qd(a, b) = Qd(b, a) = m;
+        }
+      // state mean + FEJ are both replaced by the propagated mean (:448-453)
+      for (int k = 0; k < 4; k++)
+        iv[k] = nq[k];
+      for (int k = 0; k < 3; k++) {
+        iv[4 + k] = np[k];
+        iv[7 + k] = nv[k];
+      }
+      for (int k = 0; k < 16; k++)
+        ifej[k] = iv[k];
+      // Phi_summed = F Phi ; Qd_summed = F Qd_summed F^T + Qdi, symmetrised (:100-102)
+      Phi = mul(F, Phi);
+      M15 FQ = mul(F, Qs);
+      Qs = mulT(FQ, F);
+      for (int a = 0; a < 225; a++)
+        Qs.a[a] += Qd.a[a];
+      for (int a = 0; a < 15; a++)
+        for (int b = a + 1; b < 15; b++) {
+          double m = 0.5 * (Qs(a, b) + Qs(b, a));
+          Qs(a, b) = Qs(b, a) = m;
+        }
+    }
+  }
+  double last_w[3] = {0, 0, 0};
+  if (prop.size() > 1)
+    for (int k = 0; k < 3; k++)
+      last_w[k] = prop[prop.size() - 2].wm[k] - iv[10 + k];
+  else if (!prop.empty())
+    for (int k = 0; k < 3; k++)
+      last_w[k] = prop.back().wm[k] - iv[10 + k];
+  st = push_host_values(c, c->h_imu);
+  if (st)
+    return st;
+  // column-major copies for the device
+  double PhiC[225], QC[225];
+  for (int i = 0; i < 15; i++)
+    for (int j = 0; j < 15; j++) {
+      PhiC[j * 15 + i] = Phi(i, j);
+      QC[j * 15 + i] = Qs(i, j);
+    }
+  int hi = c->h_imu;
+  st = ovp_ekf_propagation(h, &hi, 1, &hi, 1, PhiC, 15, 15, QC);
+  if (st)
+    return st;
+  c->last_prop_time_offset = t_off;
+  int nh = -1;
+  st = ovp_augment_clone(h, timestamp, last_w, &nh);
+  if (st)
+    return st;
+  if (Phi15)
+    std::memcpy(Phi15, PhiC, sizeof(PhiC));
+  if (Q15)
+    std::memcpy(Q15, QC, sizeof(QC));
+  if (new_handle)
+    *new_handle = nh;
+  return OVP_OK;
+}
+
+// ---- instrumentation -----------------------------------------------------------------------------------------------------
+int64_t ovp_launch_count(ovp_ctx *h) { return h->c.launches; }
+void *ovp_stream(ovp_ctx *h) { return (void *)h->c.stream; }
+int ovp_last_timing(ovp_ctx *h, double *ms4) {
+  for (int i = 0; i < 4; i++)
+    ms4[i] = h->c.last_ms[i];
+  return OVP_OK;
+}
+int ovp_synchronize(ovp_ctx *h) {
+  Ctx *c = &h->c;
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
+  return OVP_OK;
+}
+int ovp_selftest_dgemm_tflops(ovp_ctx *h, int n, int iters, double *tflops) {
+  Ctx *c = &h->c;
+  if (n < 64 || iters < 1)
+    return fail(c, OVP_ERR_BAD_ARGS, "selftest: bad sizes");
+  double *A, *B, *C;
+  size_t e = (size_t)n * n;
+  OVP_CUDA(cudaMalloc(&A, e * sizeof(double)));
+  OVP_CUDA(cudaMalloc(&B, e * sizeof(double)));
+  OVP_CUDA(cudaMalloc(&C, e * sizeof(double)));
+  dmma_selftest_fill<<<(unsigned)((e + 255) / 256), 256, 0, c->stream>>>(A, e, 1.0);
+  dmma_selftest_fill<<<(unsigned)((e + 255) / 256), 256, 0, c->stream>>>(B, e, 0.5);
+  GemmProblem p = make_problem(n, n, n, mv(A, n), mv(B, n), C, n);
+  for (int i = 0; i < 3; i++)
+    launch_gemm1(c, p);
+  cudaEventRecord(c->ev[2], c->stream);
+  for (int i = 0; i < iters; i++)
+    launch_gemm1(c, p);
+  cudaEventRecord(c->ev[3], c->stream);
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+  *tflops = 2.0 * (double)n * n * n * iters / (ms * 1e-3) / 1e12;
+  cudaFree(A);
+  cudaFree(B);
+  cudaFree(C);
+  return OVP_OK;
+}
+
+} // extern "C"
+
+// ---- prepared-batch variant of UpdaterMSCKF::update, snapshots and per-kernel profiling (measurement support) ----------
+extern "C" {
+
+int ovp_msckf_prepare(ovp_ctx *h, const ovp_feature_batch *batch, const ovp_updater_options *opt) {
+  Ctx *c = &h->c;
+  if (!batch || !opt)
+    return fail(c, OVP_ERR_BAD_ARGS, "null batch / options");
+  return msckf_prepare(c, batch, opt, nullptr);
+}
+int ovp_msckf_launch(ovp_ctx *h) { return msckf_launch(&h->c); }
+int ovp_msckf_finish(ovp_ctx *h, int *feat_status, double *feat_chi2, int *plane_status, double *plane_chi2, int *hx_order, int *hx_order_n) {
+  if (hx_order_n)
+    *hx_order_n = 0;
+  return msckf_finish(&h->c, feat_status, feat_chi2, plane_status, plane_chi2, hx_order, hx_order_n);
+}
+
+int ovp_snapshot(ovp_ctx *h) {
+  Ctx *c = &h->c;
+  size_t pe = (size_t)c->ldP * c->Nmax, ve = (size_t)c->max_handles * OVP_VAL_STRIDE;
+  if (!c->snapP) {
+    OVP_CUDA(cudaMalloc(&c->snapP, pe * sizeof(double)));
+    OVP_CUDA(cudaMalloc(&c->snap_val, ve * sizeof(double)));
+    OVP_CUDA(cudaMalloc(&c->snap_fej, ve * sizeof(double)));
+  }
+  OVP_CUDA(cudaMemcpyAsync(c->snapP, c->dP, (size_t)c->ldP * c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(c->snap_val, c->d_val, c->vars.size() * OVP_VAL_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(c->snap_fej, c->d_fej, c->vars.size() * OVP_VAL_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  c->snapN = c->N;
+  return OVP_OK;
+}
+int ovp_restore(ovp_ctx *h) {
+  Ctx *c = &h->c;
+  if (c->snapN != c->N)
+    return fail(c, OVP_ERR_BAD_ARGS, "restore: no snapshot of a %d-row state", c->N);
+  OVP_CUDA(cudaMemcpyAsync(c->dP, c->snapP, (size_t)c->ldP * c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(c->d_val, c->snap_val, c->vars.size() * OVP_VAL_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(c->d_fej, c->snap_fej, c->vars.size() * OVP_VAL_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  c->launches += 3;
+  c->host_values_stale = true;
+  return OVP_OK;
+}
+
+int ovp_set_profiling(ovp_ctx *h, int on) {
+  Ctx *c = &h->c;
+  cudaStreamSynchronize(c->stream);
+  c->profiling = on != 0;
+  c->prof_recs.clear();
+  c->ev_used = 0;
+  c->prof_pending = nullptr;
+  return OVP_OK;
+}
+// per kernel class [gemm, gram, potrf, feature, other]: total ms, launch count, algorithmic work (flops or bytes)
+int ovp_profile_report(ovp_ctx *h, double *ms, int64_t *count, double *work) {
+  Ctx *c = &h->c;
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < PROF_N; i++) {
+    ms[i] = 0;
+    count[i] = 0;
+    work[i] = 0;
+  }
+  for (auto &r : c->prof_recs) {
+    float t = 0;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    ms[r.id] += t;
+    count[r.id]++;
+    work[r.id] += r.work;
+  }
+  c->prof_recs.clear();
+  c->ev_used = 0;
+  return OVP_OK;
+}
+int ovp_transfer_bytes(ovp_ctx *h, int64_t *h2d, int64_t *d2h) {
+  *h2d = h->c.h2d_bytes;
+  *d2h = h->c.d2h_bytes;
+  return OVP_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,231 @@
+// Device-resident State (covariance + variable values) and the StateHelper algebra:
+// EKFUpdate (StateHelper.cpp:121-202), EKFPropagation (:41-119), clone / augment_clone (:346-396, :588-625),
+// marginalize (:276-344), get_marginal_covariance (:231-259), set_initial_covariance (:204-229),
+// initialize_invertible's covariance growth (:568-573) and ov_type::*::update (the manifold update of every variable).
+#include "ovp_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace ovp {
+
+// -------------------------------------------------------------------------------------------------------------------
+// ov_type::Vec/JPLQuat/PoseJPL/IMU/Landmark::update on the device (JPL left-multiplicative quaternion update)
+// -------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void quat_left_update(double *q, const double *dth) {
+  // dq = quatnorm([0.5*dth; 1]); q <- quat_multiply(dq, q)   (ov_core quat_ops.h semantics)
+  double a0 = 0.5 * dth[0], a1 = 0.5 * dth[1], a2 = 0.5 * dth[2], a3 = 1.0;
+  double nrm = sqrt(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3);
+  a0 /= nrm;
+  a1 /= nrm;
+  a2 /= nrm;
+  a3 /= nrm;
+  double p0 = q[0], p1 = q[1], p2 = q[2], p3 = q[3];
+  // Qm = [a3*I - skew(av), av; -av^T, a3]
+  double r0 = a3 * p0 + a2 * p1 - a1 * p2 + a0 * p3;
+  double r1 = -a2 * p0 + a3 * p1 + a0 * p2 + a1 * p3;
+  double r2 = a1 * p0 - a0 * p1 + a3 * p2 + a2 * p3;
+  double r3 = -a0 * p0 - a1 * p1 - a2 * p2 + a3 * p3;
+  if (r3 < 0) {
+    r0 = -r0;
+    r1 = -r1;
+    r2 = -r2;
+    r3 = -r3;
+  }
+  double n2 = sqrt(r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3);
+  q[0] = r0 / n2;
+  q[1] = r1 / n2;
+  q[2] = r2 / n2;
+  q[3] = r3 / n2;
+}
+
+__global__ void apply_dx_kernel(int nh, const int *var_id, const int *var_size, const int *var_kind, double *val, const double *dx,
+                                const int *flag) {
+  int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= nh)
+    return;
+  if (flag && *flag == 0)
+    return;
+  int id = var_id[h];
+  if (id < 0)
+    return;
+  const double *d = dx + id;
+  double *v = val + (size_t)h * OVP_VAL_STRIDE;
+  int kind = var_kind[h];
+  if (kind == OVP_KIND_VEC || kind == OVP_KIND_LANDMARK) {
+    int s = var_size[h];
+    for (int i = 0; i < s; i++)
+      v[i] += d[i];
+    return;
+  }
+  quat_left_update(v, d);
+  v[4] += d[3];
+  v[5] += d[4];
+  v[6] += d[5];
+  if (kind == OVP_KIND_IMU)
+    for (int i = 0; i < 9; i++)
+      v[7 + i] += d[6 + i];
+}
+
+__global__ void diag_check_kernel(const double *P, int ld, int N, int *flag_out, const int *flag) {
+  if (flag && *flag == 0)
+    return;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N && P[(size_t)i * ld + i] < 0.0)
+    atomicExch(flag_out, 1);
+}
+
+__global__ void gate_kernel(const double *chi2, double thresh, int *flag) {
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    *flag = (thresh < 0.0 || !(chi2[0] > thresh)) ? 1 : 0;
+}
+
+int upload_var_table(Ctx *c) {
+  int nh = (int)c->vars.size();
+  if (nh > c->max_handles)
+    return fail(c, OVP_ERR_CAPACITY, "variable handle capacity %d exceeded", c->max_handles);
+  std::vector<int> id(nh), sz(nh), kd(nh);
+  for (int h = 0; h < nh; h++) {
+    id[h] = c->vars[h].alive ? c->vars[h].id : -1;
+    sz[h] = c->vars[h].size;
+    kd[h] = c->vars[h].kind;
+  }
+  OVP_CUDA(cudaMemcpyAsync(c->d_var_id, id.data(), nh * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(c->d_var_size, sz.data(), nh * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(c->d_var_kind, kd.data(), nh * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  OVP_CUDA(cudaStreamSynchronize(c->stream)); // host vectors go out of scope
+  c->var_table_dirty = false;
+  return OVP_OK;
+}
+
+int sync_host_values(Ctx *c) {
+  if (!c->host_values_stale)
+    return OVP_OK;
+  size_t n = c->vars.size() * OVP_VAL_STRIDE;
+  OVP_CUDA(cudaMemcpyAsync(c->h_val.data(), c->d_val, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
+  c->host_values_stale = false;
+  return OVP_OK;
+}
+
+int push_host_values(Ctx *c, int h) {
+  OVP_CUDA(cudaMemcpyAsync(c->d_val + (size_t)h * OVP_VAL_STRIDE, c->h_val.data() + (size_t)h * OVP_VAL_STRIDE,
+                           OVP_VAL_STRIDE * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(c->d_fej + (size_t)h * OVP_VAL_STRIDE, c->h_fej.data() + (size_t)h * OVP_VAL_STRIDE,
+                           OVP_VAL_STRIDE * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
+  return OVP_OK;
+}
+
+// zero the new rows / cols [N, N+s) of P
+__global__ void zero_band_kernel(double *P, int ld, int N, int s) {
+  int total = (N + s) * s;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    int i = idx % (N + s), j = idx / (N + s);
+    P[(size_t)(N + j) * ld + i] = 0.0;
+    P[(size_t)i * ld + (N + j)] = 0.0;
+  }
+}
+
+int state_append_variable(Ctx *c, Var v, const double *value, const double *fej, int *handle) {
+  if ((int)c->vars.size() >= c->max_handles)
+    return fail(c, OVP_ERR_CAPACITY, "variable handle capacity %d exceeded", c->max_handles);
+  int st = sync_host_values(c);
+  if (st)
+    return st;
+  int h = (int)c->vars.size();
+  c->vars.push_back(v);
+  c->h_val.resize((size_t)(h + 1) * OVP_VAL_STRIDE, 0.0);
+  c->h_fej.resize((size_t)(h + 1) * OVP_VAL_STRIDE, 0.0);
+  for (int i = 0; i < v.nvalue; i++) {
+    c->h_val[(size_t)h * OVP_VAL_STRIDE + i] = value ? value[i] : 0.0;
+    c->h_fej[(size_t)h * OVP_VAL_STRIDE + i] = fej ? fej[i] : (value ? value[i] : 0.0);
+  }
+  c->var_table_dirty = true;
+  *handle = h;
+  return push_host_values(c, h);
+}
+
+int check_status_flags(Ctx *c) {
+  int f[2] = {0, 0};
+  OVP_CUDA(cudaMemcpyAsync(f, c->dflags, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
+  if (f[0] || f[1]) {
+    OVP_CUDA(cudaMemsetAsync(c->dflags, 0, 2 * sizeof(int), c->stream));
+    if (f[1])
+      return fail(c, OVP_ERR_NOT_POSITIVE_DEFINITE, "innovation covariance not positive definite");
+    return fail(c, OVP_ERR_NEGATIVE_DIAGONAL, "covariance has a negative diagonal entry (reference: std::exit, StateHelper.cpp:176-187)");
+  }
+  return OVP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// EKF update core (see ovp_internal.h).  K M^T = M S^-1 M^T is applied as (M L^-T)(M L^-T)^T and dx = (M L^-T)(L^-1 z):
+// algebraically the reference's K = M S^-1, P -= K M^T, dx = K res (StateHelper.cpp:165-171,190).
+// -------------------------------------------------------------------------------------------------------------------
+int ekf_update_core(Ctx *c, const int *d_cols, int nc, MatView HT, int rr, const double *d_z, const double *d_Rdiag, double gate_thresh,
+                    int *d_gate_flag, double *d_chi2, bool apply) {
+  if (rr <= 0 || nc <= 0)
+    return OVP_OK;
+  if (rr > c->wsS.cap || nc > c->Rcap)
+    return fail(c, OVP_ERR_CAPACITY, "ekf_update: system %d x %d exceeds capacity %d", rr, nc, c->Rcap);
+  if (c->var_table_dirty) {
+    int st = upload_var_table(c);
+    if (st)
+      return st;
+  }
+  const int N = c->N;
+  // 1. M = P[:, cols] * HT        (N x rr)
+  {
+    GemmProblem p = make_problem(N, rr, nc, mv(c->dP, c->ldP, 0, nullptr, d_cols), HT, c->dM, c->Nmax);
+    launch_gemm1(c, p);
+  }
+  // 2. S = HT^T * M[cols, :] + R  (lower part)
+  {
+    MatView HTt = HT;
+    HTt.trans ^= 1;
+    GemmProblem p = make_problem(rr, rr, nc, HTt, mv(c->dM, c->Nmax, 0, d_cols, nullptr), c->wsS.S, c->wsS.cap);
+    p.diag_add = d_Rdiag;
+    p.diag_const = 1.0;
+    p.tri = TRI_LOWER;
+    p.b_kfast = 0; // gathered rows: no contiguous direction along k
+    launch_gemm1(c, p);
+  }
+  // 3. S = L L^T, L^-1
+  int st = chol_partial(c, c->wsS, c->wsS.S, c->wsS.cap, rr, rr, 0.0, true);
+  if (st)
+    return st;
+  // 4. Y = M * L^-T
+  {
+    GemmProblem p = make_problem(N, rr, rr, mv(c->dM, c->Nmax), mv(c->wsS.Linv, c->wsS.cap, 1), c->dY, c->Nmax);
+    launch_gemm1(c, p);
+  }
+  // 5. w = L^-1 z ; chi2 = |w|^2 ; gate
+  double *d_w = c->dvec;                 // [0, Rcap)
+  double *d_dx = c->dvec + 2 * c->Rcap;  // [2Rcap, 2Rcap + Nmax)
+  launch_gemv(c, rr, rr, mv(c->wsS.Linv, c->wsS.cap), d_z, d_w);
+  double *chi2 = d_chi2 ? d_chi2 : c->dscal;
+  launch_sumsq(c, d_w, rr, chi2);
+  int *flag = d_gate_flag ? d_gate_flag : (c->dflags + 2);
+  gate_kernel<<<1, 32, 0, c->stream>>>(chi2, gate_thresh, flag);
+  c->launches++;
+  if (!apply)
+    return OVP_OK;
+  // 6. P -= Y Y^T (lower tiles, mirrored)  [skipped on the device when the gate failed]
+  {
+    GemmProblem p = make_problem(N, N, rr, mv(c->dY, c->Nmax), mv(c->dY, c->Nmax, 1), c->dP, c->ldP, -1.0, 1.0);
+    p.tri = TRI_LOWER_MIRROR;
+    launch_gemm1(c, p, flag);
+  }
+  // 7. dx = Y w ; update every variable ; negative-diagonal check
+  launch_gemv(c, N, rr, mv(c->dY, c->Nmax), d_w, d_dx, flag);
+  int nh = (int)c->vars.size();
+  apply_dx_kernel<<<(nh + 127) / 128, 128, 0, c->stream>>>(nh, c->d_var_id, c->d_var_size, c->d_var_kind, c->d_val, d_dx, flag);
+  c->launches++;
+  diag_check_kernel<<<(N + 127) / 128, 128, 0, c->stream>>>(c->dP, c->ldP, N, c->dflags, flag);
+  c->launches++;
+  c->host_values_stale = true;
+  return OVP_OK;
+}
+
+} // namespace ovp

@@ -1,0 +1,413 @@
+// UpdaterMSCKF::update from "features triangulated, plane CPs known" onward (UpdaterMSCKF.cpp:407-828), device side:
+//   feature kernel  : one CTA per tracked feature — Jacobian rows (UpdaterHelper.cpp:195-513) built in shared memory from
+//                     the device-resident clone/calibration values, left-nullspace projection of H_f (UpdaterHelper.cpp:515-546,
+//                     UpdaterPlane.cpp:483-517; 3 Householder reflectors instead of 3*(rows-2) sequential Givens rotations),
+//                     per-feature Mahalanobis gate against P (UpdaterMSCKF.cpp:739-764) and scatter into the stacked system;
+//   gram kernel     : G = [H_x H_cp r]^T [H_x H_cp r] on FP64 tensor cores (split-K, deterministic reduction);
+//   compression     : partial Cholesky of G = the Q-less QR of the stacked system (UpdaterHelper.cpp:548-579,
+//                     UpdaterPlane.cpp:519-552 incl. its "keep the first n rows" semantics), then ekf_update_core.
+#include "jacobian_core.h"
+#include "ovp_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <set>
+
+namespace ovp {
+
+struct FeatArgs {
+  const int *meas_offset;
+  const int *meas_clone;
+  const float *uv;
+  const double *pf;       // 3 per feature (position used for this pass)
+  const int *feat_sel;    // feature indices processed by this launch
+  const int *row_off;     // per selected feature: first row in the stacked system
+  const int *feat_plane_slot; // per feature (global index): slot of its plane in plane_pass[] or -1
+  const int *plane_pass;  // device flags written by the plane updates (1 = passed => feature consumed)
+  const double *val;
+  const double *fej;
+  const int *var_id;
+  int h_calib, h_intr;
+  int do_fej, do_calib_pose, do_calib_intr;
+  int plane_mode;         // 1: add point-on-plane rows, carry H_cp, no per-feature gate
+  int plane_handle;       // >= 0: plane is in the state (cp from val/fej tables); -1: use plane_cp
+  double plane_cp[3];
+  double white_px, white_c;
+  const double *P;
+  int ldP;
+  const int *state2compact;
+  int col_cp, col_res;    // stacked-system columns of H_cp (3) and of the residual
+  double *Hs;
+  int ldHs;
+  const double *chi2_table;
+  int chi2_n;
+  double chi2_mult;
+  int *feat_flag;
+  double *feat_chi2;
+  int lda;   // smem column stride of the feature block (odd)
+  int ldt;   // smem column stride of T / S (odd)
+  int maxcols; // capacity of local columns
+};
+
+__device__ __forceinline__ double warp_sum(double s) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+// Local column layout of the feature block A (col-major, stride lda):
+//   [0,3) H_f | [3, 3+cf) H_x = [extrinsics 6][intrinsics 8][clone_0 6]...[clone_{m-1} 6] | [3+cf, 3+cf+3) H_cp | last: res
+__global__ void __launch_bounds__(128) feature_kernel(FeatArgs a) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x;
+  const int f = a.feat_sel[blockIdx.x];
+  const int m0 = a.meas_offset[f];
+  const int m = a.meas_offset[f + 1] - m0;
+  if (!a.plane_mode) {
+    int slot = a.feat_plane_slot[f];
+    if (slot >= 0 && a.plane_pass[slot] == 1) { // consumed by a successful plane update (UpdaterMSCKF.cpp:640-644,659)
+      if (tid == 0) {
+        a.feat_flag[f] = 2;
+        a.feat_chi2[f] = nan("");
+      }
+      return;
+    }
+  }
+  const int ncal = (a.do_calib_pose ? 6 : 0) + (a.do_calib_intr ? 8 : 0);
+  const int cf = ncal + 6 * m;
+  const int rows = a.plane_mode ? 3 * m : 2 * m;
+  const int ncols = 3 + cf + 3 + 1;
+  const int c_cp = 3 + cf, c_res = 3 + cf + 3;
+  const int lda = a.lda;
+  double *A = sm;                                   // lda * maxcols
+  double *T = A + (size_t)lda * a.maxcols;          // ldt * (maxcols)   (gate only)
+  double *S = T + (size_t)a.ldt * a.maxcols;        // ldt * ldt         (gate only)
+  double *vbuf = a.plane_mode ? T : S + (size_t)a.ldt * a.ldt; // reflector (rows)
+  __shared__ int lsid[14 + 6 * 64];
+  __shared__ double s_beta, s_chi2;
+  __shared__ int s_ok;
+
+  for (int idx = tid; idx < lda * ncols; idx += 128)
+    A[idx] = 0.0;
+  __syncthreads();
+
+  // ---- Jacobian rows: one thread per measurement ----
+  if (tid < m) {
+    const int k = tid;
+    const int hcl = a.meas_clone[m0 + k];
+    const double *vc = a.val + (size_t)hcl * OVP_VAL_STRIDE;
+    const double *fc = a.fej + (size_t)hcl * OVP_VAL_STRIDE;
+    const double *vcal = a.val + (size_t)a.h_calib * OVP_VAL_STRIDE;
+    const double *cam = a.val + (size_t)a.h_intr * OVP_VAL_STRIDE;
+    double R_C[9];
+    quat_to_rot(vcal, R_C);
+    const double *pf = a.pf + 3 * (size_t)f;
+    double res[2], Hf[6], Hcl[12], Hcal[12], Hin[16];
+    bearing_rows(vc, vc + 4, fc, fc + 4, a.do_fej, R_C, vcal + 4, cam, pf, pf, a.uv[2 * (m0 + k)], a.uv[2 * (m0 + k) + 1], a.white_px,
+                 res, Hf, Hcl, Hcal, Hin);
+    for (int i = 0; i < 2; i++) {
+      int r = 2 * k + i;
+      for (int j = 0; j < 3; j++)
+        A[(size_t)j * lda + r] = Hf[3 * i + j];
+      int cb = 3;
+      if (a.do_calib_pose) {
+        for (int j = 0; j < 6; j++)
+          A[(size_t)(cb + j) * lda + r] = Hcal[6 * i + j];
+        cb += 6;
+      }
+      if (a.do_calib_intr) {
+        for (int j = 0; j < 8; j++)
+          A[(size_t)(cb + j) * lda + r] = Hin[8 * i + j];
+        cb += 8;
+      }
+      for (int j = 0; j < 6; j++)
+        A[(size_t)(cb + 6 * k + j) * lda + r] = Hcl[6 * i + j];
+      A[(size_t)c_res * lda + r] = res[i];
+    }
+    const int idc = a.var_id[hcl];
+    for (int j = 0; j < 6; j++)
+      lsid[ncal + 6 * k + j] = idc + j;
+    if (a.plane_mode) {
+      const double *cp, *cpf;
+      if (a.plane_handle >= 0) {
+        cp = a.val + (size_t)a.plane_handle * OVP_VAL_STRIDE;
+        cpf = a.fej + (size_t)a.plane_handle * OVP_VAL_STRIDE;
+      } else {
+        cp = a.plane_cp;
+        cpf = a.plane_cp;
+      }
+      double pr, pHf[3], pHcp[3];
+      plane_row(pf, pf, cp, cpf, a.do_fej, a.white_c, pr, pHf, pHcp);
+      int r = 2 * m + k;
+      for (int j = 0; j < 3; j++) {
+        A[(size_t)j * lda + r] = pHf[j];
+        A[(size_t)(c_cp + j) * lda + r] = pHcp[j];
+      }
+      A[(size_t)c_res * lda + r] = pr;
+    }
+  }
+  if (tid == 0) {
+    int cb = 0;
+    if (a.do_calib_pose) {
+      int idb = a.var_id[a.h_calib];
+      for (int j = 0; j < 6; j++)
+        lsid[cb + j] = idb + j;
+      cb += 6;
+    }
+    if (a.do_calib_intr) {
+      int idb = a.var_id[a.h_intr];
+      for (int j = 0; j < 8; j++)
+        lsid[cb + j] = idb + j;
+    }
+  }
+  __syncthreads();
+
+  // ---- left-nullspace projection of H_f: 3 Householder reflectors applied to [H_f H_x H_cp res] ----
+  for (int j = 0; j < 3; j++) {
+    if (tid < 32) {
+      double s = 0.0;
+      for (int i = j + tid; i < rows; i += 32) {
+        double v = A[(size_t)j * lda + i];
+        s += v * v;
+      }
+      s = warp_sum(s);
+      double x0 = A[(size_t)j * lda + j];
+      double nrm = sqrt(s);
+      double alpha = (x0 > 0.0) ? -nrm : nrm;
+      double v0 = x0 - alpha;
+      // v = [v0; x(j+1:)],  beta = 2 / (v^T v) = -1 / (alpha * v0)
+      double vtv = s - x0 * x0 + v0 * v0;
+      for (int i = j + tid; i < rows; i += 32)
+        vbuf[i] = (i == j) ? v0 : A[(size_t)j * lda + i];
+      if (tid == 0)
+        s_beta = (vtv > 0.0 && nrm > 0.0) ? 2.0 / vtv : 0.0;
+    }
+    __syncthreads();
+    const double beta = s_beta;
+    for (int cidx = j + 1 + tid; cidx < ncols; cidx += 128) {
+      double *col = A + (size_t)cidx * lda;
+      double s = 0.0;
+      for (int i = j; i < rows; i++)
+        s += vbuf[i] * col[i];
+      s *= beta;
+      if (s != 0.0)
+        for (int i = j; i < rows; i++)
+          col[i] -= s * vbuf[i];
+    }
+    __syncthreads();
+  }
+  const int ro = rows - 3; // projected rows live in A[3:rows, :]
+
+  int accept = 1;
+  if (!a.plane_mode) {
+    // ---- chi2 gate: S = H_o P_marg H_o^T + I, chi2 = r^T S^-1 r (UpdaterMSCKF.cpp:739-742) ----
+    const int ldt = a.ldt;
+    // T = H_o * P_marg   (ro x cf): work item = (column b, row chunk of 8)
+    const int nchunk = (ro + 7) / 8;
+    for (int w = tid; w < cf * nchunk; w += 128) {
+      int b = w % cf, ch = w / cf;
+      int i0 = ch * 8;
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const double *Pc = a.P + (size_t)lsid[b] * a.ldP;
+      for (int k = 0; k < cf; k++) {
+        double p = Pc[lsid[k]];
+        const double *hc = A + (size_t)(3 + k) * lda + 3 + i0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (i0 + i < ro)
+            acc[i] += hc[i] * p;
+      }
+      for (int i = 0; i < 8; i++)
+        if (i0 + i < ro)
+          T[(size_t)b * ldt + i0 + i] = acc[i];
+    }
+    __syncthreads();
+    for (int w = tid; w < ro * ro; w += 128) {
+      int i = w % ro, jj = w / ro;
+      if (i < jj)
+        continue;
+      double s = (i == jj) ? 1.0 : 0.0;
+      for (int b = 0; b < cf; b++)
+        s += T[(size_t)b * ldt + i] * A[(size_t)(3 + b) * lda + 3 + jj];
+      S[(size_t)jj * ldt + i] = s;
+    }
+    __syncthreads();
+    // in-place Cholesky of S (lower), then y = L^-1 r
+    if (tid == 0)
+      s_ok = 1;
+    for (int jj = 0; jj < ro; jj++) {
+      __syncthreads();
+      if (tid == 0) {
+        double d = S[(size_t)jj * ldt + jj];
+        if (!(d > 0.0)) {
+          s_ok = 0;
+          d = 1.0;
+        }
+        S[(size_t)jj * ldt + jj] = sqrt(d);
+      }
+      __syncthreads();
+      double piv = S[(size_t)jj * ldt + jj];
+      for (int i = jj + 1 + tid; i < ro; i += 128)
+        S[(size_t)jj * ldt + i] /= piv;
+      __syncthreads();
+      int nrem = ro - 1 - jj;
+      for (int w = tid; w < nrem * nrem; w += 128) {
+        int i = jj + 1 + w % nrem, k = jj + 1 + w / nrem;
+        if (i >= k)
+          S[(size_t)k * ldt + i] -= S[(size_t)jj * ldt + i] * S[(size_t)jj * ldt + k];
+      }
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // forward substitution by one warp: y_i = (r_i - sum_k L_ik y_k) / L_ii ; y stored in vbuf
+      double chi = 0.0;
+      for (int i = 0; i < ro; i++) {
+        double s = 0.0;
+        for (int k = tid; k < i; k += 32)
+          s += S[(size_t)k * ldt + i] * vbuf[k];
+        s = warp_sum(s);
+        double y = (A[(size_t)c_res * lda + 3 + i] - s) / S[(size_t)i * ldt + i];
+        if (tid == 0)
+          vbuf[i] = y;
+        __syncwarp();
+        chi += y * y;
+      }
+      if (tid == 0)
+        s_chi2 = chi;
+    }
+    __syncthreads();
+    double thr = a.chi2_mult * a.chi2_table[ro < a.chi2_n ? ro : a.chi2_n - 1];
+    accept = (s_ok && !(s_chi2 > thr)) ? 1 : 0;
+    if (tid == 0) {
+      a.feat_flag[f] = accept;
+      a.feat_chi2[f] = s_chi2;
+    }
+  }
+  if (!accept)
+    return;
+  // ---- scatter the projected block into the stacked system ----
+  const int r0 = a.row_off[blockIdx.x];
+  for (int w = tid; w < cf * ro; w += 128) {
+    int i = w % ro, b = w / ro;
+    int gc = a.state2compact[lsid[b]];
+    a.Hs[(size_t)gc * a.ldHs + r0 + i] = A[(size_t)(3 + b) * lda + 3 + i];
+  }
+  if (a.plane_mode)
+    for (int w = tid; w < 3 * ro; w += 128) {
+      int i = w % ro, b = w / ro;
+      a.Hs[(size_t)(a.col_cp + b) * a.ldHs + r0 + i] = A[(size_t)(c_cp + b) * lda + 3 + i];
+    }
+  for (int i = tid; i < ro; i += 128)
+    a.Hs[(size_t)a.col_res * a.ldHs + r0 + i] = A[(size_t)c_res * lda + 3 + i];
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// Gram kernel: partial[z] = Hs[k-chunk z, :]^T Hs[k-chunk z, :]  (lower 64x64 tiles), FP64 DMMA
+// -------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gram_kernel(const double *Hs, int ld, int rows, int nc, int kchunk, double *part, int ldp) {
+  const int tm = blockIdx.y, tn = blockIdx.x;
+  if (tm < tn)
+    return;
+  __shared__ double As[OVP_GK][OVP_GLD];
+  __shared__ double Bs[OVP_GK][OVP_GLD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int m0 = tm * OVP_GT, n0 = tn * OVP_GT;
+  const int kbeg = blockIdx.z * kchunk;
+  const int kend = min(rows, kbeg + kchunk);
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      acc[i][j][0] = acc[i][j][1] = 0.0;
+  for (int k0 = kbeg; k0 < kend; k0 += OVP_GK) {
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      int e = tid + t * 128;
+      int kk = e & 15, ii = e >> 4;
+      int gk = k0 + kk;
+      int gi = m0 + ii, gj = n0 + ii;
+      As[kk][ii] = (gk < kend && gi < nc) ? Hs[(size_t)gi * ld + gk] : 0.0;
+      Bs[kk][ii] = (gk < kend && gj < nc) ? Hs[(size_t)gj * ld + gk] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < OVP_GK; kk += 4) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        av[i] = As[kk + (lane & 3)][wm * 32 + i * 8 + (lane >> 2)];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        bv[j] = Bs[kk + (lane & 3)][wn * 32 + j * 8 + (lane >> 2)];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          dmma_m8n8k4(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+    }
+    __syncthreads();
+  }
+  double *out = part + (size_t)blockIdx.z * ldp * ldp;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        int gi = m0 + wm * 32 + i * 8 + (lane >> 2);
+        int gj = n0 + wn * 32 + j * 8 + (lane & 3) * 2 + h;
+        if (gi < nc && gj < nc)
+          out[(size_t)gj * ldp + gi] = acc[i][j][h];
+      }
+}
+
+// G[i,j] (lower, i >= j) = sum_z part[z][i,j] in fixed order (deterministic)
+__global__ void gram_reduce_kernel(const double *part, int ldp, int nsplit, int nc, double *G, int ldg) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nc * nc)
+    return;
+  int i = idx % nc, j = idx / nc;
+  if (i < j) { // strictly-upper part must read as zero: the factor is later used as a dense H^T operand
+    G[(size_t)j * ldg + i] = 0.0;
+    return;
+  }
+  double s = 0.0;
+  for (int z = 0; z < nsplit; z++)
+    s += part[(size_t)z * ldp * ldp + (size_t)j * ldp + i];
+  G[(size_t)j * ldg + i] = s;
+}
+
+__global__ void extract_row_kernel(const double *A, int ld, int row, int n, double *out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n)
+    out[j] = A[(size_t)j * ld + row];
+}
+
+// Gram + reduce of the stacked system Hs (rows x nc) into ws.S (lower)
+static int gram_of_stacked(Ctx *c, int rows, int nc, int ldHs) {
+  int tiles = (nc + OVP_GT - 1) / OVP_GT;
+  int ldp = tiles * OVP_GT;
+  int ntile_lower = tiles * (tiles + 1) / 2;
+  int nsplit = std::max(1, std::min((rows + 255) / 256, std::max(1, (148 * 4) / std::max(1, ntile_lower))));
+  size_t need = (size_t)nsplit * ldp * ldp;
+  if (need > c->part_elems) {
+    nsplit = (int)(c->part_elems / ((size_t)ldp * ldp));
+    if (nsplit < 1)
+      return fail(c, OVP_ERR_CAPACITY, "gram: partial buffer too small");
+  }
+  int kchunk = ((rows + nsplit - 1) / nsplit + OVP_GK - 1) / OVP_GK * OVP_GK;
+  nsplit = (rows + kchunk - 1) / kchunk;
+  dim3 grid(tiles, tiles, nsplit);
+  prof_begin(c, PROF_GRAM, (double)nc * nc * rows); // algorithmic flops of the symmetric product: 2 * n^2 * r / 2
+  gram_kernel<<<grid, 128, 0, c->stream>>>(c->dHs, ldHs, rows, nc, kchunk, c->dPart, ldp);
+  c->launches++;
+  prof_end(c);
+  gram_reduce_kernel<<<(nc * nc + 255) / 256, 256, 0, c->stream>>>(c->dPart, ldp, nsplit, nc, c->wsG.S, c->wsG.cap);
+  c->launches++;
+  return OVP_OK;
+}
+
+#include "features_host.inc"

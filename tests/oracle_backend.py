@@ -1,0 +1,273 @@
+"""TEST INFRASTRUCTURE: ctypes mirror of oracle/liboracle.so with the same method names as ov_plane_b200.api.Context, so a
+parity test feeds one scenario to both and compares.  Never imported by the product package."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_ODIR = os.path.join(_ROOT, "oracle")
+_LIB = os.path.join(_ODIR, "liboracle.so")
+
+KIND_VEC, KIND_POSE, KIND_IMU, KIND_LANDMARK = 0, 1, 2, 3
+
+
+def _load():
+    srcs = [os.path.join(_ODIR, "oracle.hpp"), os.path.join(_ODIR, "oracle_capi.cpp")]
+    if (not os.path.exists(_LIB)) or any(os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
+        subprocess.check_call(["make", "-C", _ODIR, "CXX=g++"])
+    lib = C.CDLL(_LIB)
+    lib.orc_create.restype = C.c_void_p
+    lib.orc_last_error.restype = C.c_char_p
+    lib.orc_get_timestamp.restype = C.c_double
+    return lib
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _load()
+    return _lib
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _cm(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class OracleContext(object):
+    def __init__(self, o, **_unused):
+        self.lib = lib()
+        self.h = C.c_void_p(self.lib.orc_create(int(o["do_fej"]), int(o["use_rk4_integration"]), int(o["imu_avg"]),
+                                                int(o["do_calib_camera_pose"]), int(o["do_calib_camera_intrinsics"]),
+                                                int(o["do_calib_camera_timeoffset"]), int(o["max_clone_size"]),
+                                                C.c_double(o["sigma_constraint"]), C.c_double(o["const_init_multi"]),
+                                                C.c_double(o["const_init_chi2"])))
+        self.lib.orc_set_plane_merge_options(self.h, C.c_double(o["sigma_plane_merge"]), C.c_double(o["plane_merge_chi2"]),
+                                             C.c_double(o["plane_merge_deg_max"]))
+
+    def close(self):
+        if self.h:
+            self.lib.orc_destroy(self.h)
+            self.h = None
+
+    def _ck(self, st):
+        if st != 0:
+            raise OracleError("oracle status %d: %s" % (st, self.lib.orc_last_error(self.h).decode()))
+
+    def set_chi2_table(self, q):
+        q = _f64(q)
+        self.lib.orc_set_chi2_table(self.h, _p(q), len(q))
+
+    def cov_rows(self):
+        return self.lib.orc_cov_rows(self.h)
+
+    def cov(self):
+        n = self.cov_rows()
+        out = np.zeros((n, n), order="F")
+        self.lib.orc_get_cov(self.h, _p(out))
+        return out
+
+    def cov_upload(self, P):
+        P = _cm(P)
+        self._ck(self.lib.orc_set_cov(self.h, _p(P), P.shape[0]))
+
+    def handle_imu(self):
+        return self.lib.orc_handle_imu(self.h)
+
+    def handle_dt(self):
+        return self.lib.orc_handle_dt(self.h)
+
+    def handle_calib(self):
+        return self.lib.orc_handle_calib(self.h)
+
+    def handle_intrinsics(self):
+        return self.lib.orc_handle_intr(self.h)
+
+    def var_id(self, h):
+        return self.lib.orc_var_id(self.h, h)
+
+    def var_size(self, h):
+        return self.lib.orc_var_size(self.h, h)
+
+    def var_set(self, h, value, fej=None):
+        v = _f64(value)
+        f = _f64(fej) if fej is not None else None
+        self.lib.orc_var_set(self.h, h, _p(v), _p(f))
+
+    def var_get(self, h):
+        n = self.lib.orc_var_nvalue(self.h, h)
+        v, f = np.zeros(n), np.zeros(n)
+        self.lib.orc_var_get(self.h, h, _p(v), _p(f))
+        return v, f
+
+    def variable_order(self):
+        n = self.lib.orc_num_variables(self.h)
+        o = np.zeros(n, dtype=np.int32)
+        self.lib.orc_variable_order(self.h, _p(o))
+        return o.tolist()
+
+    def set_timestamp(self, t):
+        self.lib.orc_set_timestamp(self.h, C.c_double(t))
+
+    def get_timestamp(self):
+        return self.lib.orc_get_timestamp(self.h)
+
+    def add_clone_raw(self, t, v, f):
+        v, f = _f64(v), _f64(f)
+        return self.lib.orc_add_clone_raw(self.h, C.c_double(t), _p(v), _p(f))
+
+    def add_plane_raw(self, pid, v, f):
+        v, f = _f64(v), _f64(f)
+        return self.lib.orc_add_plane_raw(self.h, C.c_longlong(int(pid)), _p(v), _p(f))
+
+    def add_slam_raw(self, fid, v, f):
+        v, f = _f64(v), _f64(f)
+        return self.lib.orc_add_slam_raw(self.h, C.c_longlong(int(fid)), _p(v), _p(f))
+
+    def plane_handle(self, pid):
+        return self.lib.orc_plane_handle(self.h, C.c_longlong(int(pid)))
+
+    # ---- StateHelper ----
+    def set_initial_covariance(self, cov, handles):
+        cov, hs = _cm(cov), _i32(handles)
+        self._ck(self.lib.orc_set_initial_covariance(self.h, _p(cov), cov.shape[0], _p(hs), len(hs)))
+
+    def get_marginal_covariance(self, handles):
+        hs = _i32(handles)
+        n = sum(self.var_size(int(h)) for h in hs)
+        out = np.zeros((n, n), order="F")
+        self._ck(self.lib.orc_get_marginal_covariance(self.h, _p(hs), len(hs), _p(out)))
+        return out
+
+    def ekf_propagation(self, new_handles, old_handles, Phi, Q):
+        nh, oh, Phi, Q = _i32(new_handles), _i32(old_handles), _cm(Phi), _cm(Q)
+        self._ck(self.lib.orc_ekf_propagation(self.h, _p(nh), len(nh), _p(oh), len(oh), _p(Phi), Phi.shape[0], Phi.shape[1], _p(Q)))
+
+    def ekf_update(self, handles, H, res, Rdiag=None):
+        hs, H, res = _i32(handles), _cm(H), _f64(res)
+        R = _f64(Rdiag) if Rdiag is not None else None
+        self._ck(self.lib.orc_ekf_update(self.h, _p(hs), len(hs), _p(H), H.shape[0], _p(res), _p(R)))
+
+    def marginalize(self, h):
+        self._ck(self.lib.orc_marginalize(self.h, h))
+
+    def marginalize_old_clone(self):
+        self._ck(self.lib.orc_marginalize_old_clone(self.h))
+
+    def augment_clone(self, t, last_w):
+        w, nh = _f64(last_w), C.c_int(-1)
+        self._ck(self.lib.orc_augment_clone(self.h, C.c_double(t), _p(w), C.byref(nh)))
+        return nh.value
+
+    def initialize(self, kind, value, fej, tag, handles, H_R, H_L, res, sigma2, chi2_mult, do_update=True):
+        v, f, hs = _f64(value), _f64(fej), _i32(handles)
+        H_R, H_L, res = _cm(H_R), _cm(H_L), _f64(res)
+        acc, nh = C.c_int(0), C.c_int(-1)
+        self._ck(self.lib.orc_initialize(self.h, kind, len(v), _p(v), _p(f), C.c_longlong(int(tag)), _p(hs), len(hs), _p(H_R), _p(H_L),
+                                         _p(res), H_R.shape[0], C.c_double(sigma2), C.c_double(chi2_mult), int(do_update), C.byref(acc),
+                                         C.byref(nh)))
+        return bool(acc.value), nh.value
+
+    def merge_planes_and_marginalize(self, feat2plane, plane2oldplane):
+        ff = np.array(list(feat2plane.keys()), dtype=np.int64)
+        fp = np.array(list(feat2plane.values()), dtype=np.int64)
+        mn, mo = [], []
+        for k, olds in plane2oldplane.items():
+            for o in olds:
+                mn.append(k)
+                mo.append(o)
+        mn, mo = np.array(mn, dtype=np.int64), np.array(mo, dtype=np.int64)
+        self._ck(self.lib.orc_merge_planes_and_marginalize(self.h, _p(ff), _p(fp), len(ff), _p(mn), _p(mo), len(mn)))
+
+    # ---- helpers ----
+    def feature_jacobian_full(self, clone_handles, uv, p_FinG, p_FinG_fej, planeid, cp, cp_fej, sigma_px, sigma_c):
+        ch, uv = _i32(clone_handles), np.ascontiguousarray(uv, dtype=np.float32)
+        m = len(ch)
+        rows_cap, cols_cap = 3 * m + 1, 14 + 6 * m + 3
+        Hf, Hx, res = np.zeros(rows_cap * 6), np.zeros(rows_cap * cols_cap), np.zeros(rows_cap)
+        xo = np.zeros(m + 3, dtype=np.int32)
+        hfc, hxc, rows, xon = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        pf, pff = _f64(p_FinG), _f64(p_FinG_fej)
+        cpv = _f64(cp) if cp is not None else np.zeros(3)
+        cpf = _f64(cp_fej) if cp_fej is not None else np.zeros(3)
+        self._ck(self.lib.orc_feature_jacobian_full(self.h, m, _p(ch), _p(uv), _p(pf), _p(pff), C.c_longlong(int(planeid)), _p(cpv), _p(cpf),
+                                                    C.c_double(sigma_px), C.c_double(sigma_c), _p(Hf), C.byref(hfc), _p(Hx), C.byref(hxc),
+                                                    _p(res), C.byref(rows), _p(xo), C.byref(xon)))
+        r = rows.value
+        return (Hf[:r * hfc.value].reshape((r, hfc.value), order="F").copy(), Hx[:r * hxc.value].reshape((r, hxc.value), order="F").copy(),
+                res[:r].copy(), xo[:xon.value].tolist())
+
+    def nullspace_project_inplace(self, H_f, H_x, res, H_cp=None):
+        H_f, H_x, res = _cm(H_f).copy(order="F"), _cm(H_x).copy(order="F"), _f64(res).copy()
+        rows, ro = H_f.shape[0], C.c_int()
+        if H_cp is None:
+            self.lib.orc_nullspace_project_inplace(_p(H_f), H_f.shape[1], _p(H_x), H_x.shape[1], _p(res), rows, C.byref(ro))
+            r = ro.value
+            return H_x.ravel(order="F")[:r * H_x.shape[1]].reshape((r, H_x.shape[1]), order="F").copy(), res[:r].copy()
+        H_cp = _cm(H_cp).copy(order="F")
+        self.lib.orc_plane_nullspace_project_inplace(_p(H_f), H_f.shape[1], _p(H_x), H_x.shape[1], _p(H_cp), _p(res), rows, C.byref(ro))
+        r = ro.value
+        return (H_x.ravel(order="F")[:r * H_x.shape[1]].reshape((r, H_x.shape[1]), order="F").copy(),
+                H_cp.ravel(order="F")[:r * 3].reshape((r, 3), order="F").copy(), res[:r].copy())
+
+    def measurement_compress_inplace(self, H_x, res, H_cp=None):
+        H_x, res = _cm(H_x).copy(order="F"), _f64(res).copy()
+        rows, cols, ro = H_x.shape[0], H_x.shape[1], C.c_int()
+        if H_cp is None:
+            self.lib.orc_measurement_compress_inplace(_p(H_x), cols, _p(res), rows, C.byref(ro))
+            r = ro.value
+            return H_x.ravel(order="F")[:r * cols].reshape((r, cols), order="F").copy(), res[:r].copy()
+        H_cp = _cm(H_cp).copy(order="F")
+        self.lib.orc_plane_measurement_compress_inplace(_p(H_x), cols, _p(H_cp), _p(res), rows, C.byref(ro))
+        r = ro.value
+        return (H_x.ravel(order="F")[:r * cols].reshape((r, cols), order="F").copy(), H_cp.ravel(order="F")[:r * 3].reshape((r, 3), order="F").copy(),
+                res[:r].copy())
+
+    # ---- UpdaterMSCKF ----
+    def msckf_update(self, b, sigma_pix=1.0, chi2_mult=1.0, timers=None):
+        F, npl = int(b["F"]), len(b["plane_ids"])
+        fs, fc = np.zeros(F, dtype=np.int32), np.zeros(F)
+        ps, pc = np.zeros(max(1, npl), dtype=np.int32), np.zeros(max(1, npl))
+        hx, hxn = np.zeros(4096, dtype=np.int32), C.c_int(0)
+        t4 = np.zeros(4)
+        arrs = [np.ascontiguousarray(b[k]) for k in ("meas_offset", "meas_clone", "uv", "p_FinG", "p_FinG_original", "featid", "planeid",
+                                                      "plane_ids", "plane_cp")]
+        self._ck(self.lib.orc_msckf_update(self.h, F, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(arrs[4]), _p(arrs[5]), _p(arrs[6]),
+                                           npl, _p(arrs[7]), _p(arrs[8]), C.c_double(sigma_pix), C.c_double(chi2_mult), _p(fs), _p(fc), _p(ps),
+                                           _p(pc), _p(hx), C.byref(hxn), _p(t4)))
+        if timers is not None:
+            timers[:] = t4
+        return dict(feat_status=fs, feat_chi2=fc, plane_status=ps[:npl], plane_chi2=pc[:npl], hx_order=hx[:hxn.value].tolist())
+
+    # ---- Propagator ----
+    def propagator_set_noise(self, sigma_w, sigma_wb, sigma_a, sigma_ab, gravity_mag=9.81):
+        self.lib.orc_prop_set(self.h, C.c_double(sigma_w), C.c_double(sigma_wb), C.c_double(sigma_a), C.c_double(sigma_ab),
+                              C.c_double(gravity_mag))
+
+    def feed_imu(self, t, wm, am):
+        w, a = _f64(wm), _f64(am)
+        self.lib.orc_prop_feed_imu(self.h, C.c_double(t), _p(w), _p(a))
+
+    def propagate_and_clone(self, t):
+        Phi, Q, nh = np.zeros((15, 15), order="F"), np.zeros((15, 15), order="F"), C.c_int(-1)
+        self._ck(self.lib.orc_prop_propagate_and_clone(self.h, C.c_double(t), _p(Phi), _p(Q), C.byref(nh)))
+        return nh.value, Phi, Q

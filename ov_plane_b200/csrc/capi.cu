@@ -720,7 +720,6 @@ int ovp_ekf_propagation(ovp_ctx *h, const int *new_h, int kn, const int *old_h, 
   // Phi_Cov_PhiT = Qsym + Phi * Cov_PhiT[old rows, :]
   {
     GemmProblem p = make_problem(phi_rows, phi_rows, phi_cols, mv(dPhi, phi_rows), mv(c->dM, c->Nmax, 0, c->dcols, nullptr), dQ, phi_rows, 1.0, 1.0);
-    p.b_kfast = 0;
     launch_gemm1(c, p);
   }
   prop_writeback_kernel<<<std::min(148 * 4, (N * phi_rows + 255) / 256), 256, 0, c->stream>>>(c->dP, c->ldP, N, start, phi_rows, c->dM, c->Nmax,

@@ -86,7 +86,6 @@ static int init_invertible_core(Ctx *c, int kind, int s, const double *value, co
     Hx.trans ^= 1;
     GemmProblem p = make_problem(s, s, n, Hx, mv(c->dM, c->Nmax, 0, d_cols, nullptr), dMm, s);
     p.diag_const = sigma2;
-    p.b_kfast = 0;
     launch_gemm1(c, p);
   }
   // bring the s x s pieces to the host: H_finit (upper-triangular top of H_L), Mm, resinit

@@ -104,6 +104,7 @@ int sync_host_values(Ctx *c) {
   size_t n = c->vars.size() * OVP_VAL_STRIDE;
   OVP_CUDA(cudaMemcpyAsync(c->h_val.data(), c->d_val, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   OVP_CUDA(cudaStreamSynchronize(c->stream));
+  c->d2h_bytes += (int64_t)(n * sizeof(double));
   c->host_values_stale = false;
   return OVP_OK;
 }
@@ -188,7 +189,6 @@ int ekf_update_core(Ctx *c, const int *d_cols, int nc, MatView HT, int rr, const
     p.diag_add = d_Rdiag;
     p.diag_const = 1.0;
     p.tri = TRI_LOWER;
-    p.b_kfast = 0; // gathered rows: no contiguous direction along k
     launch_gemm1(c, p);
   }
   // 3. S = L L^T, L^-1

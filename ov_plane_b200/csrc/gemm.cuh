@@ -2,6 +2,11 @@
 // M = P[:,ids] H^T, S = H M[ids,:] + R, the Cholesky trailing updates, the triangular-inverse merges, Y = M L^-T and
 // P -= Y Y^T (StateHelper.cpp:142-171 restructured).  tcgen05 has no f64 kind, and the path needs fp64
 // (DESIGN.md "precision"), so the legacy-shaped DMMA instruction is the tensor-core instruction available for it.
+//
+// Operands are strided views (element (i,k) = p[i*si + K(k)*sk], optional gather K(k) = kidx[k] along the contraction
+// dimension) so that transposes and the P[:, ids] / M[ids, :] gathers of EKFUpdate need no copies and no divergent code:
+// the tile loaders are straight-line, all global loads of a k-step are issued before any is consumed, and the next k-step
+// is prefetched into registers while the current one is in the tensor pipe.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -14,7 +19,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
                : "d"(a), "d"(b));
 }
 
-// Logical matrix view: element (i,j) = p[row(i) + col(j)*ld] (after optional transpose), with optional gather indices.
+// Host-side logical matrix view: element (i,j) = p[row(i) + col(j)*ld] (after optional transpose), optional gather indices.
 struct MatView {
   const double *p;
   int ld;
@@ -42,13 +47,20 @@ inline MatView mv(const double *p, int ld, int trans = 0, const int *ridx = null
   return v;
 }
 
+// Device-side strided operand: element (x, k) = p[x * sx + K(k) * sk]   (x = row of A or column of B)
+struct SView {
+  const double *p;
+  long long sx, sk;
+  const int *kidx;
+};
+
 enum { TRI_FULL = 0, TRI_LOWER = 1, TRI_LOWER_MIRROR = 2 };
 
 // C[i + j*ldc] = alpha * sum_k A(i,k) B(k,j) + beta * C + (i==j ? diag_add[i] or diag_const : 0)
 struct GemmProblem {
   int M, N, K;
-  MatView A; // M x K
-  MatView B; // K x N
+  SView A; // M x K
+  SView B; // K x N (x = column j)
   double *C;
   int ldc;
   double alpha, beta;
@@ -69,7 +81,42 @@ struct GemmBatch {
 #define OVP_GK 16  // k step
 #define OVP_GLD 68 // smem leading dim (68 mod 16 == 4: conflict-free DMMA fragment reads)
 
-__global__ void __launch_bounds__(128) gemm_f64_kernel(GemmBatch batch) {
+template <bool GATHER>
+__device__ __forceinline__ void load_tile_regs(double (&r)[8], const SView &v, int x0, int X, int k0, int K, int kfast, int tid) {
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    int xx, kk;
+    if (kfast) {
+      kk = tid & 15;
+      xx = (tid >> 4) + 8 * t;
+    } else {
+      xx = tid & 63;
+      kk = (tid >> 6) + 2 * t;
+    }
+    int gx = x0 + xx, gk = k0 + kk;
+    bool ok = (gx < X) && (gk < K);
+    long long kphys = gk;
+    if (GATHER)
+      kphys = ok ? (long long)v.kidx[gk] : 0;
+    r[t] = ok ? v.p[(long long)gx * v.sx + kphys * v.sk] : 0.0;
+  }
+}
+__device__ __forceinline__ void store_tile_smem(const double (&r)[8], double (*sm)[OVP_GLD], int kfast, int tid) {
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    int xx, kk;
+    if (kfast) {
+      kk = tid & 15;
+      xx = (tid >> 4) + 8 * t;
+    } else {
+      xx = tid & 63;
+      kk = (tid >> 6) + 2 * t;
+    }
+    sm[kk][xx] = r[t];
+  }
+}
+
+template <bool GA, bool GB> __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmBatch batch) {
   if (batch.flag && *batch.flag == 0)
     return;
   const GemmProblem &pb = batch.p[blockIdx.z];
@@ -84,43 +131,26 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmBatch batch) {
   const int lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;
   const int m0 = tm * OVP_GT, n0 = tn * OVP_GT;
+  const int M = pb.M, N = pb.N, K = pb.K;
+  const SView va = pb.A, vb = pb.B;
+  const int akf = pb.a_kfast, bkf = pb.b_kfast;
   double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++)
       acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  for (int k0 = 0; k0 < pb.K; k0 += OVP_GK) {
-#pragma unroll
-    for (int t = 0; t < 8; t++) {
-      int e = tid + t * 128;
-      int ii, kk;
-      if (pb.a_kfast) {
-        kk = e & 15;
-        ii = e >> 4;
-      } else {
-        ii = e & 63;
-        kk = e >> 6;
-      }
-      int gi = m0 + ii, gk = k0 + kk;
-      As[kk][ii] = (gi < pb.M && gk < pb.K) ? pb.A.at(gi, gk) : 0.0;
-    }
-#pragma unroll
-    for (int t = 0; t < 8; t++) {
-      int e = tid + t * 128;
-      int jj, kk;
-      if (pb.b_kfast) {
-        kk = e & 15;
-        jj = e >> 4;
-      } else {
-        jj = e & 63;
-        kk = e >> 6;
-      }
-      int gj = n0 + jj, gk = k0 + kk;
-      Bs[kk][jj] = (gj < pb.N && gk < pb.K) ? pb.B.at(gk, gj) : 0.0;
-    }
+  double ra[8], rb[8];
+  load_tile_regs<GA>(ra, va, m0, M, 0, K, akf, tid);
+  load_tile_regs<GB>(rb, vb, n0, N, 0, K, bkf, tid);
+  for (int k0 = 0; k0 < K; k0 += OVP_GK) {
+    store_tile_smem(ra, As, akf, tid);
+    store_tile_smem(rb, Bs, bkf, tid);
     __syncthreads();
+    if (k0 + OVP_GK < K) { // prefetch the next k-step while this one is in the tensor pipe
+      load_tile_regs<GA>(ra, va, m0, M, k0 + OVP_GK, K, akf, tid);
+      load_tile_regs<GB>(rb, vb, n0, N, k0 + OVP_GK, K, bkf, tid);
+    }
 #pragma unroll
     for (int kk = 0; kk < OVP_GK; kk += 4) {
       double a[4], b[4];
@@ -138,6 +168,9 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmBatch batch) {
     }
     __syncthreads();
   }
+  const double alpha = pb.alpha, beta = pb.beta;
+  double *Cp = pb.C;
+  const int ldc = pb.ldc, tri = pb.tri;
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -146,21 +179,52 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmBatch batch) {
       for (int h = 0; h < 2; h++) {
         int gi = m0 + wm * 32 + i * 8 + (lane >> 2);
         int gj = n0 + wn * 32 + j * 8 + (lane & 3) * 2 + h;
-        if (gi < pb.M && gj < pb.N) {
-          double v = pb.alpha * acc[i][j][h];
-          if (pb.beta != 0.0)
-            v += pb.beta * pb.C[(size_t)gj * pb.ldc + gi];
+        if (gi < M && gj < N) {
+          double v = alpha * acc[i][j][h];
+          if (beta != 0.0)
+            v += beta * Cp[(size_t)gj * ldc + gi];
           if (gi == gj)
             v += pb.diag_add ? pb.diag_add[gi] : pb.diag_const;
-          if (pb.tri == TRI_FULL) {
-            pb.C[(size_t)gj * pb.ldc + gi] = v;
+          if (tri == TRI_FULL) {
+            Cp[(size_t)gj * ldc + gi] = v;
           } else if (gi >= gj) { // lower part of the (diagonal) tile
-            pb.C[(size_t)gj * pb.ldc + gi] = v;
-            if (pb.tri == TRI_LOWER_MIRROR && gi != gj && gi < pb.N && gj < pb.M)
-              pb.C[(size_t)gi * pb.ldc + gj] = v;
+            Cp[(size_t)gj * ldc + gi] = v;
+            if (tri == TRI_LOWER_MIRROR && gi != gj && gi < N && gj < M)
+              Cp[(size_t)gi * ldc + gj] = v;
           }
         }
       }
+}
+
+// A: logical M x K view; gathers are supported along K only
+inline SView sview_A(const MatView &v) {
+  SView s;
+  s.p = v.p;
+  if (!v.trans) {
+    s.sx = 1;
+    s.sk = v.ld;
+    s.kidx = v.cidx;
+  } else {
+    s.sx = v.ld;
+    s.sk = 1;
+    s.kidx = v.ridx;
+  }
+  return s;
+}
+// B: logical K x N view
+inline SView sview_B(const MatView &v) {
+  SView s;
+  s.p = v.p;
+  if (!v.trans) {
+    s.sk = 1;
+    s.sx = v.ld;
+    s.kidx = v.ridx;
+  } else {
+    s.sx = 1;
+    s.sk = v.ld;
+    s.kidx = v.cidx;
+  }
+  return s;
 }
 
 inline GemmProblem make_problem(int M, int N, int K, MatView A, MatView B, double *C, int ldc, double alpha = 1.0, double beta = 0.0) {
@@ -168,8 +232,8 @@ inline GemmProblem make_problem(int M, int N, int K, MatView A, MatView B, doubl
   p.M = M;
   p.N = N;
   p.K = K;
-  p.A = A;
-  p.B = B;
+  p.A = sview_A(A);
+  p.B = sview_B(B);
   p.C = C;
   p.ldc = ldc;
   p.alpha = alpha;
@@ -177,9 +241,9 @@ inline GemmProblem make_problem(int M, int N, int K, MatView A, MatView B, doubl
   p.diag_add = nullptr;
   p.diag_const = 0.0;
   p.tri = TRI_FULL;
-  // default loader hints: a view is contiguous along its logical rows unless transposed
-  p.a_kfast = A.trans ? 1 : 0;
-  p.b_kfast = B.trans ? 0 : 1;
+  // loader walk: along whichever logical direction is contiguous in memory
+  p.a_kfast = (p.A.sk == 1) ? 1 : 0;
+  p.b_kfast = (p.B.sk == 1) ? 1 : 0;
   return p;
 }
 

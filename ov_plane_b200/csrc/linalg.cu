@@ -32,7 +32,15 @@ void launch_gemm(Ctx *c, const GemmBatch &b) {
   for (int i = 0; i < b.n; i++)
     work += (b.p[i].tri == TRI_FULL ? 2.0 : 1.0) * (double)b.p[i].M * b.p[i].N * b.p[i].K;
   prof_begin(c, PROF_GEMM, work);
-  gemm_f64_kernel<<<grid, 128, 0, c->stream>>>(b);
+  const bool ga = b.p[0].A.kidx != nullptr, gb = b.p[0].B.kidx != nullptr;
+  if (ga && gb)
+    gemm_f64_kernel<true, true><<<grid, 128, 0, c->stream>>>(b);
+  else if (ga)
+    gemm_f64_kernel<true, false><<<grid, 128, 0, c->stream>>>(b);
+  else if (gb)
+    gemm_f64_kernel<false, true><<<grid, 128, 0, c->stream>>>(b);
+  else
+    gemm_f64_kernel<false, false><<<grid, 128, 0, c->stream>>>(b);
   c->launches++;
   prof_end(c);
 }
@@ -153,10 +161,9 @@ void launch_sumsq(Ctx *c, const double *x, int n, double *out) {
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double *A, int ld, int bs, const double *diag0, double tol, double *Linv,
                                                          int ldi, int *info) {
   extern __shared__ double sm[];
-  double(*a)[DLD] = (double(*)[DLD])sm;
-  double(*x)[DLD] = (double(*)[DLD])(sm + DB * DLD);
-  double(*t)[DLD] = (double(*)[DLD])(sm + 2 * DB * DLD);
-  __shared__ double s_inv;
+  double(*a)[DLD] = (double(*)[DLD])sm;                  // working copy (lower), later scratch of the inverse merges
+  double(*x)[DLD] = (double(*)[DLD])(sm + DB * DLD);     // inverse
+  double(*l)[DLD] = (double(*)[DLD])(sm + 2 * DB * DLD); // factor L
   __shared__ double pivinv[DB];
   const int tid = threadIdx.x;
   for (int idx = tid; idx < DB * DB; idx += 256) {
@@ -168,45 +175,40 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double *A, int ld, int 
       v = (i == j) ? 1.0 : 0.0;
     a[i][j] = v;
     x[i][j] = 0.0;
-    t[i][j] = 0.0;
+    l[i][j] = 0.0;
   }
+  // right-looking factorisation, ONE barrier per column: column j of `a` is read-only during step j (the scaled column goes
+  // to `l`), the rank-1 update uses the unscaled column times 1/d.  Thread layout: row i = tid & 63, column group tid >> 6.
+  const int ti = tid & 63, tg = tid >> 6;
   for (int j = 0; j < DB; j++) {
     __syncthreads();
+    const double d = a[j][j];
+    bool ok = true;
+    if (j < bs)
+      ok = (d > tol * diag0[j]) && (d > 0.0);
+    const double p = ok ? sqrt(d) : 0.0;
+    const double invp = ok ? 1.0 / p : 0.0;
+    const double invd = ok ? 1.0 / d : 0.0;
+    if (tg == 0 && ti >= j)
+      l[ti][j] = (ti == j) ? p : a[ti][j] * invp;
     if (tid == 0) {
-      double d = a[j][j];
-      bool ok = true;
-      if (j < bs) {
-        double thr = tol * diag0[j];
-        ok = (d > thr) && (d > 0.0);
-        if (!ok && tol == 0.0 && info)
-          atomicExch(info, 1); // strict mode: not positive definite
-      }
-      double p = ok ? sqrt(d) : 0.0;
-      a[j][j] = p;
-      s_inv = ok ? 1.0 / p : 0.0;
-      pivinv[j] = s_inv;
+      pivinv[j] = invp;
+      if (!ok && tol == 0.0 && info)
+        atomicExch(info, 1); // strict mode: not positive definite
     }
-    __syncthreads();
-    if (tid > j && tid < DB)
-      a[tid][j] *= s_inv;
-    __syncthreads();
-    int nrem = DB - 1 - j;
-    for (int idx = tid; idx < nrem * nrem; idx += 256) {
-      int i = j + 1 + idx % nrem;
-      int k = j + 1 + idx / nrem;
-      if (i >= k)
-        a[i][k] -= a[i][j] * a[k][j];
-    }
+    const double aij = a[ti][j] * invd;
+    for (int k = j + 1 + tg; k < DB; k += 4)
+      if (ti >= k)
+        a[ti][k] -= aij * a[k][j];
   }
   __syncthreads();
   // write L back (lower incl. diagonal); strictly-upper part of the block is zeroed
   for (int idx = tid; idx < DB * DB; idx += 256) {
     int i = idx & 63, j = idx >> 6;
     if (i < bs && j < bs)
-      A[(size_t)j * ld + i] = (i >= j) ? a[i][j] : 0.0;
+      A[(size_t)j * ld + i] = (i >= j) ? l[i][j] : 0.0;
   }
-  // ---- inverse by recursive doubling: 8x8 base blocks, then merges at 8, 16, 32 ----
-  // base: thread (blk, c) computes column c of the inverse of diagonal block blk
+  // ---- inverse by recursive doubling: 8x8 base blocks, then merges at 8, 16, 32 (zero-pivot rows / columns stay zero) ----
   if (tid < 64) {
     int blk = tid >> 3, cc = tid & 7;
     int o = blk * 8;
@@ -216,35 +218,34 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double *A, int ld, int 
       for (int i = c + 1; i < o + 8; i++) {
         double s = 0.0;
         for (int k = c; k < i; k++)
-          s += a[i][k] * x[k][c];
+          s += l[i][k] * x[k][c];
         x[i][c] = -s * pivinv[i];
       }
     }
   }
   __syncthreads();
-  for (int s = 8; s < DB; s *= 2) {
-    int npairs = DB / (2 * s);
-    // T = L21 * X11 for every pair
-    for (int idx = tid; idx < npairs * s * s; idx += 256) {
-      int pr = idx / (s * s);
-      int rem = idx - pr * s * s;
-      int i = rem % s, j = rem / s;
-      int o = pr * 2 * s;
+  for (int s = 8, sh = 3; s < DB; s *= 2, sh++) {
+    // work item = (pair, i, j) with i fastest; s*s items per pair, npairs*s*s = 64*s/2 items in total
+    const int nitems = (DB / (2 * s)) * s * s;
+    // T = L21 * X11 for every pair (T lives in `a`)
+    for (int idx = tid; idx < nitems; idx += 256) {
+      int i = idx & (s - 1);
+      int j = (idx >> sh) & (s - 1);
+      int o = (idx >> (2 * sh)) * 2 * s;
       double acc = 0.0;
       for (int k = j; k < s; k++) // X11 is lower triangular: X11[k][j] = 0 for k < j
-        acc += a[o + s + i][o + k] * x[o + k][o + j];
-      t[o + s + i][o + j] = acc;
+        acc += l[o + s + i][o + k] * x[o + k][o + j];
+      a[o + s + i][o + j] = acc;
     }
     __syncthreads();
     // X21 = -X22 * T
-    for (int idx = tid; idx < npairs * s * s; idx += 256) {
-      int pr = idx / (s * s);
-      int rem = idx - pr * s * s;
-      int i = rem % s, j = rem / s;
-      int o = pr * 2 * s;
+    for (int idx = tid; idx < nitems; idx += 256) {
+      int i = idx & (s - 1);
+      int j = (idx >> sh) & (s - 1);
+      int o = (idx >> (2 * sh)) * 2 * s;
       double acc = 0.0;
       for (int k = 0; k <= i; k++) // X22 lower triangular
-        acc += x[o + s + i][o + s + k] * t[o + s + k][o + j];
+        acc += x[o + s + i][o + s + k] * a[o + s + k][o + j];
       x[o + s + i][o + j] = -acc;
     }
     __syncthreads();

@@ -24,7 +24,9 @@ def compare_states(ctx, orc, S, chg, cho, tol=REL):
     assert Pg.shape == Po.shape
     e = relerr(Pg, Po)
     assert e < tol, "covariance rel. Frobenius error %.3e" % e
-    assert np.abs(Pg - Pg.T).max() == 0.0, "covariance not exactly symmetric"
+    # EKFUpdate mirrors the upper triangle (exactly symmetric); EKFPropagation writes Phi P Phi^T + Q as computed (the reference
+    # does the same, StateHelper.cpp:105), so allow round-off level asymmetry
+    assert np.abs(Pg - Pg.T).max() <= 1e-14 * np.abs(Pg).max(), "covariance not symmetric"
     hs = [(ctx.handle_imu(), orc.handle_imu()), (ctx.handle_calib(), orc.handle_calib()), (ctx.handle_intrinsics(), orc.handle_intrinsics())]
     hs += list(zip(chg, cho))
     for pid, _, _ in S.planes:

@@ -212,6 +212,8 @@ int ovp_synchronize(ovp_ctx *ctx);
  * [3] feature kernel, [4] other; report = total ms, launch count and algorithmic work (flops; bytes for [3]) since enabled */
 int ovp_set_profiling(ovp_ctx *ctx, int on);
 int ovp_profile_report(ovp_ctx *ctx, double *ms5, int64_t *count5, double *work5);
+/* 1 (default): the static launch sequence of a prepared batch is captured into a CUDA graph and replayed */
+int ovp_set_use_graphs(ovp_ctx *ctx, int on);
 /* bytes this ctx copied host->device / device->host since creation */
 int ovp_transfer_bytes(ovp_ctx *ctx, int64_t *h2d, int64_t *d2h);
 /* measured FP64 tensor-core (DMMA) throughput of this device with the library's own GEMM kernel: returns TFLOP/s */

@@ -372,16 +372,23 @@ int ovp_create(const ovp_state_options *opt, int device, int max_state, int max_
   OVP_CUDA(cudaMalloc(&c->dM, (size_t)c->Nmax * c->Rcap * sizeof(double)));
   OVP_CUDA(cudaMalloc(&c->dY, (size_t)c->Nmax * c->Rcap * sizeof(double)));
   OVP_CUDA(cudaMalloc(&c->dHT, (size_t)c->Rcap * c->Rcap * sizeof(double)));
+  OVP_CUDA(cudaMemset(c->dM, 0, (size_t)c->Nmax * c->Rcap * sizeof(double)));
+  OVP_CUDA(cudaMemset(c->dY, 0, (size_t)c->Nmax * c->Rcap * sizeof(double)));
+  OVP_CUDA(cudaMemset(c->dHT, 0, (size_t)c->Rcap * c->Rcap * sizeof(double)));
   OVP_CUDA(cudaMalloc(&c->dvec, ((size_t)8 * c->Rcap + 2 * c->Nmax) * sizeof(double)));
   OVP_CUDA(cudaMemset(c->dvec, 0, ((size_t)8 * c->Rcap + 2 * c->Nmax) * sizeof(double)));
   OVP_CUDA(cudaMalloc(&c->dcols, (size_t)8 * c->Rcap * sizeof(int)));
   OVP_CUDA(cudaMalloc(&c->dflags, 256 * sizeof(int)));
   OVP_CUDA(cudaMemset(c->dflags, 0, 256 * sizeof(int)));
   OVP_CUDA(cudaMalloc(&c->dscal, 256 * sizeof(double)));
+  OVP_CUDA(cudaMemset(c->dscal, 0, 256 * sizeof(double)));
   c->Hs_elems = (size_t)(c->max_meas_rows + 8) * c->Rcap;
   OVP_CUDA(cudaMalloc(&c->dHs, c->Hs_elems * sizeof(double)));
+  OVP_CUDA(cudaMemset(c->dHs, 0, c->Hs_elems * sizeof(double)));
   c->part_elems = (size_t)64 * c->Rcap * c->Rcap;
   OVP_CUDA(cudaMalloc(&c->dPart, c->part_elems * sizeof(double)));
+  OVP_CUDA(cudaMemset(c->dPart, 0, c->part_elems * sizeof(double)));
+  OVP_CUDA(cudaDeviceSynchronize());
   // ---- State::State(options), State.cpp:33-102 ----
   Var imu;
   imu.kind = OVP_KIND_IMU;

@@ -77,21 +77,22 @@ struct GemmBatch {
   const int *flag; // optional device flag: when non-null and *flag == 0 the whole launch is a no-op
 };
 
-#define OVP_GT 64  // tile edge
+#define OVP_GT 64  // large tile edge
 #define OVP_GK 16  // k step
-#define OVP_GLD 68 // smem leading dim (68 mod 16 == 4: conflict-free DMMA fragment reads)
+#define OVP_GLD 68 // smem leading dim of the 64-tile (68 mod 16 == 4: conflict-free DMMA fragment reads)
 
-template <bool GATHER>
-__device__ __forceinline__ void load_tile_regs(double (&r)[8], const SView &v, int x0, int X, int k0, int K, int kfast, int tid) {
+// Tile loaders.  TILE x 16 elements per operand per k-step, 128 threads => NL = TILE / 8 elements per thread.
+template <int TILE, bool GATHER>
+__device__ __forceinline__ void load_tile_regs(double (&r)[TILE / 8], const SView &v, int x0, int X, int k0, int K, int kfast, int tid) {
 #pragma unroll
-  for (int t = 0; t < 8; t++) {
+  for (int t = 0; t < TILE / 8; t++) {
     int xx, kk;
     if (kfast) {
       kk = tid & 15;
       xx = (tid >> 4) + 8 * t;
     } else {
-      xx = tid & 63;
-      kk = (tid >> 6) + 2 * t;
+      xx = tid & (TILE - 1);
+      kk = tid / TILE + (128 / TILE) * t;
     }
     int gx = x0 + xx, gk = k0 + kk;
     bool ok = (gx < X) && (gk < K);
@@ -101,88 +102,116 @@ __device__ __forceinline__ void load_tile_regs(double (&r)[8], const SView &v, i
     r[t] = ok ? v.p[(long long)gx * v.sx + kphys * v.sk] : 0.0;
   }
 }
-__device__ __forceinline__ void store_tile_smem(const double (&r)[8], double (*sm)[OVP_GLD], int kfast, int tid) {
+template <int TILE>
+__device__ __forceinline__ void store_tile_smem(const double (&r)[TILE / 8], double (*sm)[TILE + 4], int kfast, int tid) {
 #pragma unroll
-  for (int t = 0; t < 8; t++) {
+  for (int t = 0; t < TILE / 8; t++) {
     int xx, kk;
     if (kfast) {
       kk = tid & 15;
       xx = (tid >> 4) + 8 * t;
     } else {
-      xx = tid & 63;
-      kk = (tid >> 6) + 2 * t;
+      xx = tid & (TILE - 1);
+      kk = tid / TILE + (128 / TILE) * t;
     }
     sm[kk][xx] = r[t];
   }
 }
 
-template <bool GA, bool GB> __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmBatch batch) {
+// TILE = 64: 4 warps x (32x32) ; TILE = 32: 4 warps x (16x16) — the small tile spreads mid-size problems over all 148 SMs
+template <int TILE, bool GA, bool GB> __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmBatch batch) {
   if (batch.flag && *batch.flag == 0)
     return;
   const GemmProblem &pb = batch.p[blockIdx.z];
   const int tm = blockIdx.y, tn = blockIdx.x;
-  if (tm * OVP_GT >= pb.M || tn * OVP_GT >= pb.N)
+  if (tm * TILE >= pb.M || tn * TILE >= pb.N)
     return;
   if (pb.tri != TRI_FULL && tm < tn)
     return;
-  __shared__ double As[OVP_GK][OVP_GLD];
-  __shared__ double Bs[OVP_GK][OVP_GLD];
+  constexpr int WT = TILE / 2;  // warp tile edge
+  constexpr int NM = WT / 8;    // mma tiles per warp per dimension
+  __shared__ double As[OVP_GK][TILE + 4];
+  __shared__ double Bs[OVP_GK][TILE + 4];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;
-  const int m0 = tm * OVP_GT, n0 = tn * OVP_GT;
+  const int m0 = tm * TILE, n0 = tn * TILE;
   const int M = pb.M, N = pb.N, K = pb.K;
   const SView va = pb.A, vb = pb.B;
   const int akf = pb.a_kfast, bkf = pb.b_kfast;
-  double acc[4][4][2];
+  double acc[NM][NM][2];
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < NM; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++)
+    for (int j = 0; j < NM; j++)
       acc[i][j][0] = acc[i][j][1] = 0.0;
-  double ra[8], rb[8];
-  load_tile_regs<GA>(ra, va, m0, M, 0, K, akf, tid);
-  load_tile_regs<GB>(rb, vb, n0, N, 0, K, bkf, tid);
+  double ra[TILE / 8], rb[TILE / 8];
+  load_tile_regs<TILE, GA>(ra, va, m0, M, 0, K, akf, tid);
+  load_tile_regs<TILE, GB>(rb, vb, n0, N, 0, K, bkf, tid);
+  // epilogue operands that do not depend on the product are fetched now, off the critical path
+  const double alpha = pb.alpha, beta = pb.beta;
+  double *Cp = pb.C;
+  const int ldc = pb.ldc, tri = pb.tri;
+  double cin[NM][NM][2];
+  if (TILE == 32) {
+#pragma unroll
+  for (int i = 0; i < NM; i++)
+#pragma unroll
+    for (int j = 0; j < NM; j++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        int gi = m0 + wm * WT + i * 8 + (lane >> 2);
+        int gj = n0 + wn * WT + j * 8 + (lane & 3) * 2 + h;
+        cin[i][j][h] = (beta != 0.0 && gi < M && gj < N) ? Cp[(size_t)gj * ldc + gi] : 0.0;
+      }
+  }
   for (int k0 = 0; k0 < K; k0 += OVP_GK) {
-    store_tile_smem(ra, As, akf, tid);
-    store_tile_smem(rb, Bs, bkf, tid);
+    store_tile_smem<TILE>(ra, As, akf, tid);
+    store_tile_smem<TILE>(rb, Bs, bkf, tid);
     __syncthreads();
     if (k0 + OVP_GK < K) { // prefetch the next k-step while this one is in the tensor pipe
-      load_tile_regs<GA>(ra, va, m0, M, k0 + OVP_GK, K, akf, tid);
-      load_tile_regs<GB>(rb, vb, n0, N, k0 + OVP_GK, K, bkf, tid);
+      load_tile_regs<TILE, GA>(ra, va, m0, M, k0 + OVP_GK, K, akf, tid);
+      load_tile_regs<TILE, GB>(rb, vb, n0, N, k0 + OVP_GK, K, bkf, tid);
     }
 #pragma unroll
     for (int kk = 0; kk < OVP_GK; kk += 4) {
-      double a[4], b[4];
+      double a[NM], b[NM];
 #pragma unroll
-      for (int i = 0; i < 4; i++)
-        a[i] = As[kk + (lane & 3)][wm * 32 + i * 8 + (lane >> 2)];
+      for (int i = 0; i < NM; i++)
+        a[i] = As[kk + (lane & 3)][wm * WT + i * 8 + (lane >> 2)];
 #pragma unroll
-      for (int j = 0; j < 4; j++)
-        b[j] = Bs[kk + (lane & 3)][wn * 32 + j * 8 + (lane >> 2)];
+      for (int j = 0; j < NM; j++)
+        b[j] = Bs[kk + (lane & 3)][wn * WT + j * 8 + (lane >> 2)];
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+      for (int i = 0; i < NM; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+        for (int j = 0; j < NM; j++)
           dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
     __syncthreads();
   }
-  const double alpha = pb.alpha, beta = pb.beta;
-  double *Cp = pb.C;
-  const int ldc = pb.ldc, tri = pb.tri;
+  if (TILE != 32) { // large tile: fetch C after the main loop (all loads in flight together), registers are free now
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < NM; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++)
+    for (int j = 0; j < NM; j++)
 #pragma unroll
       for (int h = 0; h < 2; h++) {
-        int gi = m0 + wm * 32 + i * 8 + (lane >> 2);
-        int gj = n0 + wn * 32 + j * 8 + (lane & 3) * 2 + h;
+        int gi = m0 + wm * WT + i * 8 + (lane >> 2);
+        int gj = n0 + wn * WT + j * 8 + (lane & 3) * 2 + h;
+        cin[i][j][h] = (beta != 0.0 && gi < M && gj < N) ? Cp[(size_t)gj * ldc + gi] : 0.0;
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < NM; i++)
+#pragma unroll
+    for (int j = 0; j < NM; j++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        int gi = m0 + wm * WT + i * 8 + (lane >> 2);
+        int gj = n0 + wn * WT + j * 8 + (lane & 3) * 2 + h;
         if (gi < M && gj < N) {
-          double v = alpha * acc[i][j][h];
-          if (beta != 0.0)
-            v += beta * Cp[(size_t)gj * ldc + gi];
+          double v = alpha * acc[i][j][h] + beta * cin[i][j][h];
           if (gi == gj)
             v += pb.diag_add ? pb.diag_add[gi] : pb.diag_const;
           if (tri == TRI_FULL) {

@@ -19,28 +19,41 @@ int fail(Ctx *c, int status, const char *fmt, ...) {
   return status;
 }
 
+template <int TILE> static void launch_gemm_tile(Ctx *c, const GemmBatch &b, dim3 grid) {
+  const bool ga = b.p[0].A.kidx != nullptr, gb = b.p[0].B.kidx != nullptr;
+  if (ga && gb)
+    gemm_f64_kernel<TILE, true, true><<<grid, 128, 0, c->stream>>>(b);
+  else if (ga)
+    gemm_f64_kernel<TILE, true, false><<<grid, 128, 0, c->stream>>>(b);
+  else if (gb)
+    gemm_f64_kernel<TILE, false, true><<<grid, 128, 0, c->stream>>>(b);
+  else
+    gemm_f64_kernel<TILE, false, false><<<grid, 128, 0, c->stream>>>(b);
+}
 void launch_gemm(Ctx *c, const GemmBatch &b) {
   int tm = 0, tn = 0;
+  long long tiles64 = 0;
+  double work = 0;
   for (int i = 0; i < b.n; i++) {
-    tm = std::max(tm, (b.p[i].M + OVP_GT - 1) / OVP_GT);
-    tn = std::max(tn, (b.p[i].N + OVP_GT - 1) / OVP_GT);
+    int a = (b.p[i].M + 63) / 64, bb = (b.p[i].N + 63) / 64;
+    tm = std::max(tm, a);
+    tn = std::max(tn, bb);
+    tiles64 += (b.p[i].tri == TRI_FULL) ? (long long)a * bb : (long long)a * (a + 1) / 2;
+    work += (b.p[i].tri == TRI_FULL ? 2.0 : 1.0) * (double)b.p[i].M * b.p[i].N * b.p[i].K;
   }
   if (tm == 0 || tn == 0 || b.n == 0)
     return;
-  dim3 grid(tn, tm, b.n);
-  double work = 0;
-  for (int i = 0; i < b.n; i++)
-    work += (b.p[i].tri == TRI_FULL ? 2.0 : 1.0) * (double)b.p[i].M * b.p[i].N * b.p[i].K;
   prof_begin(c, PROF_GEMM, work);
-  const bool ga = b.p[0].A.kidx != nullptr, gb = b.p[0].B.kidx != nullptr;
-  if (ga && gb)
-    gemm_f64_kernel<true, true><<<grid, 128, 0, c->stream>>>(b);
-  else if (ga)
-    gemm_f64_kernel<true, false><<<grid, 128, 0, c->stream>>>(b);
-  else if (gb)
-    gemm_f64_kernel<false, true><<<grid, 128, 0, c->stream>>>(b);
-  else
-    gemm_f64_kernel<false, false><<<grid, 128, 0, c->stream>>>(b);
+  if (tiles64 >= 148 || c->force_tile64) {
+    launch_gemm_tile<64>(c, b, dim3(tn, tm, b.n));
+  } else { // fewer 64-tiles than SMs: 32-tiles quadruple the CTA count and quarter the per-CTA tensor work
+    int tm32 = 0, tn32 = 0;
+    for (int i = 0; i < b.n; i++) {
+      tm32 = std::max(tm32, (b.p[i].M + 31) / 32);
+      tn32 = std::max(tn32, (b.p[i].N + 31) / 32);
+    }
+    launch_gemm_tile<32>(c, b, dim3(tn32, tm32, b.n));
+  }
   c->launches++;
   prof_end(c);
 }
@@ -158,14 +171,22 @@ void launch_sumsq(Ctx *c, const double *x, int n, double *out) {
 // -------------------------------------------------------------------------------------------------------------------
 #define DB 64
 #define DLD 65
+// Diagonal 64x64 block, one CTA, shared memory: right-looking Cholesky blocked by 8 columns (8x8 diagonal factor by the
+// first 8 lanes of warp 0 with shuffles, row-parallel triangular solve, rank-8 trailing update: 3 barriers per 8 columns),
+// then the triangular inverse by recursive doubling (8x8 bases, merges at 8/16/32).  Rank-tolerant pivots: a pivot
+// <= tol * (original diagonal) (or <= 0) zeroes that row/column of L and of L^-1 (semi-definite Gram matrices).
+#define POTRF_TS(k)                                                                                                         \
+  if (tstamps && tid == 0)                                                                                                   \
+    tstamps[k] = clock64();
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double *A, int ld, int bs, const double *diag0, double tol, double *Linv,
-                                                         int ldi, int *info) {
+                                                         int ldi, int *info, long long *tstamps = nullptr) {
   extern __shared__ double sm[];
-  double(*a)[DLD] = (double(*)[DLD])sm;                  // working copy (lower), later scratch of the inverse merges
+  double(*a)[DLD] = (double(*)[DLD])sm;                  // block, factored in place
   double(*x)[DLD] = (double(*)[DLD])(sm + DB * DLD);     // inverse
-  double(*l)[DLD] = (double(*)[DLD])(sm + 2 * DB * DLD); // factor L
+  double(*t)[DLD] = (double(*)[DLD])(sm + 2 * DB * DLD); // scratch of the inverse merges
   __shared__ double pivinv[DB];
-  const int tid = threadIdx.x;
+  __shared__ double thr[DB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int idx = tid; idx < DB * DB; idx += 256) {
     int i = idx & 63, j = idx >> 6;
     double v;
@@ -175,39 +196,119 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double *A, int ld, int 
       v = (i == j) ? 1.0 : 0.0;
     a[i][j] = v;
     x[i][j] = 0.0;
-    l[i][j] = 0.0;
   }
-  // right-looking factorisation, ONE barrier per column: column j of `a` is read-only during step j (the scaled column goes
-  // to `l`), the rank-1 update uses the unscaled column times 1/d.  Thread layout: row i = tid & 63, column group tid >> 6.
-  const int ti = tid & 63, tg = tid >> 6;
-  for (int j = 0; j < DB; j++) {
-    __syncthreads();
-    const double d = a[j][j];
-    bool ok = true;
-    if (j < bs)
-      ok = (d > tol * diag0[j]) && (d > 0.0);
-    const double p = ok ? sqrt(d) : 0.0;
-    const double invp = ok ? 1.0 / p : 0.0;
-    const double invd = ok ? 1.0 / d : 0.0;
-    if (tg == 0 && ti >= j)
-      l[ti][j] = (ti == j) ? p : a[ti][j] * invp;
-    if (tid == 0) {
-      pivinv[j] = invp;
-      if (!ok && tol == 0.0 && info)
-        atomicExch(info, 1); // strict mode: not positive definite
-    }
-    const double aij = a[ti][j] * invd;
-    for (int k = j + 1 + tg; k < DB; k += 4)
-      if (ti >= k)
-        a[ti][k] -= aij * a[k][j];
-  }
+  if (tid < DB)
+    thr[tid] = (tid < bs) ? tol * diag0[tid] : 0.0;
+  POTRF_TS(0)
   __syncthreads();
-  // write L back (lower incl. diagonal); strictly-upper part of the block is zeroed
-  for (int idx = tid; idx < DB * DB; idx += 256) {
-    int i = idx & 63, j = idx >> 6;
-    if (i < bs && j < bs)
-      A[(size_t)j * ld + i] = (i >= j) ? l[i][j] : 0.0;
+  POTRF_TS(1)
+  // Blocked by 8 columns with one panel of look-ahead: while warp 0 runs the serial pivot chain of the 8x8 diagonal block of
+  // panel p (lane = row, registers + shuffles), warps 1..7 finish the rank-8 trailing update of panel p-1 on the columns
+  // beyond panel p ("part B"); the columns of panel p itself were updated first ("part A") by everyone.
+  for (int c0 = 0; c0 < DB; c0 += 8) {
+    if (warp == 0) {
+      // (1) 8x8 diagonal factor
+      double r[8];
+      const int li = lane & 7;
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+        r[c] = (c <= li) ? a[c0 + li][c0 + c] : 0.0;
+      double my_pinv = 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const double d = __shfl_sync(0xffffffffu, r[j], j);
+        const bool ok = (d > thr[c0 + j]) && (d > 0.0);
+        if (tol == 0.0 && !ok && info && lane == 0 && c0 + j < bs)
+          atomicExch(info, 1); // strict mode: not positive definite
+        const double invp = ok ? rsqrt(d) : 0.0;
+        const double l = r[j] * invp;
+        if (li >= j)
+          r[j] = l;
+        if (li == j)
+          my_pinv = invp;
+#pragma unroll
+        for (int k = j + 1; k < 8; k++) {
+          const double lk = __shfl_sync(0xffffffffu, l, k);
+          if (li >= k)
+            r[k] = fma(-l, lk, r[k]);
+        }
+      }
+      if (lane < 8) {
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+          if (c <= lane)
+            a[c0 + lane][c0 + c] = r[c];
+        pivinv[c0 + lane] = my_pinv;
+      }
+    } else if (c0 >= 8) {
+      // part B of the previous panel (columns >= c0 + 8), 224 threads: row = wt & 63 would leave holes, so use a flat map
+      const int pc = c0 - 8; // previous panel's first column
+      const int wt = tid - 32;
+      const int nrow = DB - (c0 + 8); // rows (and columns) still to update beyond the current panel
+      if (nrow > 0) {
+        // items: (row i in [c0+8, 64), column group g of 2 columns k in [c0+8, i])
+        for (int it = wt; it < nrow * ((nrow + 1) / 2); it += 224) {
+          const int i = c0 + 8 + it % nrow;
+          const int k = c0 + 8 + 2 * (it / nrow);
+          if (k > i)
+            continue;
+          double s0 = a[i][k], s1 = (k + 1 <= i) ? a[i][k + 1] : 0.0;
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const double lij = a[i][pc + j];
+            s0 = fma(-lij, a[k][pc + j], s0);
+            s1 = fma(-lij, a[(k + 1 < DB) ? k + 1 : k][pc + j], s1);
+          }
+          a[i][k] = s0;
+          if (k + 1 <= i)
+            a[i][k + 1] = s1;
+        }
+      }
+    }
+    __syncthreads();
+    // (2) rows below: L21 = A21 * L11^-T, one thread per row, outer-product form
+    if (tid < DB - c0 - 8) {
+      const int i = c0 + 8 + tid;
+      double sr[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        sr[j] = a[i][c0 + j];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const double xj = sr[j] * pivinv[c0 + j];
+        sr[j] = xj;
+#pragma unroll
+        for (int k = j + 1; k < 8; k++)
+          sr[k] = fma(-xj, a[c0 + k][c0 + j], sr[k]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        a[i][c0 + j] = sr[j];
+    }
+    __syncthreads();
+    // (3) part A: rank-8 update of the NEXT panel's columns [c0+8, c0+16) for all rows below (lower part only)
+    if (c0 + 8 < DB) {
+      const int i = c0 + 8 + (tid >> 2);
+      const int kk = (tid & 3) * 2;
+      if (i < DB) {
+        const int k = c0 + 8 + kk;
+        if (k <= i) {
+          double s0 = a[i][k], s1 = (k + 1 <= i) ? a[i][k + 1] : 0.0;
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const double lij = a[i][c0 + j];
+            s0 = fma(-lij, a[k][c0 + j], s0);
+            s1 = fma(-lij, a[k + 1][c0 + j], s1);
+          }
+          a[i][k] = s0;
+          if (k + 1 <= i)
+            a[i][k + 1] = s1;
+        }
+      }
+    }
+    __syncthreads();
   }
+  POTRF_TS(2)
   // ---- inverse by recursive doubling: 8x8 base blocks, then merges at 8, 16, 32 (zero-pivot rows / columns stay zero) ----
   if (tid < 64) {
     int blk = tid >> 3, cc = tid & 7;
@@ -218,43 +319,58 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double *A, int ld, int 
       for (int i = c + 1; i < o + 8; i++) {
         double s = 0.0;
         for (int k = c; k < i; k++)
-          s += l[i][k] * x[k][c];
+          s += a[i][k] * x[k][c];
         x[i][c] = -s * pivinv[i];
       }
     }
   }
   __syncthreads();
+  POTRF_TS(3)
   for (int s = 8, sh = 3; s < DB; s *= 2, sh++) {
-    // work item = (pair, i, j) with i fastest; s*s items per pair, npairs*s*s = 64*s/2 items in total
-    const int nitems = (DB / (2 * s)) * s * s;
-    // T = L21 * X11 for every pair (T lives in `a`)
+    // work item = (pair, row i, group of 4 columns): 4 independent accumulators share every load of the left operand
+    const int nitems = (DB / (2 * s)) * s * (s / 4);
     for (int idx = tid; idx < nitems; idx += 256) {
       int i = idx & (s - 1);
-      int j = (idx >> sh) & (s - 1);
-      int o = (idx >> (2 * sh)) * 2 * s;
-      double acc = 0.0;
-      for (int k = j; k < s; k++) // X11 is lower triangular: X11[k][j] = 0 for k < j
-        acc += l[o + s + i][o + k] * x[o + k][o + j];
-      a[o + s + i][o + j] = acc;
+      int jg = ((idx >> sh) & (s / 4 - 1)) * 4;
+      int o = (idx / (s * (s / 4))) * 2 * s;
+      double acc[4] = {0, 0, 0, 0};
+      for (int k = jg; k < s; k++) { // X11 lower triangular: X11[k][j] = 0 for k < j (zeros are stored, so k >= jg suffices)
+        const double av = a[o + s + i][o + k];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          acc[q] = fma(av, x[o + k][o + jg + q], acc[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        t[o + s + i][o + jg + q] = acc[q];
     }
     __syncthreads();
-    // X21 = -X22 * T
     for (int idx = tid; idx < nitems; idx += 256) {
       int i = idx & (s - 1);
-      int j = (idx >> sh) & (s - 1);
-      int o = (idx >> (2 * sh)) * 2 * s;
-      double acc = 0.0;
-      for (int k = 0; k <= i; k++) // X22 lower triangular
-        acc += x[o + s + i][o + s + k] * a[o + s + k][o + j];
-      x[o + s + i][o + j] = -acc;
+      int jg = ((idx >> sh) & (s / 4 - 1)) * 4;
+      int o = (idx / (s * (s / 4))) * 2 * s;
+      double acc[4] = {0, 0, 0, 0};
+      for (int k = 0; k <= i; k++) { // X22 lower triangular
+        const double xv = x[o + s + i][o + s + k];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          acc[q] = fma(xv, t[o + s + k][o + jg + q], acc[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        x[o + s + i][o + jg + q] = -acc[q];
     }
     __syncthreads();
   }
+  POTRF_TS(4)
   for (int idx = tid; idx < DB * DB; idx += 256) {
     int i = idx & 63, j = idx >> 6;
-    if (i < bs && j < bs)
+    if (i < bs && j < bs) {
+      A[(size_t)j * ld + i] = (i >= j) ? a[i][j] : 0.0;
       Linv[(size_t)j * ldi + i] = x[i][j];
+    }
   }
+  POTRF_TS(5)
 }
 
 __global__ void save_diag_kernel(const double *A, int ld, int n, double *d) {
@@ -310,10 +426,15 @@ int chol_partial(Ctx *c, DenseWs &ws, double *A, int ld, int n, int npiv, double
     int r0 = j0 + bs;
     int nb = n - r0;
     if (nb > 0) {
-      // L21 = A21 * Linv11^T (in place: one tile column, every CTA owns its rows)
+      // L21 = A21 * Linv11^T IN PLACE: legal only with ONE tile column (every CTA then owns the rows it reads and writes), so
+      // this launch must use the 64-wide tile (bs <= 64); with 32-wide tiles the two column-CTAs of a row block would overwrite
+      // columns the other one is still reading.
       GemmProblem p = make_problem(nb, bs, bs, mv(A + (size_t)j0 * ld + r0, ld), mv(ws.Linv + (size_t)j0 * ws.cap + j0, ws.cap, 1),
                                    A + (size_t)j0 * ld + r0, ld);
+      const bool keep = c->force_tile64;
+      c->force_tile64 = true;
       launch_gemm1(c, p);
+      c->force_tile64 = keep;
       int nc = npiv - r0;
       if (nc > 0) {
         // A22 -= L21 L21^T for columns < npiv, lower tiles

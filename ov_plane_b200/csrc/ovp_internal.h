@@ -41,6 +41,8 @@ struct Ctx {
   ovp_state_options opt;
   std::string last_error;
   int64_t launches = 0;
+  bool force_tile64 = false; // micro-benchmarks only
+  bool use_graphs = true;    // replay the static launch sequence of a prepared batch as a CUDA graph
 
   // --- State mirror -------------------------------------------------------------------------------------------
   int Nmax = 0, ldP = 0, N = 0;

@@ -1,0 +1,275 @@
+"""Pins the CPU oracle (oracle/oracle.hpp).  The reference ships no tests or golden vectors, so the
+oracle is pinned by (i) mathematical properties that define correctness independently of any implementation (numerical
+derivatives, orthogonality, algebraic identities of the Kalman update), (ii) a NumPy/LAPACK second opinion, (iii) committed
+golden vectors (tests/golden/, regression pin of the oracle itself; regenerate with tests/golden/make_golden.py)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_backend as ob
+from ov_plane_b200 import jpl, synth
+
+L = ob.lib()
+
+
+def _v(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def q2R(q):
+    R = np.zeros((3, 3), order="F")
+    L.orc_quat_2_Rot(_v(q).ctypes.data_as(C.c_void_p), R.ctypes.data_as(C.c_void_p))
+    return np.array(R)
+
+
+def test_quaternion_ops():
+    rng = np.random.RandomState(0)
+    for _ in range(20):
+        q = rng.randn(4)
+        q /= np.linalg.norm(q)
+        R = q2R(q)
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-14) and abs(np.linalg.det(R) - 1) < 1e-13
+        assert np.allclose(R, jpl.quat_2_Rot(q), atol=1e-15)
+        q2 = np.zeros(4)
+        L.orc_rot_2_quat(np.asfortranarray(R).ctypes.data_as(C.c_void_p), q2.ctypes.data_as(C.c_void_p))
+        assert np.allclose(q2, q if q[3] >= 0 else -q, atol=1e-12)
+        p = rng.randn(4)
+        p /= np.linalg.norm(p)
+        qp = np.zeros(4)
+        L.orc_quat_multiply(_v(q).ctypes.data_as(C.c_void_p), _v(p).ctypes.data_as(C.c_void_p), qp.ctypes.data_as(C.c_void_p))
+        assert np.allclose(q2R(qp), q2R(q) @ q2R(p), atol=1e-13)  # JPL: R(q (x) p) = R(q) R(p)
+        assert qp[3] >= 0 and abs(np.linalg.norm(qp) - 1) < 1e-14
+
+
+def test_exp_so3_and_Jr():
+    from scipy.linalg import expm
+    rng = np.random.RandomState(1)
+    for sc in (1e-9, 1e-3, 0.5, 2.0):
+        w = sc * rng.randn(3)
+        R = np.zeros((3, 3), order="F")
+        L.orc_exp_so3(_v(w).ctypes.data_as(C.c_void_p), R.ctypes.data_as(C.c_void_p))
+        assert np.allclose(R, expm(jpl.skew(w)), atol=1e-12)
+        J = np.zeros((3, 3), order="F")
+        L.orc_Jr_so3(_v(w).ctypes.data_as(C.c_void_p), J.ctypes.data_as(C.c_void_p))
+        d = 1e-6 * rng.randn(3)
+        lhs = expm(jpl.skew(w + d))
+        rhs = expm(jpl.skew(w)) @ expm(jpl.skew(J @ d))  # right Jacobian: exp(w + d) ~ exp(w) exp(Jr d)
+        assert np.allclose(lhs, rhs, atol=1e-10)
+
+
+def test_jpl_update_is_left_multiplicative():
+    """R(q (+) dth) = exp(-[dth x]) R(q): the convention the clone Jacobian R_ItoC [p_FinIi x] assumes (UpdaterHelper.cpp:400)."""
+    from scipy.linalg import expm
+    rng = np.random.RandomState(2)
+    for kind, nv in ((ob.KIND_POSE, 7), (ob.KIND_IMU, 16)):
+        val = rng.randn(nv)
+        val[:4] /= np.linalg.norm(val[:4])
+        dx = 1e-2 * rng.randn(15)
+        new = val.copy()
+        L.orc_var_update(kind, new.ctypes.data_as(C.c_void_p), dx.ctypes.data_as(C.c_void_p))
+        assert np.allclose(q2R(new[:4]), expm(-jpl.skew(dx[:3])) @ q2R(val[:4]), atol=1e-6 * 1e-2)
+        assert np.allclose(new[4:7], val[4:7] + dx[3:6])
+        if kind == ob.KIND_IMU:
+            assert np.allclose(new[7:16], val[7:16] + dx[6:15])
+
+
+def test_radtan_jacobian_numeric():
+    cam = synth.EUROC_CAM.copy()
+    rng = np.random.RandomState(3)
+    for _ in range(10):
+        x, y = rng.uniform(-0.6, 0.6, 2)
+        uv = np.zeros(2)
+        dzn, dze = np.zeros((2, 2), order="F"), np.zeros((2, 8), order="F")
+        L.orc_radtan_jacobian(cam.ctypes.data_as(C.c_void_p), C.c_double(x), C.c_double(y), dzn.ctypes.data_as(C.c_void_p),
+                              dze.ctypes.data_as(C.c_void_p))
+
+        def f(c, xx, yy):
+            o = np.zeros(2)
+            L.orc_radtan_distort(_v(c).ctypes.data_as(C.c_void_p), C.c_double(xx), C.c_double(yy), o.ctypes.data_as(C.c_void_p))
+            return o
+        assert np.allclose(f(cam, x, y), jpl.radtan_distort(cam, x, y))
+        h = 1e-6
+        num = np.stack([(f(cam, x + h, y) - f(cam, x - h, y)) / (2 * h), (f(cam, x, y + h) - f(cam, x, y - h)) / (2 * h)], axis=1)
+        assert np.allclose(dzn, num, rtol=1e-6, atol=1e-6)
+        for k in range(8):
+            cp, cm = cam.copy(), cam.copy()
+            hk = 1e-6 * max(1.0, abs(cam[k]))
+            cp[k] += hk
+            cm[k] -= hk
+            assert np.allclose(dze[:, k], (f(cp, x, y) - f(cm, x, y)) / (2 * hk), rtol=1e-5, atol=1e-6)
+
+
+def test_make_givens():
+    rng = np.random.RandomState(4)
+    cases = [(1.0, 0.0), (-2.0, 0.0), (0.0, 3.0), (0.0, -3.0), (0.0, 0.0)] + [tuple(rng.randn(2)) for _ in range(20)]
+    for p, q in cases:
+        cs = np.zeros(2)
+        L.orc_make_givens(C.c_double(p), C.c_double(q), cs.ctypes.data_as(C.c_void_p))
+        c, s = cs
+        assert abs(c * c + s * s - 1) < 1e-14
+        # applyOnTheLeft(0, 1, G.adjoint()): x' = c x - s y ; y' = s x + c y must annihilate the second entry
+        assert abs(s * p + c * q) < 1e-14 * max(1.0, abs(p) + abs(q))
+        assert abs(abs(c * p - s * q) - np.hypot(p, q)) < 1e-13 * max(1.0, np.hypot(p, q))
+
+
+def _feature_residual(S, o, ch, f, pf):
+    a, b = S.meas_offset[f], S.meas_offset[f + 1]
+    idx = S.meas_clone_idx[a:b]
+    pid = int(S.planeid[f])
+    cp = cpf = None
+    if pid:
+        cp, cpf = o.var_get(o.plane_handle(pid))
+    return o.feature_jacobian_full([ch[i] for i in idx], S.uv[a:b], pf, pf, pid, cp, cpf, 1.0, 0.01)
+
+
+def test_feature_jacobian_matches_numerical_derivative():
+    """Without FEJ the Jacobian must be the derivative of the residual w.r.t. the error state under ov_type's update rules:
+    r(x (+) dx, p_f + dp) ~ r(x, p_f) - H_x dx - H_f dp.  Covers bearing rows, extrinsics, intrinsics, clone pose, in-state plane."""
+    S = synth.make_scenario("tiny_planes", seed=5)
+    opt = dict(S.options)
+    opt["do_fej"] = 0
+    rng = np.random.RandomState(6)
+    checked = 0
+    for f in range(S.F):
+        o = ob.OracleContext(opt)
+        ch = synth.load_scenario_into(o, S)
+        pf = S.p_FinG[f].copy()
+        Hf, Hx, r0, order = _feature_residual(S, o, ch, f, pf)
+        sizes = [o.var_size(h) for h in order]
+        for trial in range(2):
+            dxs = [1e-6 * rng.randn(s) for s in sizes]
+            dp = 1e-6 * rng.randn(3)
+            o2 = ob.OracleContext(opt)
+            ch2 = synth.load_scenario_into(o2, S)
+            # handles are identical across contexts built the same way
+            for h, d in zip(order, dxs):
+                v, fe = o2.var_get(h)
+                kind = ob.KIND_POSE if len(v) == 7 else ob.KIND_VEC
+                vv = np.zeros(16)
+                vv[:len(v)] = v
+                dd = np.zeros(15)
+                dd[:len(d)] = d
+                if kind == ob.KIND_POSE:
+                    L.orc_var_update(kind, vv.ctypes.data_as(C.c_void_p), dd.ctypes.data_as(C.c_void_p))
+                else:
+                    vv[:len(v)] = v + d
+                o2.var_set(h, vv[:len(v)], fe)
+            _, _, r1, _ = _feature_residual(S, o2, ch2, f, pf + dp)
+            pred = r0 - Hx @ np.concatenate(dxs) - Hf[:, :3] @ dp
+            assert np.allclose(r1, pred, atol=5e-9 * max(1.0, np.abs(Hx).max())), np.abs(r1 - pred).max()
+            checked += 1
+        if checked >= 12:
+            break
+
+
+def _numpy_update(P, cols, H, r, Rd=None):
+    Ps = P[np.ix_(cols, cols)]
+    S_ = H @ Ps @ H.T + (np.eye(len(r)) if Rd is None else np.diag(Rd))
+    K = P[:, cols] @ H.T @ np.linalg.inv(S_)
+    return P - K @ H @ P[cols, :], K @ r
+
+
+def test_ekf_update_against_numpy_and_identities():
+    S = synth.make_scenario("tiny_points", seed=7)
+    o = ob.OracleContext(S.options)
+    ch = synth.load_scenario_into(o, S)
+    rng = np.random.RandomState(8)
+    hs = [o.handle_calib(), ch[1], ch[4]]
+    cols = np.concatenate([np.arange(o.var_id(h), o.var_id(h) + o.var_size(h)) for h in hs])
+    H = rng.randn(40, len(cols)) * 30
+    r = rng.randn(40)
+    P0 = o.cov()
+    Pn, dxn = _numpy_update(P0, cols, H, r)
+    v0 = {h: o.var_get(h)[0] for h in ch}
+    o.ekf_update(hs, H, r)
+    P1 = o.cov()
+    assert np.linalg.norm(P1 - Pn) / np.linalg.norm(Pn) < 1e-10
+    assert np.abs(P1 - P1.T).max() == 0.0
+    assert np.linalg.eigvalsh(P1).min() > -1e-12
+    # the mean moved by dx under the update rules (position part is additive)
+    for h in ch:
+        assert np.allclose(o.var_get(h)[0][4:7], v0[h][4:7] + dxn[o.var_id(h) + 3:o.var_id(h) + 6], atol=1e-12)
+    # compress-then-update == update with the uncompressed system (measurement_compress_inplace is lossless for (x+, P+))
+    o2 = ob.OracleContext(S.options)
+    synth.load_scenario_into(o2, S)
+    Hc, rc = o2.measurement_compress_inplace(H, r)
+    assert Hc.shape == (len(cols), len(cols)) and np.abs(np.tril(Hc, -1)).max() < 1e-9 * np.abs(Hc).max()
+    o2.ekf_update(hs, Hc, rc)
+    assert np.linalg.norm(o2.cov() - P1) / np.linalg.norm(P1) < 1e-10
+    for h in ch:
+        assert np.allclose(o2.var_get(h)[0], o.var_get(h)[0], atol=1e-11)
+    # column permutation of (H, H_order) leaves the posterior unchanged
+    o3 = ob.OracleContext(S.options)
+    synth.load_scenario_into(o3, S)
+    perm_h = [hs[2], hs[0], hs[1]]
+    Hp = np.hstack([H[:, 12:18], H[:, 0:6], H[:, 6:12]])
+    o3.ekf_update(perm_h, Hp, r)
+    assert np.linalg.norm(o3.cov() - P1) / np.linalg.norm(P1) < 1e-11
+
+
+def test_nullspace_projection_properties():
+    o = ob.OracleContext(synth.make_scenario("tiny_points").options)
+    rng = np.random.RandomState(9)
+    Hf, Hx, r = rng.randn(20, 3), rng.randn(20, 30), rng.randn(20)
+    Ho, ro = o.nullspace_project_inplace(Hf, Hx, r)
+    assert Ho.shape == (17, 30)
+    Pi = np.eye(20) - Hf @ np.linalg.solve(Hf.T @ Hf, Hf.T)  # projector onto the left nullspace of H_f
+    assert np.allclose(Ho.T @ Ho, Hx.T @ Pi @ Hx, atol=1e-10)
+    assert np.allclose(Ho.T @ ro, Hx.T @ Pi @ r, atol=1e-10)
+    assert abs(ro @ ro - r @ Pi @ r) < 1e-10
+
+
+def test_propagation_phi_matches_numerical_derivative_of_the_mean():
+    """Without FEJ, F = d(x_{k+1} (-) x_hat_{k+1}) / d(error state) for one IMU interval (Propagator.cpp:411-432): checks theta, p, v
+    blocks against finite differences of the discrete mean propagation."""
+    S = synth.make_scenario("tiny_points", seed=1)
+    opt = dict(S.options)
+    opt["do_fej"] = 0
+    opt["use_rk4_integration"] = 0
+    t0 = S.timestamp
+
+    def run(dx):
+        o = ob.OracleContext(opt)
+        synth.load_scenario_into(o, S)
+        v, f = o.var_get(o.handle_imu())
+        vv = v.copy()
+        L.orc_var_update(ob.KIND_IMU, vv.ctypes.data_as(C.c_void_p), _v(dx).ctypes.data_as(C.c_void_p))
+        o.var_set(o.handle_imu(), vv, vv)
+        o.var_set(o.handle_dt(), np.zeros(1), np.zeros(1))
+        o.propagator_set_noise(1e-4, 1e-5, 1e-3, 1e-3, 9.81)
+        o.feed_imu(t0, [0.1, -0.2, 0.15], [0.3, 9.6, 0.5])
+        o.feed_imu(t0 + 0.01, [0.1, -0.2, 0.15], [0.3, 9.6, 0.5])
+        o.feed_imu(t0 + 0.02, [0.1, -0.2, 0.15], [0.3, 9.6, 0.5])
+        _, Phi, Q = o.propagate_and_clone(t0 + 0.01)
+        return o.var_get(o.handle_imu())[0], Phi
+    x0, Phi = run(np.zeros(15))
+    assert np.allclose(Phi[9:15, 9:15], np.eye(6)) and np.allclose(Phi[3:6, 3:6], np.eye(3))
+    h = 1e-6
+    for k in [0, 1, 2, 3, 6, 7, 9, 12]:
+        d = np.zeros(15)
+        d[k] = h
+        x1, _ = run(d)
+        err = np.zeros(15)
+        dR = q2R(x1[:4]) @ q2R(x0[:4]).T  # = exp(-[dth x])
+        err[0:3] = -np.array([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]]) / 2
+        err[3:15] = x1[4:16] - x0[4:16]
+        assert np.allclose(err / h, Phi[:, k], atol=2e-5), (k, np.abs(err / h - Phi[:, k]).max())
+
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name,seed", [("tiny_points", 0), ("tiny_planes", 0), ("small_planes", 1), ("cfg1_euroc_n96", 0)])
+def test_oracle_reproduces_golden_vectors(name, seed, chi2_table):
+    g = np.load(os.path.join(GOLD, "%s_s%d.npz" % (name, seed)))
+    S = synth.make_scenario(name, seed=seed)
+    assert np.array_equal(S.P0, g["P0"]) and np.array_equal(S.uv, g["uv"]), "scenario generator changed: regenerate the goldens"
+    o = ob.OracleContext(S.options)
+    o.set_chi2_table(chi2_table)
+    ch = synth.load_scenario_into(o, S)
+    r = o.msckf_update(synth.feature_batch(S, ch), 1.0, 1.0)
+    assert np.array_equal(r["feat_status"], g["feat_status"]) and np.array_equal(r["plane_status"], g["plane_status"])
+    assert np.allclose(o.cov(), g["P1"], rtol=0, atol=1e-12 * np.abs(g["P1"]).max())
+    assert np.allclose(o.var_get(o.handle_imu())[0], g["imu1"], atol=1e-12)

@@ -170,6 +170,13 @@ typedef struct ovp_updater_options { /* UpdaterOptions.h:38-54 */
 int ovp_msckf_update(ovp_ctx *ctx, const ovp_feature_batch *batch, const ovp_updater_options *opt, int *feat_status,
                      double *feat_chi2, int *plane_status, double *plane_chi2, int *hx_order, int *hx_order_n);
 
+/* UpdaterPlane::init_vio_plane from "plane linearisation points known" on (UpdaterPlane.cpp:297-481): every plane of the batch
+ * that is NOT in the state (ascending id) and has >= 3 features is stacked (Jacobians with sigma_c * const_init_multi),
+ * compressed and handed to StateHelper::initialize with const_init_chi2.  plane_status[i]: 1 initialised, 0 chi2-rejected,
+ * -1 not attempted; new_handles[i]: handle of the new plane variable (or -1).  Features are NOT consumed here: the caller
+ * removes the features of initialised planes from its MSCKF list like UpdaterPlane.cpp:459-475. */
+int ovp_plane_init(ovp_ctx *ctx, const ovp_feature_batch *batch, const ovp_updater_options *opt, int *plane_status, int *new_handles);
+
 /* ---- Multi-GPU sharding of one large update ----------------------------------------------------------- */
 /* Rank-local half: Jacobians, nullspace, chi2 gates and compression of THIS rank's point features against the replicated
  * state; writes the (n+1) x (n+1) lower-triangular factor block [R^T ; z^T] in the canonical column order of the FULL batch

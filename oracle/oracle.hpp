@@ -1503,6 +1503,96 @@ struct UpdaterMSCKF {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// UpdaterPlane::init_vio_plane from "plane linearisation points known" onward (update/UpdaterPlane.cpp:297-481); the
+// RANSAC fit / Ceres refinement before it (:61-293) are upstream of the path, their outputs arrive as inputs.
+// ---------------------------------------------------------------------------------------------------------------
+struct PlaneInitResult {
+  std::vector<std::pair<size_t, int>> plane_status; // (planeid, 1 initialised / 0 rejected)
+  std::vector<int> new_handles;
+};
+struct UpdaterPlaneInit {
+  double sigma_pix = 1.0;
+  Chi2Table chi2tab;
+  PlaneInitResult init_vio_plane(StateP state, std::vector<Feature> &feature_vec, const std::map<size_t, size_t> &feat2plane,
+                                 const std::map<size_t, Mat> &plane_estimates_cp_inG) {
+    PlaneInitResult out;
+    std::map<size_t, std::vector<Feature *>> plane_feats;
+    for (auto &feat : feature_vec) {
+      auto it = feat2plane.find(feat.featid);
+      if (it != feat2plane.end())
+        plane_feats[it->second].push_back(&feat);
+    }
+    for (auto const &planepair : plane_estimates_cp_inG) {
+      size_t planeid = planepair.first;
+      Mat cp_inG = planepair.second;
+      if (plane_feats.find(planeid) == plane_feats.end())
+        continue;
+      if (state->_features_PLANE.find(planeid) != state->_features_PLANE.end())
+        continue; // only planes that are not in the state are initialised (:304)
+      std::vector<Feature *> features = plane_feats.at(planeid);
+      if (features.size() < 3)
+        continue; // assert(features.size() >= 3), :303
+      size_t max_meas_size = 0;
+      for (auto *f : features)
+        max_meas_size += 3 * f->timestamps.size();
+      size_t max_hx_size = state->max_covariance_size();
+      Mat res_big((int)max_meas_size, 1), Hx_big((int)max_meas_size, (int)max_hx_size), Hcp_big((int)max_meas_size, 3);
+      std::unordered_map<Var *, size_t> Hx_mapping;
+      std::vector<VarP> Hx_order_big;
+      size_t ct_jacob = 0, ct_meas = 0;
+      for (auto *feature : features) {
+        Feature feat = *feature;
+        feat.planeid = planeid;
+        feat.cp_FinG = cp_inG;
+        feat.cp_FinG_fej = cp_inG;
+        feat.p_FinG_fej = feat.p_FinG;
+        Mat H_f, H_x, res;
+        std::vector<VarP> Hx_order;
+        double sigma_c = state->_options.const_init_multi * state->_options.sigma_constraint; // :384
+        UpdaterHelper::get_feature_jacobian_full(state, feat, sigma_pix, sigma_c, H_f, H_x, res, Hx_order);
+        assert(H_f.cols() == 6);
+        Mat H_cp = H_f.block(0, 3, H_f.rows(), 3);
+        H_f = H_f.block(0, 0, H_f.rows(), 3);
+        UpdaterPlane::nullspace_project_inplace(H_f, H_x, H_cp, res);
+        size_t ct_hx = 0;
+        for (auto &var : Hx_order) {
+          if (Hx_mapping.find(var.get()) == Hx_mapping.end()) {
+            Hx_mapping.insert({var.get(), ct_jacob});
+            Hx_order_big.push_back(var);
+            ct_jacob += var->size();
+          }
+          Hx_big.setBlock((int)ct_meas, (int)Hx_mapping[var.get()], H_x.block(0, (int)ct_hx, H_x.rows(), var->size()));
+          ct_hx += var->size();
+        }
+        Hcp_big.setBlock((int)ct_meas, 0, H_cp);
+        res_big.setBlock((int)ct_meas, 0, res);
+        ct_meas += res.rows();
+      }
+      res_big.conservativeResize((int)ct_meas, 1);
+      Hx_big.conservativeResize((int)ct_meas, (int)ct_jacob);
+      Hcp_big.conservativeResize((int)ct_meas, 3);
+      UpdaterPlane::measurement_compress_inplace(Hx_big, Hcp_big, res_big);
+      Mat R_big = Mat::Identity(res_big.rows());
+      VarP plane = Var::makeVec(3);
+      for (int i = 0; i < 3; i++) {
+        plane->value[i] = cp_inG(i, 0);
+        plane->fej[i] = cp_inG(i, 0);
+      }
+      if (StateHelper::initialize(state, plane, Hx_order_big, Hx_big, Hcp_big, R_big, res_big, state->_options.const_init_chi2, chi2tab)) {
+        state->reg(plane);
+        state->_features_PLANE.insert({planeid, plane});
+        out.plane_status.push_back({planeid, 1});
+        out.new_handles.push_back(plane->handle);
+      } else {
+        out.plane_status.push_back({planeid, 0});
+        out.new_handles.push_back(-1);
+      }
+    }
+    return out;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 // Propagator (state/Propagator.cpp)
 // ---------------------------------------------------------------------------------------------------------------
 struct ImuData {

@@ -427,6 +427,48 @@ int orc_msckf_update(void *p, int F, const int *meas_offset, const int *meas_clo
   });
 }
 
+// ---- UpdaterPlane::init_vio_plane core ------------------------------------------------------------------------------
+int orc_plane_init(void *p, int F, const int *meas_offset, const int *meas_clone, const float *uv, const double *p_FinG,
+                   const long long *featid, const long long *planeid, int nplanes, const long long *plane_est_ids,
+                   const double *plane_est_cp, double sigma_pix, int *plane_status, int *new_handles) {
+  Ctx *c = (Ctx *)p;
+  return guarded(c, [&] {
+    std::vector<Feature> fv(F);
+    std::map<size_t, size_t> feat2plane;
+    std::unordered_map<Var *, double> clone_ts;
+    for (auto &kv : c->state->_clones_IMU)
+      clone_ts[kv.second.get()] = kv.first;
+    for (int i = 0; i < F; i++) {
+      Feature &f = fv[i];
+      f.featid = (size_t)featid[i];
+      for (int k = meas_offset[i]; k < meas_offset[i + 1]; k++) {
+        f.timestamps.push_back(clone_ts.at(c->state->by_handle.at(meas_clone[k]).get()));
+        f.uvs.push_back(uv[2 * k]);
+        f.uvs.push_back(uv[2 * k + 1]);
+      }
+      f.p_FinG = vec3(p_FinG[3 * i], p_FinG[3 * i + 1], p_FinG[3 * i + 2]);
+      if (planeid[i] != 0)
+        feat2plane[f.featid] = (size_t)planeid[i];
+    }
+    std::map<size_t, Mat> plane_est;
+    for (int i = 0; i < nplanes; i++) {
+      plane_est[(size_t)plane_est_ids[i]] = vec3(plane_est_cp[3 * i], plane_est_cp[3 * i + 1], plane_est_cp[3 * i + 2]);
+      plane_status[i] = -1;
+      new_handles[i] = -1;
+    }
+    UpdaterPlaneInit up;
+    up.sigma_pix = sigma_pix;
+    up.chi2tab = c->chi2;
+    PlaneInitResult r = up.init_vio_plane(c->state, fv, feat2plane, plane_est);
+    for (size_t k = 0; k < r.plane_status.size(); k++)
+      for (int i = 0; i < nplanes; i++)
+        if ((size_t)plane_est_ids[i] == r.plane_status[k].first) {
+          plane_status[i] = r.plane_status[k].second;
+          new_handles[i] = r.new_handles[k];
+        }
+  });
+}
+
 // ---- Propagator -----------------------------------------------------------------------------------------------
 void orc_prop_set(void *p, double sigma_w, double sigma_wb, double sigma_a, double sigma_ab, double gravity_mag) {
   Ctx *c = (Ctx *)p;

@@ -320,6 +320,14 @@ class Context(object):
         self._ck(self.lib.ovp_msckf_update(self.h, C.byref(fb), C.byref(uo), _p(fs), _p(fc), _p(ps), _p(pc), _p(hx), C.byref(hxn)))
         return dict(feat_status=fs, feat_chi2=fc, plane_status=ps[:fb.nplanes], plane_chi2=pc[:fb.nplanes], hx_order=hx[:hxn.value].tolist())
 
+    def plane_init(self, batch, sigma_pix=1.0, chi2_mult=1.0):
+        fb, keep = self._batch_struct(batch)
+        uo = UpdaterOptions(sigma_pix, chi2_mult)
+        npl = max(1, fb.nplanes)
+        ps, nh = np.zeros(npl, dtype=np.int32), np.zeros(npl, dtype=np.int32)
+        self._ck(self.lib.ovp_plane_init(self.h, C.byref(fb), C.byref(uo), _p(ps), _p(nh)))
+        return dict(plane_status=ps[:fb.nplanes], new_handles=nh[:fb.nplanes])
+
     # ---- multi-GPU shard halves ----
     def msckf_shard_columns(self, all_clone_handles):
         ch, n = _i32(all_clone_handles), C.c_int()

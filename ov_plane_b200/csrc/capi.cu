@@ -105,50 +105,6 @@ __global__ void init_grow_kernel(double *P, int ld, int N, int s, const double *
   }
 }
 
-// stand-alone Householder left-nullspace projection on a global-memory matrix (col-major, ld): reflectors from the first
-// nref columns applied to all ncols columns.  One CTA.
-__global__ void __launch_bounds__(256) householder_cols_kernel(double *A, int ld, int rows, int ncols, int nref) {
-  extern __shared__ double vbuf[];
-  __shared__ double s_beta;
-  const int tid = threadIdx.x;
-  for (int j = 0; j < nref; j++) {
-    if (tid < 32) {
-      double s = 0.0;
-      for (int i = j + tid; i < rows; i += 32) {
-        double v = A[(size_t)j * ld + i];
-        s += v * v;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-      double x0 = A[(size_t)j * ld + j];
-      double nrm = sqrt(s);
-      double alpha = (x0 > 0.0) ? -nrm : nrm;
-      double v0 = x0 - alpha;
-      double vtv = s - x0 * x0 + v0 * v0;
-      for (int i = j + tid; i < rows; i += 32) {
-        vbuf[i] = (i == j) ? v0 : A[(size_t)j * ld + i];
-        if (nrm > 0.0)
-          A[(size_t)j * ld + i] = (i == j) ? alpha : 0.0; // the reflected column itself: [alpha; 0]
-      }
-      if (tid == 0)
-        s_beta = (vtv > 0.0 && nrm > 0.0) ? 2.0 / vtv : 0.0;
-    }
-    __syncthreads();
-    const double beta = s_beta;
-    for (int cidx = j + 1 + tid; cidx < ncols; cidx += 256) {
-      double *col = A + (size_t)cidx * ld;
-      double s = 0.0;
-      for (int i = j; i < rows; i++)
-        s += vbuf[i] * col[i];
-      s *= beta;
-      for (int i = j; i < rows; i++)
-        col[i] -= s * vbuf[i];
-    }
-    __syncthreads();
-  }
-}
-
 // UpdaterHelper::get_feature_jacobian_full as a stand-alone kernel: one thread per measurement, output in the reference's
 // layout: H_f rows x (3|6), H_x rows x total_hx in x_order [extrinsics, intrinsics, clones (measurement order), plane]
 struct JacArgs {

@@ -292,6 +292,57 @@ int ovp_initialize_invertible(ovp_ctx *h, int kind, int s, const double *value, 
   return init_invertible_core(c, kind, s, value, fej, tag, c->dcols, n, W, s, sigma2, new_handle);
 }
 
+} // extern "C"
+
+namespace ovp {
+// StateHelper::initialize (StateHelper.cpp:398-487) on a device-staged system W = [H_L (s) | H_R (n) | res] with `rows` rows:
+// s reflectors on H_L (Givens in the reference, :434-446; orthogonal-equivalent), chi2 of the updating portion against the
+// CURRENT covariance with dof = dof_rows (the reference uses the full row count, :471-472), then initialize_invertible and the
+// EKF update with the remaining rows.
+int initialize_core(Ctx *c, int kind, int s, const double *value, const double *fej, int64_t tag, const int *d_cols, int n, double *W,
+                    int ldW, int rows, int dof_rows, double sigma2, double chi2_mult, int do_update, int *accepted, int *new_handle) {
+  *accepted = 0;
+  *new_handle = -1;
+  if (dof_rows >= c->chi2_table_n)
+    return fail(c, OVP_ERR_BAD_ARGS, "initialize: chi2 table too short for %d rows", dof_rows);
+  if (rows - s > c->Rcap)
+    return fail(c, OVP_ERR_CAPACITY, "initialize: %d rows exceed capacity", rows);
+  householder_cols_kernel<<<1, 256, (size_t)rows * sizeof(double), c->stream>>>(W, ldW, rows, s + n + 1, s);
+  c->launches++;
+  const int ru = rows - s;
+  double *dR = c->dvec + 3 * (size_t)c->Rcap;
+  MatView HupT = mv(W + (size_t)s * ldW + s, ldW, 1);
+  const double *d_resup = W + (size_t)(s + n) * ldW + s;
+  double chi2 = 0.0;
+  if (ru > 0) {
+    launch_fill(c, dR, ru, sigma2);
+    int st = ekf_update_core(c, d_cols, n, HupT, ru, d_resup, dR, -1.0, nullptr, c->dscal, false); // dry run: chi2 only (:464-475)
+    if (st)
+      return st;
+    OVP_CUDA(cudaMemcpyAsync(&chi2, c->dscal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    OVP_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  int st = check_status_flags(c);
+  if (st)
+    return st;
+  if (chi2 > chi2_mult * c->chi2_table[dof_rows])
+    return OVP_OK; // accepted = 0, state untouched
+  st = init_invertible_core(c, kind, s, value, fej, tag, d_cols, n, W, ldW, sigma2, new_handle);
+  if (st)
+    return st;
+  *accepted = 1;
+  if (ru > 0 && do_update) {
+    st = ekf_update_core(c, d_cols, n, HupT, ru, d_resup, dR, -1.0, nullptr, nullptr);
+    if (st)
+      return st;
+    return check_status_flags(c);
+  }
+  return OVP_OK;
+}
+} // namespace ovp
+
+extern "C" {
+
 int ovp_initialize(ovp_ctx *h, int kind, int s, const double *value, const double *fej, int64_t tag, const int *handles, int k,
                    const double *H_R, const double *H_L, const double *res, int rows, double sigma2, double chi2_mult, int do_update,
                    int *accepted, int *new_handle) {
@@ -302,52 +353,67 @@ int ovp_initialize(ovp_ctx *h, int kind, int s, const double *value, const doubl
     return fail(c, OVP_ERR_BAD_ARGS, "initialize: bad sizes (s=%d rows=%d)", s, rows);
   if ((kind == OVP_KIND_LANDMARK && c->slam.count(tag)) || (kind == OVP_KIND_VEC && c->planes.count(tag)))
     return fail(c, OVP_ERR_ALREADY_IN_STATE, "initialize: variable already in the state (StateHelper.cpp:403-407)");
-  if (rows >= c->chi2_table_n)
-    return fail(c, OVP_ERR_BAD_ARGS, "initialize: chi2 table too short for %d rows", rows);
   int n = 0;
   int st = upload_cols(c, handles, k, 0, &n);
   if (st)
     return st;
-  if (rows - s > c->Rcap)
-    return fail(c, OVP_ERR_CAPACITY, "initialize: %d rows exceed capacity", rows);
   double *W;
   st = stage_init_system(c, H_R, H_L, res, rows, n, s, &W);
   if (st)
     return st;
-  // separate the system with s reflectors on H_L (Givens in the reference, StateHelper.cpp:434-446; orthogonal-equivalent)
-  householder_cols_kernel<<<1, 256, (size_t)rows * sizeof(double), c->stream>>>(W, rows, rows, s + n + 1, s);
-  c->launches++;
-  const int ru = rows - s;
-  double *dR = c->dvec + 3 * (size_t)c->Rcap;
-  if (ru > 0) {
-    launch_fill(c, dR, ru, sigma2);
-    // chi2 of the updating portion against the CURRENT covariance (dry run), :464-475
-    st = ekf_update_core(c, c->dcols, n, mv(W + (size_t)s * rows + s, rows, 1), ru, W + (size_t)(s + n) * rows + s, dR, -1.0, nullptr,
-                         c->dscal, false);
+  return initialize_core(c, kind, s, value, fej, tag, c->dcols, n, W, rows, rows, rows, sigma2, chi2_mult, do_update, accepted, new_handle);
+}
+
+// UpdaterPlane::init_vio_plane from "plane linearisation points known" on (UpdaterPlane.cpp:297-481): for every plane of the
+// batch that is NOT in the state (ascending id, std::map order) and has >= 3 features: per-feature Jacobians with
+// sigma_c * const_init_multi (:384), H_cp split off H_f (:388-390), left-nullspace projection, stacking, compression and
+// StateHelper::initialize(plane Vec(3), ..., const_init_chi2) (:436-446).  plane_status[i]: 1 initialised, 0 chi2-rejected,
+// -1 not attempted; new_handles[i]: handle of the new plane variable or -1.
+int ovp_plane_init(ovp_ctx *h, const ovp_feature_batch *batch, const ovp_updater_options *opt, int *plane_status, int *new_handles) {
+  Ctx *c = &h->c;
+  if (!batch || !opt || !batch->plane_cp)
+    return fail(c, OVP_ERR_BAD_ARGS, "plane_init: null batch / options / plane_cp");
+  std::vector<std::pair<int64_t, int>> ps;
+  for (int i = 0; i < batch->nplanes; i++) {
+    ps.push_back({batch->plane_ids[i], i});
+    plane_status[i] = -1;
+    new_handles[i] = -1;
+  }
+  std::sort(ps.begin(), ps.end());
+  for (auto &pp : ps) {
+    const int64_t pid = pp.first;
+    if (pid == 0 || c->planes.count(pid))
+      continue;
+    int nf = 0;
+    for (int f = 0; f < batch->F; f++)
+      nf += batch->planeid[f] == pid;
+    if (nf < 3)
+      continue; // assert(features.size() >= 3), UpdaterPlane.cpp:303
+    MsckfExtra ex;
+    ex.only_plane_id = pid;
+    ex.sigma_c_scale = c->opt.const_init_multi;
+    int st = msckf_prepare(c, batch, opt, &ex);
     if (st)
       return st;
-  }
-  double chi2 = 0.0;
-  if (ru > 0) {
-    OVP_CUDA(cudaMemcpyAsync(&chi2, c->dscal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    OVP_CUDA(cudaStreamSynchronize(c->stream));
-  }
-  st = check_status_flags(c);
-  if (st)
-    return st;
-  double chi2_check = c->chi2_table[rows]; // dof = full rows, not rows - s (:471-472)
-  if (chi2 > chi2_mult * chi2_check)
-    return OVP_OK; // accepted = 0, state untouched
-  st = init_invertible_core(c, kind, s, value, fej, tag, c->dcols, n, W, rows, sigma2, new_handle);
-  if (st)
-    return st;
-  *accepted = 1;
-  if (ru > 0 && do_update) {
-    st = ekf_update_core(c, c->dcols, n, mv(W + (size_t)s * rows + s, rows, 1), ru, W + (size_t)(s + n) * rows + s, dR, -1.0, nullptr,
-                         nullptr);
+    c->use_graphs = false; // one-shot system
+    st = msckf_launch(c);
+    c->use_graphs = true;
     if (st)
       return st;
-    return check_status_flags(c);
+    int rowsW, ncx, rows_ref;
+    const int *d_cols;
+    st = msckf_last_W(c, &rowsW, &ncx, &rows_ref, &d_cols);
+    if (st)
+      return st;
+    if (rowsW < 3)
+      continue;
+    const double *cp = batch->plane_cp + 3 * pp.second;
+    int acc = 0, nh = -1;
+    st = initialize_core(c, OVP_KIND_VEC, 3, cp, cp, pid, d_cols, ncx, c->dHT, c->Rcap, rowsW, rows_ref, 1.0, c->opt.const_init_chi2, 1, &acc, &nh);
+    if (st)
+      return st;
+    plane_status[pp.second] = acc;
+    new_handles[pp.second] = nh;
   }
   return OVP_OK;
 }

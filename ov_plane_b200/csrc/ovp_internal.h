@@ -168,7 +168,10 @@ int check_status_flags(Ctx *c);
 struct MsckfExtra {
   const std::vector<int> *forced_cols = nullptr;
   double *d_export = nullptr;
+  int64_t only_plane_id = 0;   // init_vio_plane: build the W system of this (out-of-state) plane only and stop
+  double sigma_c_scale = 0.0;  // > 0: multiply sigma_constraint (const_init_multi)
 };
+int msckf_last_W(Ctx *c, int *rowsW, int *ncx, int *rows_ref, const int **d_cols);
 int msckf_update_impl(Ctx *c, const ovp_feature_batch *batch, const ovp_updater_options *opt, int *feat_status, double *feat_chi2,
                       int *plane_status, double *plane_chi2, int *hx_order, int *hx_order_n, const MsckfExtra *extra = nullptr);
 

@@ -324,3 +324,18 @@ def feature_batch(S, clone_handles, sel=None):
         p_FinG_original=np.ascontiguousarray(S.p_FinG_original[idx], dtype=np.float64),
         featid=np.ascontiguousarray(S.featid[idx], dtype=np.int64), planeid=np.ascontiguousarray(S.planeid[idx], dtype=np.int64),
         plane_ids=np.ascontiguousarray(S.plane_ids, dtype=np.int64), plane_cp=np.ascontiguousarray(S.plane_cp, dtype=np.float64))
+
+
+def drop_planes_from_state(S):
+    """Variant of a scenario whose planes are NOT state variables (fresh planes: MSCKF update with the plane projected away,
+    UpdaterMSCKF.cpp:601-604, and plane initialisation, UpdaterPlane.cpp:297-481).  Returns the removed (id, cp, cp_fej) list."""
+    planes = S.planes
+    drop = set()
+    for pid, _, _ in planes:
+        b = S.ids["plane%d" % pid]
+        drop.update(range(b, b + 3))
+    keep = [i for i in range(S.N) if i not in drop]
+    S.P0 = np.ascontiguousarray(S.P0[np.ix_(keep, keep)])
+    S.N = len(keep)
+    S.planes = []
+    return planes

@@ -258,6 +258,14 @@ class OracleContext(object):
             timers[:] = t4
         return dict(feat_status=fs, feat_chi2=fc, plane_status=ps[:npl], plane_chi2=pc[:npl], hx_order=hx[:hxn.value].tolist())
 
+    def plane_init(self, b, sigma_pix=1.0):
+        F, npl = int(b["F"]), len(b["plane_ids"])
+        ps, nh = np.zeros(max(1, npl), dtype=np.int32), np.zeros(max(1, npl), dtype=np.int32)
+        arrs = [np.ascontiguousarray(b[k]) for k in ("meas_offset", "meas_clone", "uv", "p_FinG", "featid", "planeid", "plane_ids", "plane_cp")]
+        self._ck(self.lib.orc_plane_init(self.h, F, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(arrs[4]), _p(arrs[5]), npl,
+                                         _p(arrs[6]), _p(arrs[7]), C.c_double(sigma_pix), _p(ps), _p(nh)))
+        return dict(plane_status=ps[:npl], new_handles=nh[:npl])
+
     # ---- Propagator ----
     def propagator_set_noise(self, sigma_w, sigma_wb, sigma_a, sigma_ab, gravity_mag=9.81):
         self.lib.orc_prop_set(self.h, C.c_double(sigma_w), C.c_double(sigma_wb), C.c_double(sigma_a), C.c_double(sigma_ab),

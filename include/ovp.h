@@ -177,6 +177,26 @@ int ovp_msckf_update(ovp_ctx *ctx, const ovp_feature_batch *batch, const ovp_upd
  * removes the features of initialised planes from its MSCKF list like UpdaterPlane.cpp:459-475. */
 int ovp_plane_init(ovp_ctx *ctx, const ovp_feature_batch *batch, const ovp_updater_options *opt, int *plane_status, int *new_handles);
 
+/* ---- UpdaterSLAM (update/UpdaterSLAM.cpp) — GLOBAL_3D landmarks, mono camera ----------------------------------------- */
+/* UpdaterSLAM::update from "calculate the max possible measurement size" on (:389-735): per landmark feature
+ * get_feature_jacobian_full with the landmark (and its in-state plane, when use_plane_constraint and
+ * _features_SLAM_to_PLANE allows it) as state columns, chi2 gate against the marginal covariance, on failure WITH a plane
+ * one retry without it (:547-609), then ONE EKF update with the stack of the accepted blocks (R = I).
+ * planeid[f]: the feat2plane entry of the feature (0 = none).  feat_status[f]: 1 accepted (plane constraint included when the
+ * feature had one), 3 accepted after dropping the plane constraint, 0 rejected (landmark flagged should_marg).  */
+int ovp_slam_update(ovp_ctx *ctx, int F, const int *meas_offset, const int *meas_clone, const float *uv, const int64_t *featid,
+                    const int64_t *planeid, const ovp_updater_options *opt, int use_plane_constraint, int *feat_status,
+                    double *feat_chi2);
+/* UpdaterSLAM::delayed_init from "8. Finally, initialize" on (:225-372): per feature, in order, Jacobians at p_FinG (FEJ =
+ * value), StateHelper::initialize(Landmark, ..., chi2_multipler); a failure WITH a plane retries without it from
+ * p_FinG_original (:310-359).  feat_status[f]: 1 / 3 as above, 0 not initialised; new_handles[f]: landmark handle or -1. */
+int ovp_slam_delayed_init(ovp_ctx *ctx, int F, const int *meas_offset, const int *meas_clone, const float *uv, const double *p_FinG,
+                          const double *p_FinG_original, const int64_t *featid, const int64_t *planeid,
+                          const ovp_updater_options *opt, int use_plane_constraint, int *feat_status, int *new_handles);
+int ovp_slam_handle(ovp_ctx *ctx, int64_t featid);       /* State::_features_SLAM lookup; -1 = absent */
+int ovp_slam_should_marg(ovp_ctx *ctx, int64_t featid);  /* Landmark::should_marg (1/0), -1 = absent */
+int64_t ovp_slam_plane_of(ovp_ctx *ctx, int64_t featid); /* State::_features_SLAM_to_PLANE entry, -1 = no entry */
+
 /* ---- Multi-GPU sharding of one large update ----------------------------------------------------------- */
 /* Rank-local half: Jacobians, nullspace, chi2 gates and compression of THIS rank's point features against the replicated
  * state; writes the (n+1) x (n+1) lower-triangular factor block [R^T ; z^T] in the canonical column order of the FULL batch

@@ -1593,6 +1593,178 @@ struct UpdaterPlaneInit {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// UpdaterSLAM (update/UpdaterSLAM.cpp): update (:376-682) from "measurements cleaned" on, delayed_init (:205-364) from
+// "triangulated (and plane-refined)" on.  GLOBAL_3D landmarks, no ArUco.
+// ---------------------------------------------------------------------------------------------------------------
+struct SlamOptions {
+  double sigma_pix = 1.0, chi2_multipler = 1.0;
+  bool use_plane_constraint_slamu = true, use_plane_constraint_slamd = true;
+};
+struct UpdaterSLAM {
+  SlamOptions opt;
+  Chi2Table chi2tab;
+
+  // returns per feature: 1 accepted (with its plane constraint if any), 3 accepted after dropping the plane constraint, 0 rejected
+  std::vector<int> update(StateP state, std::vector<Feature> &feature_vec, const std::map<size_t, size_t> &feat2plane,
+                          std::vector<double> *chi2_out = nullptr) {
+    std::vector<int> status(feature_vec.size(), 0);
+    if (chi2_out)
+      chi2_out->assign(feature_vec.size(), NAN);
+    if (feature_vec.empty())
+      return status;
+    size_t max_meas_size = 0;
+    for (auto &f : feature_vec)
+      max_meas_size += 3 * f.timestamps.size();
+    size_t max_hx_size = state->max_covariance_size();
+    Mat res_big((int)max_meas_size, 1), Hx_big((int)max_meas_size, (int)max_hx_size);
+    std::unordered_map<Var *, size_t> Hx_mapping;
+    std::vector<VarP> Hx_order_big;
+    size_t ct_jacob = 0, ct_meas = 0;
+    for (size_t fi = 0; fi < feature_vec.size(); fi++) {
+      Feature feat = feature_vec[fi];
+      VarP landmark = state->_features_SLAM.at(feat.featid);
+      feat.planeid = 0;
+      auto itp = feat2plane.find(feat.featid);
+      if (opt.use_plane_constraint_slamu && itp != feat2plane.end() && state->_features_PLANE.count(itp->second)) {
+        auto its = state->_features_SLAM_to_PLANE.find(feat.featid);
+        if (its == state->_features_SLAM_to_PLANE.end() || its->second != 0) {
+          feat.planeid = itp->second;
+          feat.cp_FinG = state->_features_PLANE.at(itp->second)->vecvalue(false);
+          feat.cp_FinG_fej = state->_features_PLANE.at(itp->second)->vecvalue(true);
+        }
+      }
+      feat.p_FinG = landmark->vecvalue(false);
+      feat.p_FinG_fej = landmark->vecvalue(true);
+      Mat H_f, H_x, res;
+      std::vector<VarP> Hx_order;
+      auto build = [&](Mat &H_xf, std::vector<VarP> &Hxf_order, double &chi2) {
+        UpdaterHelper::get_feature_jacobian_full(state, feat, opt.sigma_pix, state->_options.sigma_constraint, H_f, H_x, res, Hx_order);
+        H_xf = H_x;
+        H_xf.conservativeResize(H_x.rows(), H_x.cols() + H_f.cols());
+        H_xf.setBlock(0, H_x.cols(), H_f);
+        Hxf_order = Hx_order;
+        Hxf_order.push_back(landmark);
+        Mat P_marg = StateHelper::get_marginal_covariance(state, Hxf_order);
+        Mat S = H_xf * P_marg * H_xf.T();
+        for (int i = 0; i < S.rows(); i++)
+          S(i, i) += 1.0;
+        Mat L;
+        if (!chol_lower(S, L))
+          ref_exit("UpdaterSLAM: S not positive definite");
+        Mat y = res;
+        chol_solve_inplace(L, y);
+        chi2 = dot(res, y);
+      };
+      Mat H_xf;
+      std::vector<VarP> Hxf_order;
+      double chi2;
+      build(H_xf, Hxf_order, chi2);
+      double chi2_check = chi2tab.at(res.rows());
+      int st = 1;
+      if (feat.planeid != 0 && chi2 > opt.chi2_multipler * chi2_check) {
+        feat.planeid = 0; // fallback without the plane (:547-609)
+        state->_features_SLAM_to_PLANE[feat.featid] = 0;
+        build(H_xf, Hxf_order, chi2);
+        chi2_check = chi2tab.at(res.rows());
+        st = 3;
+        if (chi2 > opt.chi2_multipler * chi2_check) {
+          landmark->should_marg = true;
+          status[fi] = 0;
+          if (chi2_out)
+            (*chi2_out)[fi] = chi2;
+          continue;
+        }
+      } else if (chi2 > opt.chi2_multipler * chi2_check) {
+        landmark->should_marg = true;
+        status[fi] = 0;
+        if (chi2_out)
+          (*chi2_out)[fi] = chi2;
+        continue;
+      }
+      if (chi2_out)
+        (*chi2_out)[fi] = chi2;
+      if (feat.planeid != 0)
+        state->_features_SLAM_to_PLANE[feat.featid] = feat.planeid;
+      status[fi] = st;
+      size_t ct_hx = 0;
+      for (auto &var : Hxf_order) {
+        if (Hx_mapping.find(var.get()) == Hx_mapping.end()) {
+          Hx_mapping.insert({var.get(), ct_jacob});
+          Hx_order_big.push_back(var);
+          ct_jacob += var->size();
+        }
+        Hx_big.setBlock((int)ct_meas, (int)Hx_mapping[var.get()], H_xf.block(0, (int)ct_hx, H_xf.rows(), var->size()));
+        ct_hx += var->size();
+      }
+      res_big.setBlock((int)ct_meas, 0, res);
+      ct_meas += res.rows();
+    }
+    if (ct_meas < 1)
+      return status;
+    res_big.conservativeResize((int)ct_meas, 1);
+    Hx_big.conservativeResize((int)ct_meas, (int)ct_jacob);
+    Mat R_big = Mat::Identity((int)ct_meas);
+    StateHelper::EKFUpdate(state, Hx_order_big, Hx_big, res_big, R_big); // no compression (:672-673)
+    return status;
+  }
+
+  // returns per feature: 1 initialised (with plane constraint if any), 3 initialised after dropping the plane, 0 failed
+  std::vector<int> delayed_init(StateP state, std::vector<Feature> &feature_vec, const std::map<size_t, size_t> &feat2plane,
+                                std::vector<int> *handles_out = nullptr) {
+    std::vector<int> status(feature_vec.size(), 0);
+    if (handles_out)
+      handles_out->assign(feature_vec.size(), -1);
+    for (size_t fi = 0; fi < feature_vec.size(); fi++) {
+      Feature feat = feature_vec[fi];
+      feat.planeid = 0;
+      auto itp = feat2plane.find(feat.featid);
+      if (opt.use_plane_constraint_slamd && itp != feat2plane.end() && state->_features_PLANE.count(itp->second)) {
+        auto its = state->_features_SLAM_to_PLANE.find(feat.featid);
+        if (its == state->_features_SLAM_to_PLANE.end() || its->second != 0) {
+          feat.planeid = itp->second;
+          feat.cp_FinG = state->_features_PLANE.at(itp->second)->vecvalue(false);
+          feat.cp_FinG_fej = state->_features_PLANE.at(itp->second)->vecvalue(true);
+        }
+      }
+      feat.p_FinG_fej = feat.p_FinG;
+      auto attempt = [&]() -> bool {
+        Mat H_f, H_x, res;
+        std::vector<VarP> Hx_order;
+        UpdaterHelper::get_feature_jacobian_full(state, feat, opt.sigma_pix, state->_options.sigma_constraint, H_f, H_x, res, Hx_order);
+        VarP landmark = Var::makeLandmark(3);
+        landmark->featid = feat.featid;
+        for (int i = 0; i < 3; i++) {
+          landmark->value[i] = feat.p_FinG(i, 0);
+          landmark->fej[i] = feat.p_FinG_fej(i, 0);
+        }
+        Mat R = Mat::Identity(res.rows());
+        if (StateHelper::initialize(state, landmark, Hx_order, H_x, H_f, R, res, opt.chi2_multipler, chi2tab)) {
+          state->reg(landmark);
+          state->_features_SLAM.insert({feat.featid, landmark});
+          if (handles_out)
+            (*handles_out)[fi] = landmark->handle;
+          return true;
+        }
+        return false;
+      };
+      if (attempt()) {
+        status[fi] = 1;
+        if (feat.planeid != 0)
+          state->_features_SLAM_to_PLANE[feat.featid] = feat.planeid;
+      } else if (feat.planeid != 0) {
+        feat.planeid = 0; // fallback (:310-359): no plane, position before the plane refinement
+        state->_features_SLAM_to_PLANE[feat.featid] = 0;
+        feat.p_FinG = feat.p_FinG_original;
+        feat.p_FinG_fej = feat.p_FinG_original;
+        if (attempt())
+          status[fi] = 3;
+      }
+    }
+    return status;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 // Propagator (state/Propagator.cpp)
 // ---------------------------------------------------------------------------------------------------------------
 struct ImuData {

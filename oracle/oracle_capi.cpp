@@ -469,6 +469,85 @@ int orc_plane_init(void *p, int F, const int *meas_offset, const int *meas_clone
   });
 }
 
+// ---- UpdaterSLAM cores -----------------------------------------------------------------------------------------------
+static void fill_features(Ctx *c, int F, const int *meas_offset, const int *meas_clone, const float *uv, const double *p_FinG,
+                          const double *p_FinG_original, const long long *featid, const long long *planeid, std::vector<Feature> &fv,
+                          std::map<size_t, size_t> &feat2plane) {
+  std::unordered_map<Var *, double> clone_ts;
+  for (auto &kv : c->state->_clones_IMU)
+    clone_ts[kv.second.get()] = kv.first;
+  fv.resize(F);
+  for (int i = 0; i < F; i++) {
+    Feature &f = fv[i];
+    f.featid = (size_t)featid[i];
+    for (int k = meas_offset[i]; k < meas_offset[i + 1]; k++) {
+      f.timestamps.push_back(clone_ts.at(c->state->by_handle.at(meas_clone[k]).get()));
+      f.uvs.push_back(uv[2 * k]);
+      f.uvs.push_back(uv[2 * k + 1]);
+    }
+    if (p_FinG)
+      f.p_FinG = vec3(p_FinG[3 * i], p_FinG[3 * i + 1], p_FinG[3 * i + 2]);
+    if (p_FinG_original)
+      f.p_FinG_original = vec3(p_FinG_original[3 * i], p_FinG_original[3 * i + 1], p_FinG_original[3 * i + 2]);
+    if (planeid[i] != 0)
+      feat2plane[f.featid] = (size_t)planeid[i];
+  }
+}
+int orc_slam_update(void *p, int F, const int *meas_offset, const int *meas_clone, const float *uv, const long long *featid,
+                    const long long *planeid, double sigma_pix, double chi2_mult, int *feat_status, double *feat_chi2) {
+  Ctx *c = (Ctx *)p;
+  return guarded(c, [&] {
+    std::vector<Feature> fv;
+    std::map<size_t, size_t> f2p;
+    fill_features(c, F, meas_offset, meas_clone, uv, nullptr, nullptr, featid, planeid, fv, f2p);
+    UpdaterSLAM up;
+    up.opt.sigma_pix = sigma_pix;
+    up.opt.chi2_multipler = chi2_mult;
+    up.chi2tab = c->chi2;
+    std::vector<double> chi;
+    std::vector<int> st = up.update(c->state, fv, f2p, &chi);
+    for (int i = 0; i < F; i++) {
+      feat_status[i] = st[i];
+      if (feat_chi2)
+        feat_chi2[i] = chi[i];
+    }
+  });
+}
+int orc_slam_delayed_init(void *p, int F, const int *meas_offset, const int *meas_clone, const float *uv, const double *p_FinG,
+                          const double *p_FinG_original, const long long *featid, const long long *planeid, double sigma_pix,
+                          double chi2_mult, int *feat_status, int *new_handles) {
+  Ctx *c = (Ctx *)p;
+  return guarded(c, [&] {
+    std::vector<Feature> fv;
+    std::map<size_t, size_t> f2p;
+    fill_features(c, F, meas_offset, meas_clone, uv, p_FinG, p_FinG_original, featid, planeid, fv, f2p);
+    UpdaterSLAM up;
+    up.opt.sigma_pix = sigma_pix;
+    up.opt.chi2_multipler = chi2_mult;
+    up.chi2tab = c->chi2;
+    std::vector<int> hs;
+    std::vector<int> st = up.delayed_init(c->state, fv, f2p, &hs);
+    for (int i = 0; i < F; i++) {
+      feat_status[i] = st[i];
+      new_handles[i] = hs[i];
+    }
+  });
+}
+int orc_marginalize_slam(void *p) {
+  Ctx *c = (Ctx *)p;
+  return guarded(c, [&] { StateHelper::marginalize_slam(c->state); });
+}
+int orc_slam_handle(void *p, long long featid) {
+  Ctx *c = (Ctx *)p;
+  auto it = c->state->_features_SLAM.find((size_t)featid);
+  return it == c->state->_features_SLAM.end() ? -1 : it->second->handle;
+}
+int orc_slam_should_marg(void *p, long long featid) {
+  Ctx *c = (Ctx *)p;
+  auto it = c->state->_features_SLAM.find((size_t)featid);
+  return it == c->state->_features_SLAM.end() ? -1 : (it->second->should_marg ? 1 : 0);
+}
+
 // ---- Propagator -----------------------------------------------------------------------------------------------
 void orc_prop_set(void *p, double sigma_w, double sigma_wb, double sigma_a, double sigma_ab, double gravity_mag) {
   Ctx *c = (Ctx *)p;

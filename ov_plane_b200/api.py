@@ -48,6 +48,7 @@ def load_library():
     lib.ovp_get_timestamp.restype = C.c_double
     lib.ovp_launch_count.restype = C.c_int64
     lib.ovp_stream.restype = C.c_void_p
+    lib.ovp_slam_plane_of.restype = C.c_int64
     return lib
 
 
@@ -327,6 +328,41 @@ class Context(object):
         ps, nh = np.zeros(npl, dtype=np.int32), np.zeros(npl, dtype=np.int32)
         self._ck(self.lib.ovp_plane_init(self.h, C.byref(fb), C.byref(uo), _p(ps), _p(nh)))
         return dict(plane_status=ps[:fb.nplanes], new_handles=nh[:fb.nplanes])
+
+    # ---- UpdaterSLAM ----
+    def slam_update(self, b, sigma_pix=1.0, chi2_mult=1.0, use_plane_constraint=True):
+        F = int(b["F"])
+        uo = UpdaterOptions(sigma_pix, chi2_mult)
+        fs, fc = np.zeros(max(1, F), dtype=np.int32), np.zeros(max(1, F))
+        mo, mc = _i32(b["meas_offset"]), _i32(b["meas_clone"])
+        uv = np.ascontiguousarray(b["uv"], dtype=np.float32)
+        fid = np.ascontiguousarray(b["featid"], dtype=np.int64)
+        pid = np.ascontiguousarray(b["planeid"], dtype=np.int64)
+        self._ck(self.lib.ovp_slam_update(self.h, F, _p(mo), _p(mc), _p(uv), _p(fid), _p(pid), C.byref(uo), int(bool(use_plane_constraint)),
+                                          _p(fs), _p(fc)))
+        return dict(feat_status=fs[:F], feat_chi2=fc[:F])
+
+    def slam_delayed_init(self, b, sigma_pix=1.0, chi2_mult=1.0, use_plane_constraint=True):
+        F = int(b["F"])
+        uo = UpdaterOptions(sigma_pix, chi2_mult)
+        fs, nh = np.zeros(max(1, F), dtype=np.int32), np.zeros(max(1, F), dtype=np.int32)
+        mo, mc = _i32(b["meas_offset"]), _i32(b["meas_clone"])
+        uv = np.ascontiguousarray(b["uv"], dtype=np.float32)
+        pf, pfo = _f64(b["p_FinG"]), _f64(b["p_FinG_original"])
+        fid = np.ascontiguousarray(b["featid"], dtype=np.int64)
+        pid = np.ascontiguousarray(b["planeid"], dtype=np.int64)
+        self._ck(self.lib.ovp_slam_delayed_init(self.h, F, _p(mo), _p(mc), _p(uv), _p(pf), _p(pfo), _p(fid), _p(pid), C.byref(uo),
+                                                int(bool(use_plane_constraint)), _p(fs), _p(nh)))
+        return dict(feat_status=fs[:F], new_handles=nh[:F])
+
+    def slam_handle(self, featid):
+        return self.lib.ovp_slam_handle(self.h, C.c_int64(int(featid)))
+
+    def slam_should_marg(self, featid):
+        return self.lib.ovp_slam_should_marg(self.h, C.c_int64(int(featid)))
+
+    def slam_plane_of(self, featid):
+        return int(self.lib.ovp_slam_plane_of(self.h, C.c_int64(int(featid))))
 
     # ---- multi-GPU shard halves ----
     def msckf_shard_columns(self, all_clone_handles):

@@ -113,6 +113,7 @@ struct JacArgs {
   const float *uv;
   double pf[3], pf_fej[3];
   int has_plane, plane_in_state;
+  int plane_handle; // >= 0: linearisation points of the plane come from the device value / fej tables
   double cp[3], cp_fej[3];
   const double *val, *fej;
   int h_calib, h_intr;
@@ -157,7 +158,9 @@ __global__ void jacobian_only_kernel(JacArgs a) {
   }
   if (a.has_plane) {
     double pr, pHf[3], pHcp[3];
-    plane_row(a.pf, a.pf_fej, a.cp, a.cp_fej, a.do_fej, a.white_c, pr, pHf, pHcp);
+    const double *cp = a.plane_handle >= 0 ? a.val + (size_t)a.plane_handle * OVP_VAL_STRIDE : a.cp;
+    const double *cpf = a.plane_handle >= 0 ? a.fej + (size_t)a.plane_handle * OVP_VAL_STRIDE : a.cp_fej;
+    plane_row(a.pf, a.pf_fej, cp, cpf, a.do_fej, a.white_c, pr, pHf, pHcp);
     int r = 2 * a.m + k;
     for (int j = 0; j < 3; j++) {
       a.Hf[(size_t)j * ld + r] = pHf[j];

@@ -521,10 +521,14 @@ int ovp_merge_planes_and_marginalize(ovp_ctx *h, const int64_t *f2p_feat, const 
 }
 
 // ---- stateless helpers -----------------------------------------------------------------------------------------------
-int ovp_feature_jacobian_full(ovp_ctx *h, int m, const int *clone_handles, const float *uv, const double *p_FinG, const double *p_FinG_fej,
-                              int64_t planeid, const double *cp, const double *cp_fej, double sigma_px, double sigma_c, double *H_f,
-                              int *hf_cols, double *H_x, int *hx_cols, double *res, int *rows_out, int *x_order, int *x_order_n) {
-  Ctx *c = &h->c;
+} // extern "C"
+namespace ovp {
+// get_feature_jacobian_full of ONE feature staged on the device in the layout StateHelper::initialize wants:
+// d_stage = [H_f (rows x hfc) | H_x (rows x hxc) | res (rows)], all with leading dimension `rows`.
+// plane_handle >= 0: plane in the state (its values come from the device tables); otherwise cp / cp_fej (may be null: no plane).
+static int stage_feature_jacobian(Ctx *c, int m, const int *clone_handles, const float *uv, const double *p_FinG, const double *p_FinG_fej,
+                                  bool has_plane, int plane_handle, const double *cp, const double *cp_fej, double sigma_px, double sigma_c,
+                                  int *rows_out, int *hfc_out, int *hxc_out) {
   if (m < 1 || m > 64)
     return fail(c, OVP_ERR_BAD_ARGS, "feature_jacobian_full: m=%d not in 1..64", m);
   for (int i = 0; i < m; i++) {
@@ -534,8 +538,7 @@ int ovp_feature_jacobian_full(ovp_ctx *h, int m, const int *clone_handles, const
       if (clone_handles[j] == clone_handles[i])
         return fail(c, OVP_ERR_BAD_ARGS, "feature_jacobian_full: duplicate clone (mono camera assumed)");
   }
-  const bool has_plane = planeid != 0;
-  const bool in_state = has_plane && c->planes.count(planeid);
+  const bool in_state = has_plane && plane_handle >= 0;
   const int ncal = (c->opt.do_calib_camera_pose ? 6 : 0) + (c->opt.do_calib_camera_intrinsics ? 8 : 0);
   const int rows = has_plane ? 3 * m : 2 * m;
   const int hfc = 3 + ((has_plane && !in_state) ? 3 : 0);
@@ -556,11 +559,12 @@ int ovp_feature_jacobian_full(ovp_ctx *h, int m, const int *clone_handles, const
   for (int i = 0; i < 3; i++) {
     a.pf[i] = p_FinG[i];
     a.pf_fej[i] = p_FinG_fej[i];
-    a.cp[i] = has_plane ? cp[i] : 0.0;
-    a.cp_fej[i] = has_plane ? cp_fej[i] : 0.0;
+    a.cp[i] = (has_plane && cp) ? cp[i] : 0.0;
+    a.cp_fej[i] = (has_plane && cp_fej) ? cp_fej[i] : 0.0;
   }
   a.has_plane = has_plane;
   a.plane_in_state = in_state;
+  a.plane_handle = (in_state && !cp) ? plane_handle : -1;
   a.val = c->d_val;
   a.fej = c->d_fej;
   a.h_calib = c->h_calib;
@@ -578,6 +582,28 @@ int ovp_feature_jacobian_full(ovp_ctx *h, int m, const int *clone_handles, const
   a.hx_cols = hxc;
   jacobian_only_kernel<<<1, 64, 0, c->stream>>>(a);
   c->launches++;
+  *rows_out = rows;
+  *hfc_out = hfc;
+  *hxc_out = hxc;
+  return OVP_OK;
+}
+} // namespace ovp
+extern "C" {
+
+int ovp_feature_jacobian_full(ovp_ctx *h, int m, const int *clone_handles, const float *uv, const double *p_FinG, const double *p_FinG_fej,
+                              int64_t planeid, const double *cp, const double *cp_fej, double sigma_px, double sigma_c, double *H_f,
+                              int *hf_cols, double *H_x, int *hx_cols, double *res, int *rows_out, int *x_order, int *x_order_n) {
+  Ctx *c = &h->c;
+  const bool has_plane = planeid != 0;
+  const bool in_state = has_plane && c->planes.count(planeid);
+  int rows, hfc, hxc;
+  int st = stage_feature_jacobian(c, m, clone_handles, uv, p_FinG, p_FinG_fej, has_plane, in_state ? c->planes[planeid] : -1, cp, cp_fej,
+                                  sigma_px, sigma_c, &rows, &hfc, &hxc);
+  if (st)
+    return st;
+  struct {
+    double *Hf, *Hx, *res;
+  } a = {c->d_stage, c->d_stage + (size_t)rows * hfc, c->d_stage + (size_t)rows * (hfc + hxc)};
   OVP_CUDA(cudaMemcpyAsync(H_f, a.Hf, (size_t)rows * hfc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   OVP_CUDA(cudaMemcpyAsync(H_x, a.Hx, (size_t)rows * hxc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   OVP_CUDA(cudaMemcpyAsync(res, a.res, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1373,4 +1399,115 @@ extern "C" int ovp_debug_fp64_latency(ovp_ctx *h, double *out8) {
   OVP_CUDA(cudaStreamSynchronize(c->stream));
   OVP_CUDA(cudaMemcpy(out8, c->dscal + 160, 8 * sizeof(double), cudaMemcpyDeviceToHost));
   return OVP_OK;
+}
+
+namespace ovp {
+int slam_update_impl(Ctx *c, int F, const int *meas_offset, const int *meas_clone, const float *uv, const int64_t *featid,
+                     const int64_t *planeid, const ovp_updater_options *opt, int use_plane, int *feat_status, double *feat_chi2);
+
+// UpdaterSLAM::delayed_init, estimator half (UpdaterSLAM.cpp:225-372): per feature, in order, get_feature_jacobian_full with the
+// plane constraint when the plane is in the state, StateHelper::initialize(landmark, ..., chi2_multipler); when that fails WITH a
+// plane, detach the landmark from the plane and retry from the pre-refinement position (:310-359).
+static int slam_delayed_init_impl(Ctx *c, int F, const int *meas_offset, const int *meas_clone, const float *uv, const double *p_FinG,
+                                  const double *p_FinG_original, const int64_t *featid, const int64_t *planeid,
+                                  const ovp_updater_options *opt, int use_plane, int *feat_status, int *new_handles) {
+  for (int f = 0; f < F; f++) {
+    feat_status[f] = 0;
+    new_handles[f] = -1;
+  }
+  for (int f = 0; f < F; f++) {
+    const int m = meas_offset[f + 1] - meas_offset[f];
+    const int *cl = meas_clone + meas_offset[f];
+    if (c->slam.count(featid[f]))
+      return fail(c, OVP_ERR_ALREADY_IN_STATE, "delayed_init: feature %lld already has a landmark", (long long)featid[f]);
+    int ph = -1;
+    if (use_plane && planeid && planeid[f] != 0) {
+      auto ip = c->planes.find(planeid[f]);
+      auto is = c->slam_to_plane.find(featid[f]);
+      if (ip != c->planes.end() && (is == c->slam_to_plane.end() || is->second != 0))
+        ph = ip->second;
+    }
+    auto attempt = [&](const double *pf, int plane_h, int *acc, int *nh) -> int {
+      int rows, hfc, hxc;
+      int st = stage_feature_jacobian(c, m, cl, uv + 2 * (size_t)meas_offset[f], pf, pf, plane_h >= 0, plane_h, nullptr, nullptr,
+                                      opt->sigma_pix, c->opt.sigma_constraint, &rows, &hfc, &hxc);
+      if (st)
+        return st;
+      std::vector<int> xo;
+      if (c->opt.do_calib_camera_pose)
+        xo.push_back(c->h_calib);
+      if (c->opt.do_calib_camera_intrinsics)
+        xo.push_back(c->h_intr);
+      for (int i = 0; i < m; i++)
+        xo.push_back(cl[i]);
+      if (plane_h >= 0)
+        xo.push_back(plane_h);
+      int n = 0;
+      st = upload_cols(c, xo.data(), (int)xo.size(), 0, &n);
+      if (st)
+        return st;
+      if (n != hxc)
+        return fail(c, OVP_ERR_BAD_ARGS, "delayed_init: internal column mismatch %d vs %d", n, hxc);
+      if (c->var_table_dirty) {
+        st = upload_var_table(c);
+        if (st)
+          return st;
+      }
+      return initialize_core(c, OVP_KIND_LANDMARK, 3, pf, pf, featid[f], c->dcols, n, c->d_stage, rows, rows, rows, 1.0, opt->chi2_multipler,
+                             1, acc, nh);
+    };
+    int acc = 0, nh = -1;
+    int st = attempt(p_FinG + 3 * (size_t)f, ph, &acc, &nh);
+    if (st)
+      return st;
+    if (acc) {
+      feat_status[f] = 1;
+      new_handles[f] = nh;
+      if (ph >= 0)
+        c->slam_to_plane[featid[f]] = planeid[f];
+    } else if (ph >= 0) {
+      c->slam_to_plane[featid[f]] = 0;
+      const double *po = (p_FinG_original ? p_FinG_original : p_FinG) + 3 * (size_t)f;
+      st = attempt(po, -1, &acc, &nh);
+      if (st)
+        return st;
+      if (acc) {
+        feat_status[f] = 3;
+        new_handles[f] = nh;
+      }
+    }
+  }
+  return OVP_OK;
+}
+} // namespace ovp
+
+extern "C" {
+int ovp_slam_update(ovp_ctx *h, int F, const int *meas_offset, const int *meas_clone, const float *uv, const int64_t *featid,
+                    const int64_t *planeid, const ovp_updater_options *opt, int use_plane_constraint, int *feat_status, double *feat_chi2) {
+  Ctx *c = &h->c;
+  if (F > 0 && (!meas_offset || !meas_clone || !uv || !featid || !opt))
+    return fail(c, OVP_ERR_BAD_ARGS, "slam_update: null argument");
+  return slam_update_impl(c, F, meas_offset, meas_clone, uv, featid, planeid, opt, use_plane_constraint, feat_status, feat_chi2);
+}
+int ovp_slam_delayed_init(ovp_ctx *h, int F, const int *meas_offset, const int *meas_clone, const float *uv, const double *p_FinG,
+                          const double *p_FinG_original, const int64_t *featid, const int64_t *planeid, const ovp_updater_options *opt,
+                          int use_plane_constraint, int *feat_status, int *new_handles) {
+  Ctx *c = &h->c;
+  if (F > 0 && (!meas_offset || !meas_clone || !uv || !featid || !opt || !p_FinG || !feat_status || !new_handles))
+    return fail(c, OVP_ERR_BAD_ARGS, "slam_delayed_init: null argument");
+  return slam_delayed_init_impl(c, F, meas_offset, meas_clone, uv, p_FinG, p_FinG_original, featid, planeid, opt, use_plane_constraint,
+                                feat_status, new_handles);
+}
+int ovp_slam_handle(ovp_ctx *h, int64_t featid) {
+  auto it = h->c.slam.find(featid);
+  return it == h->c.slam.end() ? -1 : it->second;
+}
+int ovp_slam_should_marg(ovp_ctx *h, int64_t featid) {
+  auto it = h->c.slam.find(featid);
+  return it == h->c.slam.end() ? -1 : (h->c.vars[it->second].should_marg ? 1 : 0);
+}
+int64_t ovp_slam_plane_of(ovp_ctx *h, int64_t featid) { /* State::_features_SLAM_to_PLANE; -1 = no entry */
+  auto it = h->c.slam_to_plane.find(featid);
+  return it == h->c.slam_to_plane.end() ? -1 : it->second;
+}
 }

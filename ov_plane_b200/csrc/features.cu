@@ -19,24 +19,27 @@ struct FeatArgs {
   const int *meas_offset;
   const int *meas_clone;
   const float *uv;
-  const double *pf;       // 3 per feature (position used for this pass)
+  const double *pf;       // 3 per feature (position used for this pass); unused in SLAM mode
   const int *feat_sel;    // feature indices processed by this launch
   const int *row_off;     // per selected feature: first row in the stacked system
   const int *feat_plane_slot; // per feature (global index): slot of its plane in plane_pass[] or -1
   const int *plane_pass;  // device flags written by the plane updates (1 = passed => feature consumed)
+  const int *feat_lm;     // SLAM mode: per feature, handle of its landmark variable
+  const int *feat_ph;     // SLAM mode: per feature, handle of its in-state plane or -1
   const double *val;
   const double *fej;
   const int *var_id;
   int h_calib, h_intr;
   int do_fej, do_calib_pose, do_calib_intr;
-  int plane_mode;         // 1: add point-on-plane rows, carry H_cp, no per-feature gate
-  int plane_handle;       // >= 0: plane is in the state (cp from val/fej tables); -1: use plane_cp
+  int mode;               // 0: MSCKF point (nullspace + per-feature gate), 1: MSCKF plane (nullspace, H_cp carried, no gate),
+                          // 2: SLAM (landmark and plane are state columns, no nullspace, gate with plane -> no-plane fallback)
+  int plane_handle;       // mode 1: >= 0: plane is in the state (cp from val/fej tables); -1: use plane_cp
   double plane_cp[3];
   double white_px, white_c;
   const double *P;
   int ldP;
   const int *state2compact;
-  int col_cp, col_res;    // stacked-system columns of H_cp (3) and of the residual
+  int col_cp, col_res;    // stacked-system columns of H_cp (3, mode 1) and of the residual
   double *Hs;
   int ldHs;
   const double *chi2_table;
@@ -56,6 +59,85 @@ __device__ __forceinline__ double warp_sum(double s) {
   return s;
 }
 
+// Mahalanobis gate on the sub-block rows [rb, rb+nr) x columns [cb, cb+ncg) of the feature block A:
+// S = H P_marg H^T + I, chi2 = r^T S^-1 r (UpdaterMSCKF.cpp:739-742, UpdaterSLAM.cpp:528-532).  gid[c] = state index of local column c.
+// Returns chi2 (NaN-safe: ok flag in *ok_out).  All 128 threads participate.
+__device__ double gate_chi2(const double *A, int lda, double *T, double *S, int ldt, double *ybuf, int rb, int nr, int cb, int ncg,
+                            const int *gid, const double *P, int ldP, int c_res, int tid, int *s_ok, double *s_chi2) {
+  const int nchunk = (nr + 7) / 8;
+  for (int w = tid; w < ncg * nchunk; w += 128) {
+    int b = w % ncg, ch = w / ncg;
+    int i0 = ch * 8;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const double *Pc = P + (size_t)gid[cb + b] * ldP;
+    for (int k = 0; k < ncg; k++) {
+      double p = Pc[gid[cb + k]];
+      const double *hc = A + (size_t)(cb + k) * lda + rb + i0;
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        if (i0 + i < nr)
+          acc[i] += hc[i] * p;
+    }
+    for (int i = 0; i < 8; i++)
+      if (i0 + i < nr)
+        T[(size_t)b * ldt + i0 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int w = tid; w < nr * nr; w += 128) {
+    int i = w % nr, jj = w / nr;
+    if (i < jj)
+      continue;
+    double s = (i == jj) ? 1.0 : 0.0;
+    for (int b = 0; b < ncg; b++)
+      s += T[(size_t)b * ldt + i] * A[(size_t)(cb + b) * lda + rb + jj];
+    S[(size_t)jj * ldt + i] = s;
+  }
+  __syncthreads();
+  if (tid == 0)
+    *s_ok = 1;
+  for (int jj = 0; jj < nr; jj++) {
+    __syncthreads();
+    if (tid == 0) {
+      double d = S[(size_t)jj * ldt + jj];
+      if (!(d > 0.0)) {
+        *s_ok = 0;
+        d = 1.0;
+      }
+      S[(size_t)jj * ldt + jj] = sqrt(d);
+    }
+    __syncthreads();
+    double piv = S[(size_t)jj * ldt + jj];
+    for (int i = jj + 1 + tid; i < nr; i += 128)
+      S[(size_t)jj * ldt + i] /= piv;
+    __syncthreads();
+    int nrem = nr - 1 - jj;
+    for (int w = tid; w < nrem * nrem; w += 128) {
+      int i = jj + 1 + w % nrem, k = jj + 1 + w / nrem;
+      if (i >= k)
+        S[(size_t)k * ldt + i] -= S[(size_t)jj * ldt + i] * S[(size_t)jj * ldt + k];
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    double chi = 0.0;
+    for (int i = 0; i < nr; i++) {
+      double s = 0.0;
+      for (int k = tid; k < i; k += 32)
+        s += S[(size_t)k * ldt + i] * ybuf[k];
+      s = warp_sum(s);
+      double y = (A[(size_t)c_res * lda + rb + i] - s) / S[(size_t)i * ldt + i];
+      if (tid == 0)
+        ybuf[i] = y;
+      __syncwarp();
+      chi += y * y;
+    }
+    if (tid == 0)
+      *s_chi2 = chi;
+  }
+  __syncthreads();
+  return *s_chi2;
+}
+
 // Local column layout of the feature block A (col-major, stride lda):
 //   [0,3) H_f | [3, 3+cf) H_x = [extrinsics 6][intrinsics 8][clone_0 6]...[clone_{m-1} 6] | [3+cf, 3+cf+3) H_cp | last: res
 __global__ void __launch_bounds__(128) feature_kernel(FeatArgs a) {
@@ -64,7 +146,7 @@ __global__ void __launch_bounds__(128) feature_kernel(FeatArgs a) {
   const int f = a.feat_sel[blockIdx.x];
   const int m0 = a.meas_offset[f];
   const int m = a.meas_offset[f + 1] - m0;
-  if (!a.plane_mode) {
+  if (a.mode == 0) {
     int slot = a.feat_plane_slot[f];
     if (slot >= 0 && a.plane_pass[slot] == 1) { // consumed by a successful plane update (UpdaterMSCKF.cpp:640-644,659)
       if (tid == 0) {
@@ -74,17 +156,20 @@ __global__ void __launch_bounds__(128) feature_kernel(FeatArgs a) {
       return;
     }
   }
+  const int lm = (a.mode == 2) ? a.feat_lm[f] : -1;
+  const int ph = (a.mode == 2) ? a.feat_ph[f] : a.plane_handle;
+  const bool has_plane = (a.mode == 1) || (a.mode == 2 && ph >= 0);
   const int ncal = (a.do_calib_pose ? 6 : 0) + (a.do_calib_intr ? 8 : 0);
   const int cf = ncal + 6 * m;
-  const int rows = a.plane_mode ? 3 * m : 2 * m;
+  const int rows = has_plane ? 3 * m : 2 * m;
   const int ncols = 3 + cf + 3 + 1;
   const int c_cp = 3 + cf, c_res = 3 + cf + 3;
   const int lda = a.lda;
   double *A = sm;                                   // lda * maxcols
   double *T = A + (size_t)lda * a.maxcols;          // ldt * (maxcols)   (gate only)
   double *S = T + (size_t)a.ldt * a.maxcols;        // ldt * ldt         (gate only)
-  double *vbuf = a.plane_mode ? T : S + (size_t)a.ldt * a.ldt; // reflector (rows)
-  __shared__ int lsid[14 + 6 * 64];
+  double *vbuf = (a.mode == 1) ? T : S + (size_t)a.ldt * a.ldt; // reflector / forward-substitution vector
+  __shared__ int gid[3 + 14 + 6 * 64 + 3]; // state index of every local column except the residual
   __shared__ double s_beta, s_chi2;
   __shared__ int s_ok;
 
@@ -102,9 +187,16 @@ __global__ void __launch_bounds__(128) feature_kernel(FeatArgs a) {
     const double *cam = a.val + (size_t)a.h_intr * OVP_VAL_STRIDE;
     double R_C[9];
     quat_to_rot(vcal, R_C);
-    const double *pf = a.pf + 3 * (size_t)f;
+    const double *pf, *pff;
+    if (a.mode == 2) { // landmark in the state: value and first-estimate (UpdaterSLAM.cpp:488-489)
+      pf = a.val + (size_t)lm * OVP_VAL_STRIDE;
+      pff = a.fej + (size_t)lm * OVP_VAL_STRIDE;
+    } else { // MSCKF feature: both are the triangulated point (UpdaterMSCKF.cpp:721-722)
+      pf = a.pf + 3 * (size_t)f;
+      pff = pf;
+    }
     double res[2], Hf[6], Hcl[12], Hcal[12], Hin[16];
-    bearing_rows(vc, vc + 4, fc, fc + 4, a.do_fej, R_C, vcal + 4, cam, pf, pf, a.uv[2 * (m0 + k)], a.uv[2 * (m0 + k) + 1], a.white_px,
+    bearing_rows(vc, vc + 4, fc, fc + 4, a.do_fej, R_C, vcal + 4, cam, pf, pff, a.uv[2 * (m0 + k)], a.uv[2 * (m0 + k) + 1], a.white_px,
                  res, Hf, Hcl, Hcal, Hin);
     for (int i = 0; i < 2; i++) {
       int r = 2 * k + i;
@@ -127,18 +219,18 @@ __global__ void __launch_bounds__(128) feature_kernel(FeatArgs a) {
     }
     const int idc = a.var_id[hcl];
     for (int j = 0; j < 6; j++)
-      lsid[ncal + 6 * k + j] = idc + j;
-    if (a.plane_mode) {
+      gid[3 + ncal + 6 * k + j] = idc + j;
+    if (has_plane) {
       const double *cp, *cpf;
-      if (a.plane_handle >= 0) {
-        cp = a.val + (size_t)a.plane_handle * OVP_VAL_STRIDE;
-        cpf = a.fej + (size_t)a.plane_handle * OVP_VAL_STRIDE;
+      if (ph >= 0) {
+        cp = a.val + (size_t)ph * OVP_VAL_STRIDE;
+        cpf = a.fej + (size_t)ph * OVP_VAL_STRIDE;
       } else {
         cp = a.plane_cp;
         cpf = a.plane_cp;
       }
       double pr, pHf[3], pHcp[3];
-      plane_row(pf, pf, cp, cpf, a.do_fej, a.white_c, pr, pHf, pHcp);
+      plane_row(pf, pff, cp, cpf, a.do_fej, a.white_c, pr, pHf, pHcp);
       int r = 2 * m + k;
       for (int j = 0; j < 3; j++) {
         A[(size_t)j * lda + r] = pHf[j];
@@ -148,158 +240,108 @@ __global__ void __launch_bounds__(128) feature_kernel(FeatArgs a) {
     }
   }
   if (tid == 0) {
-    int cb = 0;
+    int cb = 3;
     if (a.do_calib_pose) {
       int idb = a.var_id[a.h_calib];
       for (int j = 0; j < 6; j++)
-        lsid[cb + j] = idb + j;
+        gid[cb + j] = idb + j;
       cb += 6;
     }
     if (a.do_calib_intr) {
       int idb = a.var_id[a.h_intr];
       for (int j = 0; j < 8; j++)
-        lsid[cb + j] = idb + j;
+        gid[cb + j] = idb + j;
+    }
+    for (int j = 0; j < 3; j++) {
+      gid[j] = (lm >= 0) ? a.var_id[lm] + j : 0;
+      gid[c_cp + j] = (ph >= 0) ? a.var_id[ph] + j : 0;
     }
   }
   __syncthreads();
 
-  // ---- left-nullspace projection of H_f: 3 Householder reflectors applied to [H_f H_x H_cp res] ----
-  for (int j = 0; j < 3; j++) {
-    if (tid < 32) {
-      double s = 0.0;
-      for (int i = j + tid; i < rows; i += 32) {
-        double v = A[(size_t)j * lda + i];
-        s += v * v;
-      }
-      s = warp_sum(s);
-      double x0 = A[(size_t)j * lda + j];
-      double nrm = sqrt(s);
-      double alpha = (x0 > 0.0) ? -nrm : nrm;
-      double v0 = x0 - alpha;
-      // v = [v0; x(j+1:)],  beta = 2 / (v^T v) = -1 / (alpha * v0)
-      double vtv = s - x0 * x0 + v0 * v0;
-      for (int i = j + tid; i < rows; i += 32)
-        vbuf[i] = (i == j) ? v0 : A[(size_t)j * lda + i];
-      if (tid == 0)
-        s_beta = (vtv > 0.0 && nrm > 0.0) ? 2.0 / vtv : 0.0;
-    }
-    __syncthreads();
-    const double beta = s_beta;
-    for (int cidx = j + 1 + tid; cidx < ncols; cidx += 128) {
-      double *col = A + (size_t)cidx * lda;
-      double s = 0.0;
-      for (int i = j; i < rows; i++)
-        s += vbuf[i] * col[i];
-      s *= beta;
-      if (s != 0.0)
-        for (int i = j; i < rows; i++)
-          col[i] -= s * vbuf[i];
-    }
-    __syncthreads();
-  }
-  const int ro = rows - 3; // projected rows live in A[3:rows, :]
-
-  int accept = 1;
-  if (!a.plane_mode) {
-    // ---- chi2 gate: S = H_o P_marg H_o^T + I, chi2 = r^T S^-1 r (UpdaterMSCKF.cpp:739-742) ----
-    const int ldt = a.ldt;
-    // T = H_o * P_marg   (ro x cf): work item = (column b, row chunk of 8)
-    const int nchunk = (ro + 7) / 8;
-    for (int w = tid; w < cf * nchunk; w += 128) {
-      int b = w % cf, ch = w / cf;
-      int i0 = ch * 8;
-      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      const double *Pc = a.P + (size_t)lsid[b] * a.ldP;
-      for (int k = 0; k < cf; k++) {
-        double p = Pc[lsid[k]];
-        const double *hc = A + (size_t)(3 + k) * lda + 3 + i0;
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-          if (i0 + i < ro)
-            acc[i] += hc[i] * p;
-      }
-      for (int i = 0; i < 8; i++)
-        if (i0 + i < ro)
-          T[(size_t)b * ldt + i0 + i] = acc[i];
-    }
-    __syncthreads();
-    for (int w = tid; w < ro * ro; w += 128) {
-      int i = w % ro, jj = w / ro;
-      if (i < jj)
-        continue;
-      double s = (i == jj) ? 1.0 : 0.0;
-      for (int b = 0; b < cf; b++)
-        s += T[(size_t)b * ldt + i] * A[(size_t)(3 + b) * lda + 3 + jj];
-      S[(size_t)jj * ldt + i] = s;
-    }
-    __syncthreads();
-    // in-place Cholesky of S (lower), then y = L^-1 r
-    if (tid == 0)
-      s_ok = 1;
-    for (int jj = 0; jj < ro; jj++) {
-      __syncthreads();
-      if (tid == 0) {
-        double d = S[(size_t)jj * ldt + jj];
-        if (!(d > 0.0)) {
-          s_ok = 0;
-          d = 1.0;
-        }
-        S[(size_t)jj * ldt + jj] = sqrt(d);
-      }
-      __syncthreads();
-      double piv = S[(size_t)jj * ldt + jj];
-      for (int i = jj + 1 + tid; i < ro; i += 128)
-        S[(size_t)jj * ldt + i] /= piv;
-      __syncthreads();
-      int nrem = ro - 1 - jj;
-      for (int w = tid; w < nrem * nrem; w += 128) {
-        int i = jj + 1 + w % nrem, k = jj + 1 + w / nrem;
-        if (i >= k)
-          S[(size_t)k * ldt + i] -= S[(size_t)jj * ldt + i] * S[(size_t)jj * ldt + k];
-      }
-    }
-    __syncthreads();
-    if (tid < 32) {
-      // forward substitution by one warp: y_i = (r_i - sum_k L_ik y_k) / L_ii ; y stored in vbuf
-      double chi = 0.0;
-      for (int i = 0; i < ro; i++) {
+  int accept = 1, rb = 0, nr = rows, cb0 = 0, ncs = 3 + cf + (has_plane ? 3 : 0); // accepted sub-block: rows [rb, rb+nr), cols [cb0, cb0+ncs)
+  if (a.mode != 2) {
+    // ---- left-nullspace projection of H_f: 3 Householder reflectors applied to [H_f H_x H_cp res] ----
+    for (int j = 0; j < 3; j++) {
+      if (tid < 32) {
         double s = 0.0;
-        for (int k = tid; k < i; k += 32)
-          s += S[(size_t)k * ldt + i] * vbuf[k];
+        for (int i = j + tid; i < rows; i += 32) {
+          double v = A[(size_t)j * lda + i];
+          s += v * v;
+        }
         s = warp_sum(s);
-        double y = (A[(size_t)c_res * lda + 3 + i] - s) / S[(size_t)i * ldt + i];
+        double x0 = A[(size_t)j * lda + j];
+        double nrm = sqrt(s);
+        double alpha = (x0 > 0.0) ? -nrm : nrm;
+        double v0 = x0 - alpha;
+        double vtv = s - x0 * x0 + v0 * v0;
+        for (int i = j + tid; i < rows; i += 32)
+          vbuf[i] = (i == j) ? v0 : A[(size_t)j * lda + i];
         if (tid == 0)
-          vbuf[i] = y;
-        __syncwarp();
-        chi += y * y;
+          s_beta = (vtv > 0.0 && nrm > 0.0) ? 2.0 / vtv : 0.0;
       }
-      if (tid == 0)
-        s_chi2 = chi;
+      __syncthreads();
+      const double beta = s_beta;
+      for (int cidx = j + 1 + tid; cidx < ncols; cidx += 128) {
+        double *col = A + (size_t)cidx * lda;
+        double s = 0.0;
+        for (int i = j; i < rows; i++)
+          s += vbuf[i] * col[i];
+        s *= beta;
+        if (s != 0.0)
+          for (int i = j; i < rows; i++)
+            col[i] -= s * vbuf[i];
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    double thr = a.chi2_mult * a.chi2_table[ro < a.chi2_n ? ro : a.chi2_n - 1];
-    accept = (s_ok && !(s_chi2 > thr)) ? 1 : 0;
+    rb = 3;
+    nr = rows - 3;
+    cb0 = 3;
+    ncs = cf;
+    if (a.mode == 0) {
+      double chi2 = gate_chi2(A, lda, T, S, a.ldt, vbuf, rb, nr, cb0, ncs, gid, a.P, a.ldP, c_res, tid, &s_ok, &s_chi2);
+      double thr = a.chi2_mult * a.chi2_table[nr < a.chi2_n ? nr : a.chi2_n - 1];
+      accept = (s_ok && !(chi2 > thr)) ? 1 : 0;
+      if (tid == 0) {
+        a.feat_flag[f] = accept;
+        a.feat_chi2[f] = chi2;
+      }
+    }
+  } else {
+    // ---- SLAM landmark: no nullspace; gate with the plane constraint, on failure retry without it (UpdaterSLAM.cpp:528-622) ----
+    double chi2 = gate_chi2(A, lda, T, S, a.ldt, vbuf, 0, nr, 0, ncs, gid, a.P, a.ldP, c_res, tid, &s_ok, &s_chi2);
+    double thr = a.chi2_mult * a.chi2_table[nr < a.chi2_n ? nr : a.chi2_n - 1];
+    int st = (s_ok && !(chi2 > thr)) ? 1 : 0;
+    if (!st && has_plane) {
+      __syncthreads();
+      nr = 2 * m;
+      ncs = 3 + cf;
+      chi2 = gate_chi2(A, lda, T, S, a.ldt, vbuf, 0, nr, 0, ncs, gid, a.P, a.ldP, c_res, tid, &s_ok, &s_chi2);
+      thr = a.chi2_mult * a.chi2_table[nr < a.chi2_n ? nr : a.chi2_n - 1];
+      st = (s_ok && !(chi2 > thr)) ? 3 : 0;
+    }
+    accept = st;
     if (tid == 0) {
-      a.feat_flag[f] = accept;
-      a.feat_chi2[f] = s_chi2;
+      a.feat_flag[f] = st;
+      a.feat_chi2[f] = chi2;
     }
   }
   if (!accept)
     return;
-  // ---- scatter the projected block into the stacked system ----
+  // ---- scatter the accepted block into the stacked system ----
   const int r0 = a.row_off[blockIdx.x];
-  for (int w = tid; w < cf * ro; w += 128) {
-    int i = w % ro, b = w / ro;
-    int gc = a.state2compact[lsid[b]];
-    a.Hs[(size_t)gc * a.ldHs + r0 + i] = A[(size_t)(3 + b) * lda + 3 + i];
+  for (int w = tid; w < ncs * nr; w += 128) {
+    int i = w % nr, b = w / nr;
+    int gc = a.state2compact[gid[cb0 + b]];
+    a.Hs[(size_t)gc * a.ldHs + r0 + i] = A[(size_t)(cb0 + b) * lda + rb + i];
   }
-  if (a.plane_mode)
-    for (int w = tid; w < 3 * ro; w += 128) {
-      int i = w % ro, b = w / ro;
-      a.Hs[(size_t)(a.col_cp + b) * a.ldHs + r0 + i] = A[(size_t)(c_cp + b) * lda + 3 + i];
+  if (a.mode == 1)
+    for (int w = tid; w < 3 * nr; w += 128) {
+      int i = w % nr, b = w / nr;
+      a.Hs[(size_t)(a.col_cp + b) * a.ldHs + r0 + i] = A[(size_t)(c_cp + b) * lda + rb + i];
     }
-  for (int i = tid; i < ro; i += 128)
-    a.Hs[(size_t)a.col_res * a.ldHs + r0 + i] = A[(size_t)c_res * lda + 3 + i];
+  for (int i = tid; i < nr; i += 128)
+    a.Hs[(size_t)a.col_res * a.ldHs + r0 + i] = A[(size_t)c_res * lda + rb + i];
 }
 
 // -------------------------------------------------------------------------------------------------------------------
@@ -411,3 +453,4 @@ static int gram_of_stacked(Ctx *c, int rows, int nc, int ldHs) {
 }
 
 #include "features_host.inc"
+#include "slam_host.inc"

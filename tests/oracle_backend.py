@@ -266,6 +266,31 @@ class OracleContext(object):
                                          _p(arrs[6]), _p(arrs[7]), C.c_double(sigma_pix), _p(ps), _p(nh)))
         return dict(plane_status=ps[:npl], new_handles=nh[:npl])
 
+    def slam_update(self, b, sigma_pix=1.0, chi2_mult=1.0):
+        F = int(b["F"])
+        fs, fc = np.zeros(F, dtype=np.int32), np.zeros(F)
+        arrs = [np.ascontiguousarray(b[k]) for k in ("meas_offset", "meas_clone", "uv", "featid", "planeid")]
+        self._ck(self.lib.orc_slam_update(self.h, F, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(arrs[4]), C.c_double(sigma_pix),
+                                          C.c_double(chi2_mult), _p(fs), _p(fc)))
+        return dict(feat_status=fs, feat_chi2=fc)
+
+    def slam_delayed_init(self, b, sigma_pix=1.0, chi2_mult=1.0):
+        F = int(b["F"])
+        fs, nh = np.zeros(F, dtype=np.int32), np.zeros(F, dtype=np.int32)
+        arrs = [np.ascontiguousarray(b[k]) for k in ("meas_offset", "meas_clone", "uv", "p_FinG", "p_FinG_original", "featid", "planeid")]
+        self._ck(self.lib.orc_slam_delayed_init(self.h, F, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(arrs[4]), _p(arrs[5]),
+                                                _p(arrs[6]), C.c_double(sigma_pix), C.c_double(chi2_mult), _p(fs), _p(nh)))
+        return dict(feat_status=fs, new_handles=nh)
+
+    def marginalize_slam(self):
+        self._ck(self.lib.orc_marginalize_slam(self.h))
+
+    def slam_handle(self, featid):
+        return self.lib.orc_slam_handle(self.h, C.c_longlong(int(featid)))
+
+    def slam_should_marg(self, featid):
+        return self.lib.orc_slam_should_marg(self.h, C.c_longlong(int(featid)))
+
     # ---- Propagator ----
     def propagator_set_noise(self, sigma_w, sigma_wb, sigma_a, sigma_ab, gravity_mag=9.81):
         self.lib.orc_prop_set(self.h, C.c_double(sigma_w), C.c_double(sigma_wb), C.c_double(sigma_a), C.c_double(sigma_ab),

@@ -273,3 +273,58 @@ def test_oracle_reproduces_golden_vectors(name, seed, chi2_table):
     assert np.array_equal(r["feat_status"], g["feat_status"]) and np.array_equal(r["plane_status"], g["plane_status"])
     assert np.allclose(o.cov(), g["P1"], rtol=0, atol=1e-12 * np.abs(g["P1"]).max())
     assert np.allclose(o.var_get(o.handle_imu())[0], g["imu1"], atol=1e-12)
+
+
+def test_slam_update_against_numpy_restack(chi2_table):
+    """UpdaterSLAM::update of the restatement == an independent numpy re-derivation: per-feature gate on the marginal covariance
+    (UpdaterSLAM.cpp:521-532), plane -> no-plane retry (:547-609), one stacked EKF update with R = I (:672-673)."""
+    S = synth.make_scenario("small_planes", seed=0)
+    orc = ob.OracleContext(S.options)
+    orc.set_chi2_table(chi2_table)
+    cho = synth.load_scenario_into(orc, S)
+    sel = np.arange(24)
+    b = synth.feature_batch(S, cho, sel)
+    o = orc.slam_delayed_init(b, 1.0, 1.0)
+    keep = np.nonzero(o["feat_status"] > 0)[0]
+    assert len(keep) >= 16 and orc.cov_rows() == S.N + 3 * len(keep)
+    u = synth.feature_batch(S, cho, keep)
+    rng = np.random.default_rng(3)
+    u["uv"] = u["uv"] + rng.normal(0.0, 0.5, u["uv"].shape).astype(np.float32)
+    u["uv"][u["meas_offset"][2]:u["meas_offset"][3]] += 30.0  # one gross outlier
+    P0 = orc.cov()
+    N = P0.shape[0]
+    sc = S.options["sigma_constraint"] if isinstance(S.options, dict) else S.options.sigma_constraint
+    # numpy side, from the state BEFORE the update
+    Hrows, rrows, expect = [], [], []
+    for f in range(len(keep)):
+        a, e = u["meas_offset"][f], u["meas_offset"][f + 1]
+        lm = orc.slam_handle(u["featid"][f])
+        p, pfej = orc.var_get(lm)
+        pid = int(u["planeid"][f])
+        ph = orc.plane_handle(pid) if pid else -1
+        st = 0
+        for attempt_plane in ([True, False] if ph >= 0 else [False]):
+            cp, cpf = orc.var_get(ph) if attempt_plane else (None, None)
+            Hf, Hx, res, xo = orc.feature_jacobian_full(u["meas_clone"][a:e], u["uv"][a:e], p, pfej, pid if attempt_plane else 0, cp, cpf, 1.0, sc)
+            Hbig = np.zeros((len(res), N))
+            c0 = 0
+            for h in xo:
+                i, s = orc.var_id(h), orc.var_size(h)
+                Hbig[:, i:i + s] += Hx[:, c0:c0 + s]
+                c0 += s
+            i = orc.var_id(lm)
+            Hbig[:, i:i + 3] += Hf[:, :3]
+            chi = res @ np.linalg.solve(Hbig @ P0 @ Hbig.T + np.eye(len(res)), res)
+            if chi <= chi2_table[len(res)]:
+                st = 1 if (attempt_plane or ph < 0) else 3
+                Hrows.append(Hbig)
+                rrows.append(res)
+                break
+        expect.append(st)
+    got = orc.slam_update(u, 1.0, 1.0)
+    assert list(got["feat_status"]) == expect and 0 in expect
+    H, r = np.vstack(Hrows), np.concatenate(rrows)
+    K = P0 @ H.T @ np.linalg.inv(H @ P0 @ H.T + np.eye(len(r)))
+    P1 = P0 - K @ H @ P0
+    assert np.abs(orc.cov() - P1).max() < 1e-9 * np.abs(P0).max()
+    assert orc.slam_should_marg(u["featid"][2]) == 1

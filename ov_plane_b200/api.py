@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libovp.so")
+LIB_PATH = os.environ.get("OVP_LIB", os.path.join(_HERE, "lib", "libovp.so"))  # OVP_LIB: A/B builds while tuning
 
 OVP_KIND_VEC, OVP_KIND_POSE, OVP_KIND_IMU, OVP_KIND_LANDMARK = 0, 1, 2, 3
 

@@ -1,5 +1,6 @@
 // extern "C" surface of include/ovp.h: State construction, StateHelper entry points, the stateless UpdaterHelper /
 // UpdaterPlane helpers, UpdaterMSCKF::update, the multi-GPU shard halves and the Propagator.
+#include <cstdlib>
 #include "jacobian_core.h"
 #include "ovp_internal.h"
 #include <algorithm>
@@ -328,6 +329,17 @@ int ovp_create(const ovp_state_options *opt, int device, int max_state, int max_
   st = ws_alloc(c, c->wsS, c->Rcap);
   if (st)
     return st;
+  if (const char *ev = getenv("OVP_FUSED_CHOL")) // A/B switch for timing the two Cholesky paths
+    c->use_fused_chol = atoi(ev) != 0;
+  c->cf_maxT = c->Rcap / 64 + 1;
+  OVP_CUDA(cudaMalloc(&c->cf_linv, (size_t)c->cf_maxT * 4096 * sizeof(double)));
+  OVP_CUDA(cudaMalloc(&c->cf_diag0, (size_t)c->cf_maxT * 64 * sizeof(double)));
+  OVP_CUDA(cudaMemset(c->cf_diag0, 0, (size_t)c->cf_maxT * 64 * sizeof(double)));
+  OVP_CUDA(cudaMalloc(&c->cf_flags, (size_t)(3 * c->cf_maxT + c->cf_maxT * c->cf_maxT) * sizeof(int)));
+  OVP_CUDA(cudaMalloc(&c->cf_ctrl, 4 * sizeof(int)));
+  OVP_CUDA(cudaMemset(c->cf_linv, 0, (size_t)c->cf_maxT * 4096 * sizeof(double)));
+  OVP_CUDA(cudaMemset(c->cf_flags, 0, (size_t)(3 * c->cf_maxT + c->cf_maxT * c->cf_maxT) * sizeof(int)));
+  OVP_CUDA(cudaMemset(c->cf_ctrl, 0, 4 * sizeof(int)));
   OVP_CUDA(cudaMalloc(&c->dM, (size_t)c->Nmax * c->Rcap * sizeof(double)));
   OVP_CUDA(cudaMalloc(&c->dY, (size_t)c->Nmax * c->Rcap * sizeof(double)));
   OVP_CUDA(cudaMalloc(&c->dHT, (size_t)c->Rcap * c->Rcap * sizeof(double)));
@@ -439,6 +451,10 @@ void ovp_destroy(ovp_ctx *h) {
   cudaFree(c->d_var_id);
   cudaFree(c->d_var_size);
   cudaFree(c->d_var_kind);
+  cudaFree(c->cf_linv);
+  cudaFree(c->cf_diag0);
+  cudaFree(c->cf_flags);
+  cudaFree(c->cf_ctrl);
   ws_free(c->wsG);
   ws_free(c->wsS);
   cudaFree(c->dM);

@@ -1,6 +1,7 @@
 // Second half of the extern "C" surface: EKFUpdate / clone / marginalize / initialize entry points, the stateless
 // UpdaterHelper / UpdaterPlane helpers, UpdaterMSCKF::update, the multi-GPU shard halves, the Propagator and instrumentation.
 // (compiled as part of the unity build ovp_unity.cu, after capi.cu)
+#include <climits>
 #include "host_math.h"
 
 using namespace ovp;
@@ -1391,13 +1392,41 @@ __global__ void fp64_latency_kernel(double *out, double seed) {
     out[6] = (double)(t1 - t0) / N;
     out[7] = x + y + z + w + s + q;
   }
+  // DMMA m8n8k4: dependent chain (latency) and 8 independent accumulators (issue rate of one warp)
+  double c0 = 0.0, c1 = 0.0, aa = 1.0 + 1e-9 * threadIdx.x, bb = 1.0 - 1e-9 * threadIdx.x;
+  t0 = clock64();
+#pragma unroll 16
+  for (int i = 0; i < N; i++)
+    dmma_m8n8k4(c0, c1, aa, bb);
+  t1 = clock64();
+  if (threadIdx.x == 0)
+    out[8] = (double)(t1 - t0) / N;
+  double e[8][2];
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    e[k][0] = e[k][1] = 0.0;
+  t0 = clock64();
+#pragma unroll 4
+  for (int i = 0; i < N / 8; i++)
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      dmma_m8n8k4(e[k][0], e[k][1], aa, bb);
+  t1 = clock64();
+  double sum = c0 + c1;
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    sum += e[k][0] + e[k][1];
+  if (threadIdx.x == 0) {
+    out[9] = (double)(t1 - t0) / N;
+    out[10] = sum;
+  }
 }
 } // namespace ovp
 extern "C" int ovp_debug_fp64_latency(ovp_ctx *h, double *out8) {
   Ctx *c = &h->c;
   fp64_latency_kernel<<<1, 32, 0, c->stream>>>(c->dscal + 160, 1.2345);
   OVP_CUDA(cudaStreamSynchronize(c->stream));
-  OVP_CUDA(cudaMemcpy(out8, c->dscal + 160, 8 * sizeof(double), cudaMemcpyDeviceToHost));
+  OVP_CUDA(cudaMemcpy(out8, c->dscal + 160, 10 * sizeof(double), cudaMemcpyDeviceToHost));
   return OVP_OK;
 }
 
@@ -1510,4 +1539,77 @@ int64_t ovp_slam_plane_of(ovp_ctx *h, int64_t featid) { /* State::_features_SLAM
   auto it = h->c.slam_to_plane.find(featid);
   return it == h->c.slam_to_plane.end() ? -1 : it->second;
 }
+}
+
+namespace ovp {
+__global__ void spd_fill_kernel(double *A, int ld, int n) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n)
+    return;
+  int i = idx % n, j = idx / n;
+  double v = (i == j) ? 4.0 + 0.001 * i : 0.3 / (1.0 + abs(i - j)) + 0.01 * ((i * 7 + j * 3) % 5);
+  if (i < j)
+    v = 0.0;
+  else if (i != j)
+    v = 0.3 / (1.0 + (i - j)) * 0.1 + 0.001 * (((i + j) * 7) % 5);
+  A[(size_t)j * ld + i] = v;
+}
+} // namespace ovp
+// microbenchmark of the fused Cholesky on a synthetic SPD n x n system (+ optional mrows x n right-hand side):
+// out[0] = us per (fill + factor), out[1] = us per fill alone, out[2..] = globaltimer stamps (ns, relative to the earliest) of the
+// last run, 16 per CTA
+extern "C" int ovp_debug_chol_fused(ovp_ctx *h, int n, int mrows, int iters, double *out, int out_cap) {
+  Ctx *c = &h->c;
+  if (n > c->wsS.cap || mrows > c->Nmax)
+    return fail(c, OVP_ERR_CAPACITY, "debug_chol_fused: too large");
+  const int T = (n + 63) / 64;
+  const int ncta = T * (T + 1) / 2 + (mrows ? (mrows + 1 + 15) / 16 : 0);
+  long long *dbg = nullptr;
+  OVP_CUDA(cudaMalloc(&dbg, ((size_t)ncta * 16 + 64) * sizeof(long long)));
+  OVP_CUDA(cudaMemset(dbg, 0, ((size_t)ncta * 16 + 64) * sizeof(long long)));
+  float ms;
+  for (int variant = 0; variant < 2; variant++) {
+    for (int rep = 0; rep < 2; rep++) {
+      if (rep == 1)
+        cudaEventRecord(c->ev[4], c->stream);
+      for (int it = 0; it < iters; it++) {
+        spd_fill_kernel<<<(n * n + 255) / 256, 256, 0, c->stream>>>(c->wsS.S, c->wsS.cap, n);
+        if (variant == 0) {
+          int st = chol_fused(c, c->wsS.S, c->wsS.cap, n, n, 0.0, mrows ? c->dM : nullptr, c->Nmax, mrows, mrows ? c->dvec + c->Rcap : nullptr,
+                              c->dY, c->Nmax, c->dvec, dbg);
+          if (st)
+            return st;
+        }
+      }
+      if (rep == 1)
+        cudaEventRecord(c->ev[5], c->stream);
+      OVP_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+    out[variant] = 1e3 * ms / iters;
+  }
+  std::vector<long long> ts((size_t)ncta * 16 + 64);
+  OVP_CUDA(cudaMemcpy(ts.data(), dbg, ts.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+  cudaFree(dbg);
+  long long t0 = LLONG_MAX;
+  const size_t nper = (size_t)ncta * 16;
+  for (size_t i = 0; i < nper; i++)
+    if (ts[i] > 0 && ((i & 15) < 8 || (i & 15) == 15)) // slots 8..14 are clock64 stamps, relative to slot 8 of the same CTA
+      t0 = std::min(t0, ts[i]);
+  out[2] = ncta;
+  for (size_t i = 0; i < ts.size() && (int)(3 + i) < out_cap; i++) {
+    if (i >= nper) { // spine phase stamps (clock64), relative to the first one
+      out[3 + i] = ts[i] > 0 ? (double)(ts[i] - ts[nper]) : -1.0;
+      continue;
+    }
+    const bool cyc = (i & 15) >= 8 && (i & 15) < 15;
+    out[3 + i] = ts[i] > 0 ? (double)(ts[i] - (cyc ? ts[(i & ~(size_t)15) + 8] : t0)) : -1.0;
+  }
+  int info = 0;
+  OVP_CUDA(cudaMemcpy(&info, c->dflags + 1, sizeof(int), cudaMemcpyDeviceToHost));
+  if (info) {
+    cudaMemset(c->dflags + 1, 0, sizeof(int));
+    return fail(c, OVP_ERR_NOT_POSITIVE_DEFINITE, "debug_chol_fused: test matrix not positive definite");
+  }
+  return OVP_OK;
 }

@@ -1,0 +1,684 @@
+// One-launch blocked Cholesky (+ optional triangular solve of a tall right-hand side) for the 64..1024-wide dense systems of the
+// update chain: G = L L^T of the stacked Gram matrix (measurement compression) and S = L L^T, Y = M L^-T, w = L^-1 z of the
+// innovation system (StateHelper.cpp:142-171 restructured).
+//
+// The multi-kernel version spent the whole update in launch boundaries: a 470-wide system is 8 diagonal blocks, each followed by
+// a panel solve and a trailing update (24 dependent launches) plus the inverse merges.  Here every 64x64 tile of the lower
+// triangle gets ONE CTA that keeps its tile in shared memory for the whole factorisation and talks to the other tiles through
+// release/acquire flags in global memory (data stays in L2):
+//   tile (i,j):  for k < j:  wait L(i,k), L(j,k);  tile -= L(i,k) L(j,k)^T              (DMMA, operands staged in smem)
+//                i == j:     in-smem Cholesky (zero-pivot rule) + triangular inverse;   publish L(j,j), Linv(j)
+//                i >  j:     wait Linv(j);  tile = tile * Linv(j)^T;                    publish L(i,j)
+//   row block r of M (16 rows, optional):  for k: wait Linv(k): Y_k = M_k Linv(k)^T; for j > k: wait L(j,k): M_j -= Y_k L(j,k)^T
+// CTAs only ever wait on CTAs with a smaller block index (tiles are numbered column by column, row blocks come last), and the
+// hardware dispatches blocks in index order, so a waiting CTA never holds the SM its producer needs.
+#include "ovp_internal.h"
+
+namespace ovp {
+
+#define CF_B 64
+#define CF_LD 68 // 68 mod 16 == 4: DMMA fragment reads (8 rows x 4 k) hit 16 distinct 8-byte banks per half warp
+#define CF_RB 16
+
+struct CholFusedArgs {
+  double *A;
+  int ld, n, npiv;
+  double tol;
+  double *LinvD; // Tp tiles, 64 x 64 col-major each
+  double *diag0; // original diagonal (Tp * 64), written by the tile CTAs for the spine
+  int *flags;    // [Tp] D, [T * Tp] P (i * Tp + k), [T] U(j,j), [T] U(i,i-1)
+  int *ctrl;     // [0] epoch, [1] finished-CTA counter
+  int *info;
+  int T, Tp, ntile;
+  const double *M; // optional tall right-hand side (mrows x npiv, ld ldm); row `mrows` of the virtual matrix is z
+  int ldm, mrows;
+  const double *z;
+  double *Y;
+  int ldy;
+  double *w;
+  int nrb, mstride;
+  long long *dbg; // optional: 16 globaltimer stamps per CTA (tools/microbench.py)
+};
+
+__device__ __forceinline__ long long cf_gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define CF_TS(slot)                                                                                                          \
+  if (p.dbg && threadIdx.x == 0)                                                                                             \
+    p.dbg[(size_t)blockIdx.x * 16 + (slot)] = cf_gtime();
+// shared-memory access with explicit 32-bit addresses: inside the pivot loop the compiler otherwise re-derives the address of a
+// shared array from SR_CgaCtaId (S2R / S2UR, >100 cycles each) every iteration
+__device__ __forceinline__ unsigned cf_saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double cf_lds(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double cf_lds_if(unsigned addr, int pred) {
+  double v = 0.0;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.shared.f64 %0, [%1];\n\t}" : "+d"(v) : "r"(addr), "r"(pred));
+  return v;
+}
+__device__ __forceinline__ void cf_sts_if(unsigned addr, double v, int pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" ::"r"(addr), "d"(v), "r"(pred) : "memory");
+}
+__device__ __forceinline__ int cf_ld_acquire(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cf_st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+__device__ __forceinline__ void cf_wait(const int *flag, int e) {
+  if (threadIdx.x == 0)
+    while (cf_ld_acquire(flag) != e) {
+    }
+  __syncthreads();
+}
+// all threads' global writes -> visible before the flag
+__device__ __forceinline__ void cf_signal(int *flag, int e) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    cf_st_release(flag, e);
+  }
+}
+
+// idx in [0, 4096) -> (r, c) of a 64x64 tile such that a warp touches 8 columns x 4 consecutive rows: full 32-byte sectors in
+// global memory (column-major) and conflict-free 8-byte banks in shared memory ([r][c], stride CF_LD)
+__device__ __forceinline__ void cf_map(int idx, int &r, int &c) {
+  r = ((idx >> 5) & 15) * 4 + (idx & 3);
+  c = (idx >> 9) * 8 + ((idx >> 2) & 7);
+}
+
+// tile (rows r0.., cols c0..) of a column-major matrix -> smem [r][c]; entries outside (rv, cv) are zero
+__device__ __noinline__ void cf_load_tile(double *s, const double *g, int ld, int rv, int cv, bool lower_only) {
+  double v[16]; // all 16 loads of a thread are in flight before the first shared-memory store
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    int r, c;
+    cf_map(threadIdx.x + 256 * q, r, c);
+    v[q] = (r < rv && c < cv && (!lower_only || r >= c)) ? __ldcg(g + (size_t)c * ld + r) : 0.0;
+  }
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    int r, c;
+    cf_map(threadIdx.x + 256 * q, r, c);
+    s[r * CF_LD + c] = v[q];
+  }
+}
+// asynchronous variant (cp.async, 8 bytes per element: the smem layout is the transpose of the global one): the copy runs
+// while the CTA computes; entries outside (rv, cv) / above the diagonal are zero-filled (src-size 0)
+__device__ __noinline__ void cf_cpasync_tile(double *s, const double *g, int ld, int rv, int cv, bool lower_only) {
+#pragma unroll 4
+  for (int q = 0; q < 16; q++) {
+    int r, c;
+    cf_map(threadIdx.x + 256 * q, r, c);
+    const bool valid = r < rv && c < cv && (!lower_only || r >= c);
+    const double *src = valid ? g + (size_t)c * ld + r : g;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(cf_saddr(s + r * CF_LD + c)), "l"(src), "r"(valid ? 8 : 0) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __noinline__ void cf_store_tile(const double *s, double *g, int ld, int rv, int cv, bool lower_zero_upper) {
+  double v[16]; // all shared-memory reads first, then the 16 stores back to back
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    int r, c;
+    cf_map(threadIdx.x + 256 * q, r, c);
+    v[q] = (lower_zero_upper && r < c) ? 0.0 : s[r * CF_LD + c];
+  }
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    int r, c;
+    cf_map(threadIdx.x + 256 * q, r, c);
+    if (r < rv && c < cv)
+      __stcg(g + (size_t)c * ld + r, v[q]);
+  }
+}
+
+// C (64x64) = (ACC ? C : 0) + alpha * A (64 x 64) * B^T, all [row][k] in smem.  TRI: B is lower triangular (k <= column).
+// Warp tile 16 x 32.  When C aliases A or B the caller passes inplace = true (barrier between the last read and the first write).
+template <bool TRI> __device__ __noinline__ void cf_mma_64(double *C, const double *A, const double *B, double alpha, bool acc_c, bool inplace) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int rb = (warp & 3) * 16, cb = (warp >> 2) * 32;
+  double acc[2][4][2];
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      acc[i][j][0] = acc[i][j][1] = 0.0;
+  const double *pa0 = A + (rb + g) * CF_LD + t, *pa1 = pa0 + 8 * CF_LD;
+  const double *pb = B + (cb + g) * CF_LD + t;
+#pragma unroll 4
+  for (int k4 = 0; k4 < CF_B; k4 += 4) {
+    if (TRI && k4 > cb + 31)
+      break;
+    const double a0 = pa0[k4], a1 = pa1[k4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (TRI && k4 > cb + 8 * j + 7)
+        continue;
+      const double b = pb[j * 8 * CF_LD + k4];
+      dmma_m8n8k4(acc[0][j][0], acc[0][j][1], a0, b);
+      dmma_m8n8k4(acc[1][j][0], acc[1][j][1], a1, b);
+    }
+  }
+  if (inplace)
+    __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        double *p = C + (rb + 8 * i + g) * CF_LD + cb + 8 * j + 2 * t + h;
+        *p = (acc_c ? *p : 0.0) + alpha * acc[i][j][h];
+      }
+}
+
+// Batched small products on 8x8 output blocks, round-robin over the 8 warps:
+//   C_b[mb*8 x nb*8] = beta * C_b + alpha * A_b[. x K] * op(B_b),  b = 0..nbatch-1, operand b at pointer + b * bstride
+// NN: B indexed [k][col]; otherwise [col][k].  lower: skip blocks above the block diagonal.
+template <bool NN>
+__device__ __noinline__ void cf_mma_blocks(double *C, const double *A, const double *B, int mb, int nb, int K, double alpha, double beta,
+                                              bool lower, int nbatch, int bstride) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int per = mb * nb;
+  for (int blk = warp; blk < per * nbatch; blk += 8) {
+    const int b = blk / per, q = blk - b * per;
+    const int bi = q % mb, bj = q / mb;
+    if (lower && bj > bi)
+      continue;
+    const double *pa = A + b * bstride + (8 * bi + g) * CF_LD + t;
+    const double *pb = NN ? (B + b * bstride + t * CF_LD + 8 * bj + g) : (B + b * bstride + (8 * bj + g) * CF_LD + t);
+    double c0 = 0.0, c1 = 0.0;
+    for (int k4 = 0; k4 < K; k4 += 4) {
+      const double a = pa[k4];
+      const double bb = NN ? pb[k4 * CF_LD] : pb[k4];
+      dmma_m8n8k4(c0, c1, a, bb);
+    }
+    double *pc = C + b * bstride + (8 * bi + g) * CF_LD + 8 * bj + 2 * t;
+    pc[0] = (beta != 0.0 ? beta * pc[0] : 0.0) + alpha * c0;
+    pc[1] = (beta != 0.0 ? beta * pc[1] : 0.0) + alpha * c1;
+  }
+}
+
+// rank-16 update of the lower triangle of the region rows/cols [c0+16, 64) of tile a with its columns [c0, c0+16):
+// 8x8 blocks of the lower triangle, up to three per warp, all operand fragments loaded before the first DMMA
+__device__ __noinline__ void cf_trail16(double *a, int c0) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int mb = (CF_B - c0 - 16) / 8;
+  const int nblk = mb * (mb + 1) / 2;
+  const int o = c0 + 16;
+  double fa[3][4], fb[3][4], acc[3][2];
+  int bi[3], bj[3];
+#pragma unroll
+  for (int s = 0; s < 3; s++) {
+    int q = warp + 8 * s;
+    bi[s] = -1;
+    bj[s] = 0;
+    if (q < nblk) {
+      int i = 0;
+      while (q >= i + 1) {
+        q -= i + 1;
+        i++;
+      }
+      bi[s] = i;
+      bj[s] = q;
+    }
+    acc[s][0] = acc[s][1] = 0.0;
+    if (bi[s] >= 0) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        fa[s][k] = a[(o + 8 * bi[s] + g) * CF_LD + c0 + 4 * k + t];
+        fb[s][k] = a[(o + 8 * bj[s] + g) * CF_LD + c0 + 4 * k + t];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int s = 0; s < 3; s++)
+      if (bi[s] >= 0)
+        dmma_m8n8k4(acc[s][0], acc[s][1], fa[s][k], fb[s][k]);
+#pragma unroll
+  for (int s = 0; s < 3; s++)
+    if (bi[s] >= 0) {
+      double *pc = a + (o + 8 * bi[s] + g) * CF_LD + o + 8 * bj[s] + 2 * t;
+      pc[0] -= acc[s][0];
+      pc[1] -= acc[s][1];
+    }
+}
+
+// In-smem Cholesky of the leading bs columns of a 64-row tile (rows below the pivot block are solved along, columns >= bs
+// receive the Schur complement).  Blocked by 16 columns.  The serial pivot chain of a 16x16 diagonal block runs in registers
+// with lane = row and shuffles; lanes 16..31 of the same warp carry 16 rows BELOW the block through the same chain, and every
+// further group of 16 rows below gets its own warp that repeats the diagonal block redundantly in its lanes 0..15 - so the
+// whole 16-column panel is finished when the chain is, with no cross-warp traffic.  Chain per column: rsqrt -> scale ->
+// shuffle -> fma (the next pivot is rebuilt on every lane from a value shuffled one column earlier).  The trailing update
+// inside the tile is DMMA.  Zero-pivot rule: pivot <= thr (= tol * original diagonal) or <= 0 -> column of zeros, pivinv = 0
+// (rank-deficient Gram matrices); strict (tol == 0) flags *info instead (S must be positive definite).
+__device__ void cf_potrf64(double *a, int bs, const double *thr, bool strict, double *pivinv, int *info, double *bcast,
+                           long long *dbgp = nullptr) {
+#define PT(slot)                                                                                                             \
+  if (dbgp && threadIdx.x == 0)                                                                                              \
+    dbgp[slot] = clock64();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  if (tid < CF_B)
+    pivinv[tid] = 0.0;
+  __syncthreads();
+  for (int c0 = 0; c0 < bs; c0 += 16) {
+    const int nbp = min(16, bs - c0);
+    const int nw = max(1, (CF_B - c0 - 16) / 16);
+    if (warp_u < nw) {
+      // warp_u is the warp index broadcast from lane 0 by a shuffle: ptxas then knows the branch is warp-uniform, emits the
+      // shuffles below without divergence checks and keeps the loop body one basic block it can schedule as a whole.  Lanes
+      // 0..15 of every chain warp repeat the diagonal block; lanes 16..31 of warp w carry rows c0+16+16w.. of the tile.
+      const int row = (lane < 16) ? c0 + lane : c0 + 16 * warp + lane;
+      const bool lower = lane >= 16;
+      const bool rok = row < CF_B;
+      // Entry k of a row, relative to the current column j: e0 = a(row, j) (final), e1 = a(row, j+1) (updated through column
+      // j-1), q[k] = a(row, j+k), k >= 2 (updated through column j-2: the update with column j-1 is DEFERRED into this
+      // iteration, behind the pivot chain - one warp issues in order, and a consumer of a shared-memory load must not sit in
+      // front of the next pivot).  Static register indices with a ROLLED column loop: the array shifts by one per column inside
+      // the deferred update.  Pivot chain per column: rsqrt -> select -> 2 multiplies -> fma; the operands from other lanes
+      // (u1, u2, next diagonal) are shuffled before they are needed.
+      double q[16];
+#pragma unroll
+      for (int c = 0; c < 16; c++)
+        q[c] = (rok && (lower || c <= lane)) ? a[row * CF_LD + c0 + c] : 0.0;
+      double e0 = q[0], e1 = q[1];
+      double *lb = bcast + warp * 96; // [0,32) and [32,64): l(., j) by column parity (16 values + 16 zeros); [64,96): zeros
+      lb[lane] = 0.0;
+      lb[32 + lane] = 0.0;
+      lb[64 + lane] = 0.0;
+      double mydiag = (lane < 16 && rok) ? a[row * CF_LD + c0 + lane] : 0.0;
+      double dcur = __shfl_sync(0xffffffffu, mydiag, 0);
+      double ediag = __shfl_sync(0xffffffffu, mydiag, 1);
+      double lprev = 0.0;
+      // loop-invariant addresses and predicates, pinned in registers
+      const unsigned thr_a = cf_saddr(thr + c0), piv_a = cf_saddr(pivinv + c0), lb_a = cf_saddr(lb);
+      const unsigned row_a = cf_saddr(a + (rok ? row : 0) * CF_LD + c0), lst_a = lb_a + 8 * lane;
+      unsigned lq_a = lb_a + 64 * 8;
+      int lane_r = lane;
+      asm volatile("" : "+r"(lane_r));
+      const int p_lo16 = lane < 16, p_row = rok && lower, p_diag = rok && !lower && warp == 0, p_w0 = warp == 0;
+      int bad = 0;
+      __syncwarp();
+#pragma unroll 1
+      for (int j = 0; j < nbp; j++) {
+        const double d = dcur;
+        const double thrj = cf_lds(thr_a + 8 * j);
+        const double u1 = __shfl_sync(0xffffffffu, e0, (j + 1) & 31);
+        const double u2 = __shfl_sync(0xffffffffu, e0, (j + 2) & 31);
+        double lq[17];
+#pragma unroll
+        for (int m = 3; m < 17; m++)
+          lq[m] = cf_lds(lq_a + 8 * m); // l(j-1+m, j-1): complete since the __syncwarp that closed the previous iteration
+        const bool ok = (d > thrj) && (d > 0.0);
+        const double rs = rsqrt(d); // speculative: a rejected pivot discards it
+        const double invp = ok ? rs : 0.0;
+        const double l = e0 * invp, l1 = u1 * invp, l2 = u2 * invp;
+        dcur = fma(-l1, l1, ediag);
+        mydiag = fma(-l, l, mydiag);
+        ediag = __shfl_sync(0xffffffffu, mydiag, (j + 2) & 31);
+        bad |= !ok;
+        const double x2 = fma(-lprev, lq[3], q[2]);
+#pragma unroll
+        for (int k = 2; k < 15; k++)
+          q[k] = fma(-lprev, lq[k + 2], q[k + 1]);
+        q[15] = 0.0;
+        const double e0n = fma(-l, l1, e1);
+        e1 = fma(-l, l2, x2);
+        const unsigned par = (j & 1) * 256;
+        cf_sts_if(lst_a + par, l, p_lo16);
+        cf_sts_if(row_a + 8 * j, l, p_row | (p_diag & (lane_r >= j)));
+        cf_sts_if(piv_a + 8 * j, invp, p_w0 & (lane_r == j));
+        e0 = e0n;
+        lprev = l;
+        lq_a = lb_a + par + 8 * j;
+        __syncwarp(); // l(., j) line complete for the next iteration's deferred update
+      }
+      if (strict && bad && tid == 0)
+        atomicExch(info, 1);
+      PT(1 + 3 * (c0 >> 4))
+    }
+    __syncthreads();
+    PT(2 + 3 * (c0 >> 4))
+    if (CF_B - c0 - 16 > 0 && nbp == 16) // (a partial block is the last pivot block: everything to its right is never read)
+      cf_trail16(a, c0);
+    __syncthreads();
+    PT(3 + 3 * (c0 >> 4))
+  }
+}
+
+// x = L^-1 for the 64x64 lower-triangular tile in `a` (zero pivots: pivinv = 0 -> zero row and column); t = scratch tile
+__device__ void cf_trinv64(const double *a, double *x, double *t, const double *pivinv, long long *dbgp = nullptr) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int idx = tid; idx < CF_B * CF_LD; idx += 256)
+    x[idx] = 0.0;
+  __syncthreads();
+  PT(13)
+  if (warp < 4) { // 16x16 diagonal blocks: lane c (< 16) owns column c of the inverse; forward substitution with the solved
+                  // entries in a SHIFTING register window (xs[m] = x(i-1-m)), so the row loop stays rolled
+    const int o = 16 * warp, c = lane & 15;
+    const unsigned a_o = cf_saddr(a + o * CF_LD + o), x_c = cf_saddr(x + o * CF_LD + o + c), pv = cf_saddr(pivinv + o);
+    const int act = lane < 16;
+    double xs[15];
+#pragma unroll
+    for (int m = 0; m < 15; m++)
+      xs[m] = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < 16; i++) {
+      const unsigned ai = a_o + i * (CF_LD * 8) + 8 * (i - 1); // &L(i, i-1); L(i, i-1-m) pairs with xs[m] (m < i)
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int m = 0; m < 14; m += 2) {
+        s0 = fma(cf_lds_if(ai - 8 * m, m < i), xs[m], s0);
+        s1 = fma(cf_lds_if(ai - 8 * m - 8, m + 1 < i), xs[m + 1], s1);
+      }
+      s0 = fma(cf_lds_if(ai - 8 * 14, 14 < i), xs[14], s0);
+      const double v = ((i == c) ? 1.0 : -(s0 + s1)) * cf_lds(pv + 8 * i);
+      cf_sts_if(x_c + i * (CF_LD * 8), v, act);
+#pragma unroll
+      for (int m = 14; m > 0; m--)
+        xs[m] = xs[m - 1];
+      xs[0] = v;
+    }
+  }
+  __syncthreads();
+  PT(14)
+  // merges: X21 = -X22 (L21 X11) at block sizes 16 and 32
+  for (int s = 16; s < CF_B; s *= 2) {
+    const int nbat = CF_B / (2 * s), bstr = 2 * s * CF_LD + 2 * s, nb8 = s / 8;
+    cf_mma_blocks<true>(t + s * CF_LD, a + s * CF_LD, x, nb8, nb8, s, 1.0, 0.0, false, nbat, bstr);
+    __syncthreads();
+    PT(s == 16 ? 15 : 17)
+    cf_mma_blocks<true>(x + s * CF_LD, x + s * CF_LD + s, t + s * CF_LD, nb8, nb8, s, -1.0, 0.0, false, nbat, bstr);
+    __syncthreads();
+    PT(s == 16 ? 16 : 18)
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
+  extern __shared__ double sm[];
+  // every shared array is carved from the one dynamic block: addresses of static __shared__ variables are re-derived from
+  // SR_CgaCtaId (S2R, ~100+ cycles) wherever the compiler rematerialises them - inside the pivot loop that tripled its latency
+  double *thr = sm + 5 * CF_B * CF_LD, *pivinv = thr + CF_B, *bcast = pivinv + CF_B; // bcast: 8 warps x 96, 16-byte aligned
+  __shared__ int s_epoch;
+  const int tid = threadIdx.x;
+  if (tid == 0)
+    s_epoch = *(volatile int *)p.ctrl + 1;
+  __syncthreads();
+  const int e = s_epoch;
+  const int Tp = p.Tp, T = p.T;
+  int *fdiag = p.flags, *fpan = p.flags + Tp; // D(k): L(k,k) and Linv(k) published; P(i,k): L(i,k) published
+  int *fud = fpan + T * Tp, *fus = fud + T;   // U(j,j) / U(i,i-1): tile updated through all panels but the last, for the spine
+
+  if (blockIdx.x == 0) {
+    // ---- spine: every diagonal block, back to back (warm instruction cache, no global-memory hop on the critical path) ----
+    double *a = sm, *b1 = sm + CF_B * CF_LD, *b2 = sm + 2 * CF_B * CF_LD, *b3 = sm + 3 * CF_B * CF_LD, *b4 = sm + 4 * CF_B * CF_LD;
+    CF_TS(0)
+    cf_load_tile(a, p.A, p.ld, min(CF_B, p.n), min(CF_B, p.n), true);
+    __syncthreads();
+    if (tid < CF_B)
+      thr[tid] = p.tol * a[tid * CF_LD + tid];
+    for (int k = 0; k < Tp; k++) {
+      const int bs = min(CF_B, p.npiv - CF_B * k), rv = min(CF_B, p.n - CF_B * k);
+      double *gA = p.A + (size_t)(CF_B * k) * p.ld + CF_B * k;
+      const bool has_panel = k + 1 < T, next_diag = k + 1 < Tp;
+      const int rv1 = has_panel ? min(CF_B, p.n - CF_B * (k + 1)) : 0;
+      double *gP = p.A + (size_t)(CF_B * k) * p.ld + CF_B * (k + 1);
+      if (k < 3)
+        CF_TS(1 + 2 * k)
+      long long *dbgp = (p.dbg && k == 1) ? p.dbg + (size_t)gridDim.x * 16 : nullptr;
+      PT(0)
+      cf_potrf64(a, bs, thr, p.tol == 0.0, pivinv, p.info, bcast, dbgp);
+      if (k < 3)
+        CF_TS(2 + 2 * k)
+      if (has_panel) { // the two tiles of the next step stream into b3 / b4 while the inverse is computed
+        if (tid == 0)
+          while (cf_ld_acquire(fus + k + 1) != e) {
+          }
+        if (tid == 32 && next_diag)
+          while (cf_ld_acquire(fud + k + 1) != e) {
+          }
+        __syncthreads();
+        cf_cpasync_tile(b3, gP, p.ld, rv1, CF_B, false);
+        if (next_diag)
+          cf_cpasync_tile(b4, gP + (size_t)CF_B * p.ld, p.ld, rv1, rv1, true);
+      }
+      cf_trinv64(a, b1, b2, pivinv, dbgp);
+      cf_store_tile(b1, p.LinvD + (size_t)k * CF_B * CF_B, CF_B, CF_B, CF_B, false);
+      PT(19)
+      cf_signal(fdiag + k, e);
+      PT(20)
+      cf_store_tile(a, gA, p.ld, rv, bs, true); // L(k,k): read only after the kernel
+      PT(21)
+      if (has_panel) {
+        if (next_diag && tid < CF_B)
+          thr[tid] = p.tol * __ldcg(p.diag0 + CF_B * (k + 1) + tid);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        PT(23)
+        __syncthreads();
+        PT(24)
+        cf_mma_64<true>(b3, b3, b1, 1.0, false, true); // L(k+1,k) = U(k+1,k) Linv(k)^T
+        __syncthreads();
+        PT(25)
+        cf_store_tile(b3, gP, p.ld, rv1, bs, false);
+        PT(26)
+        cf_signal(fpan + (k + 1) * Tp + k, e);
+        PT(27)
+        if (next_diag) {
+          cf_mma_64<false>(b4, b3, b3, -1.0, true, false);
+          __syncthreads();
+          double *tmp = a;
+          a = b4;
+          b4 = tmp;
+        }
+        PT(28)
+      }
+    }
+  } else if ((int)blockIdx.x < p.ntile) {
+    double *a = sm, *b1 = sm + CF_B * CF_LD, *b2 = sm + 2 * CF_B * CF_LD;
+    int j = 0, rem = blockIdx.x;
+    while (rem >= T - j) {
+      rem -= T - j;
+      j++;
+    }
+    const int i = j + rem;
+    const int rv = min(CF_B, p.n - CF_B * i), cv = min(CF_B, p.n - CF_B * j);
+    const int bs = min(CF_B, p.npiv - CF_B * j);
+    double *gA = p.A + (size_t)(CF_B * j) * p.ld + CF_B * i;
+    CF_TS(0)
+    cf_load_tile(a, gA, p.ld, rv, cv, i == j);
+    __syncthreads();
+    CF_TS(1)
+    if (i == j && tid < CF_B)
+      __stcg(p.diag0 + CF_B * j + tid, a[tid * CF_LD + tid]); // original diagonal: reference of the zero-pivot rule
+    const int kmax = (i == j) ? j - 1 : j; // the spine applies the last update of a diagonal tile itself
+    for (int k = 0; k < kmax; k++) {
+      cf_wait(fpan + i * Tp + k, e);
+      if (i != j)
+        cf_wait(fpan + j * Tp + k, e);
+      cf_load_tile(b1, p.A + (size_t)(CF_B * k) * p.ld + CF_B * i, p.ld, rv, CF_B, false);
+      if (i != j)
+        cf_load_tile(b2, p.A + (size_t)(CF_B * k) * p.ld + CF_B * j, p.ld, cv, CF_B, false);
+      __syncthreads();
+      cf_mma_64<false>(a, b1, (i != j) ? b2 : b1, -1.0, true, false);
+      __syncthreads();
+    }
+    CF_TS(3)
+    if (i == j) {
+      cf_store_tile(a, gA, p.ld, rv, cv, true);
+      cf_signal(fud + j, e);
+    } else if (i == j + 1) {
+      cf_store_tile(a, gA, p.ld, rv, cv, false);
+      cf_signal(fus + i, e);
+    } else {
+      cf_wait(fdiag + j, e);
+      CF_TS(4)
+      cf_load_tile(b1, p.LinvD + (size_t)j * CF_B * CF_B, CF_B, CF_B, CF_B, false);
+      __syncthreads();
+      CF_TS(5)
+      cf_mma_64<true>(a, a, b1, 1.0, false, true);
+      __syncthreads();
+      CF_TS(6)
+      cf_store_tile(a, gA, p.ld, rv, bs, false);
+      cf_signal(fpan + i * Tp + j, e);
+      CF_TS(7)
+    }
+  } else {
+    // ---- row block of the right-hand side: Y = M L^-T, right-looking ----
+    const int rb = blockIdx.x - p.ntile;
+    const int ms = p.mstride;
+    double *mrow = sm;                 // CF_RB x ms
+    double *Lt = sm + CF_RB * ms;      // 64 x CF_LD
+    double *yk = Lt + CF_B * CF_LD;    // CF_RB x CF_LD
+    const int row0 = rb * CF_RB;
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    for (int idx = tid; idx < CF_RB * Tp * CF_B; idx += 256) {
+      const int r = idx & (CF_RB - 1), k = idx >> 4;
+      const int row = row0 + r;
+      double v = 0.0;
+      if (k < p.npiv) {
+        if (row < p.mrows)
+          v = __ldcg(p.M + (size_t)k * p.ldm + row);
+        else if (row == p.mrows && p.z)
+          v = __ldcg(p.z + k);
+      }
+      mrow[r * ms + k] = v;
+    }
+    __syncthreads();
+    for (int k = 0; k < Tp; k++) {
+      const int bs = min(CF_B, p.npiv - CF_B * k);
+      cf_wait(fdiag + k, e);
+      cf_load_tile(Lt, p.LinvD + (size_t)k * CF_B * CF_B, CF_B, CF_B, CF_B, false);
+      __syncthreads();
+      { // yk (16 x 64) = mrow[:, 64k ..] * Linv^T (lower triangular: k4 <= column)
+        double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+        const double *pa = mrow + g * ms + CF_B * k + t;
+        const double *pb = Lt + (8 * warp + g) * CF_LD + t;
+        for (int k4 = 0; k4 <= 8 * warp + 7; k4 += 4) {
+          const double b = pb[k4];
+          dmma_m8n8k4(c00, c01, pa[k4], b);
+          dmma_m8n8k4(c10, c11, pa[8 * ms + k4], b);
+        }
+        yk[g * CF_LD + 8 * warp + 2 * t] = c00;
+        yk[g * CF_LD + 8 * warp + 2 * t + 1] = c01;
+        yk[(g + 8) * CF_LD + 8 * warp + 2 * t] = c10;
+        yk[(g + 8) * CF_LD + 8 * warp + 2 * t + 1] = c11;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < CF_RB * CF_B; idx += 256) {
+        const int r = idx & (CF_RB - 1), cc = idx >> 4;
+        const int row = row0 + r;
+        if (cc < bs) {
+          if (row < p.mrows)
+            __stcg(p.Y + (size_t)(CF_B * k + cc) * p.ldy + row, yk[r * CF_LD + cc]);
+          else if (row == p.mrows && p.w)
+            __stcg(p.w + CF_B * k + cc, yk[r * CF_LD + cc]);
+        }
+      }
+      for (int j = k + 1; j < Tp; j++) {
+        cf_wait(fpan + j * Tp + k, e);
+        cf_load_tile(Lt, p.A + (size_t)(CF_B * k) * p.ld + CF_B * j, p.ld, min(CF_B, p.n - CF_B * j), CF_B, false);
+        __syncthreads();
+        double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+        const double *pa = yk + g * CF_LD + t;
+        const double *pb = Lt + (8 * warp + g) * CF_LD + t;
+#pragma unroll 4
+        for (int k4 = 0; k4 < CF_B; k4 += 4) {
+          const double b = pb[k4];
+          dmma_m8n8k4(c00, c01, pa[k4], b);
+          dmma_m8n8k4(c10, c11, pa[8 * CF_LD + k4], b);
+        }
+        double *pm = mrow + g * ms + CF_B * j + 8 * warp + 2 * t;
+        pm[0] -= c00;
+        pm[1] -= c01;
+        pm[8 * ms] -= c10;
+        pm[8 * ms + 1] -= c11;
+        __syncthreads();
+      }
+    }
+  }
+  // ---- epoch bookkeeping: the last CTA to finish opens the next epoch ----
+  CF_TS(15)
+  __syncthreads();
+  if (tid == 0) {
+    const int done = atomicAdd(p.ctrl + 1, 1);
+    if (done == (int)gridDim.x - 1) {
+      p.ctrl[1] = 0;
+      __threadfence();
+      atomicAdd(p.ctrl, 1);
+    }
+  }
+}
+
+static bool g_cf_attr_set = false;
+
+// Factor the leading npiv columns of the n x n lower-stored matrix A in place (rows npiv..n-1 are solved along) and, when M is
+// given, solve Y = M L^-T (mrows x npiv) and w = L^-1 z in the same launch.
+int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const double *M, int ldm, int mrows, const double *z, double *Y,
+               int ldy, double *w, long long *dbg) {
+  if (npiv <= 0)
+    return OVP_OK;
+  if (npiv > n || n > ld)
+    return fail(c, OVP_ERR_BAD_ARGS, "chol_fused: bad sizes n=%d npiv=%d ld=%d", n, npiv, ld);
+  CholFusedArgs p;
+  p.A = A;
+  p.ld = ld;
+  p.n = n;
+  p.npiv = npiv;
+  p.tol = tol;
+  p.T = (n + CF_B - 1) / CF_B;
+  p.Tp = (npiv + CF_B - 1) / CF_B;
+  if (p.T > c->cf_maxT)
+    return fail(c, OVP_ERR_CAPACITY, "chol_fused: system %d exceeds the flag workspace (%d tiles)", n, c->cf_maxT);
+  p.ntile = 0;
+  for (int j = 0; j < p.Tp; j++)
+    p.ntile += p.T - j;
+  p.LinvD = c->cf_linv;
+  p.diag0 = c->cf_diag0;
+  p.flags = c->cf_flags;
+  p.ctrl = c->cf_ctrl;
+  p.info = c->dflags + 1;
+  p.M = M;
+  p.ldm = ldm;
+  p.mrows = M ? mrows : 0;
+  p.z = z;
+  p.Y = Y;
+  p.ldy = ldy;
+  p.w = w;
+  p.dbg = dbg;
+  const int vrows = M ? (mrows + (z ? 1 : 0)) : 0;
+  p.nrb = (vrows + CF_RB - 1) / CF_RB;
+  p.mstride = p.Tp * CF_B + 4;
+  size_t smem_tile = ((size_t)5 * CF_B * CF_LD + 2 * CF_B + 8 * 96) * sizeof(double);
+  size_t smem_rows = ((size_t)CF_RB * p.mstride + (size_t)CF_B * CF_LD + (size_t)CF_RB * CF_LD) * sizeof(double);
+  size_t smem = std::max(smem_tile, p.nrb ? smem_rows : 0);
+  if (smem > 220 * 1024)
+    return fail(c, OVP_ERR_CAPACITY, "chol_fused: %d columns need %zu B of shared memory", npiv, smem);
+  if (!g_cf_attr_set) {
+    OVP_CUDA(cudaFuncSetAttribute(chol_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    g_cf_attr_set = true;
+  }
+  const int grid = p.ntile + p.nrb;
+  double flops = (double)npiv * npiv * npiv / 3.0 + (double)(n - npiv) * npiv * npiv + (double)vrows * npiv * npiv;
+  prof_begin(c, PROF_POTRF, flops);
+  // cooperative launch: the spine waits on tile CTAs that wait on the spine, so the whole grid must be co-resident
+  void *kargs[] = {(void *)&p};
+  OVP_CUDA(cudaLaunchCooperativeKernel((const void *)chol_fused_kernel, dim3(grid), dim3(256), kargs, smem, c->stream));
+  c->launches++;
+  prof_end(c);
+  return OVP_OK;
+}
+
+} // namespace ovp

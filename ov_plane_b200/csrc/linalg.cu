@@ -406,6 +406,8 @@ int chol_partial(Ctx *c, DenseWs &ws, double *A, int ld, int n, int npiv, double
     return fail(c, OVP_ERR_CAPACITY, "chol_partial: system %d exceeds workspace %d", npiv, ws.cap);
   if (npiv <= 0)
     return OVP_OK;
+  if (c->use_fused_chol && !want_inverse)
+    return chol_fused(c, A, ld, n, npiv, tol, nullptr, 0, 0, nullptr, nullptr, 0, nullptr);
   const size_t smem = 3 * DB * DLD * sizeof(double);
   if (!g_potrf_attr_set) {
     OVP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

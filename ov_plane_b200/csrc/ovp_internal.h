@@ -74,6 +74,11 @@ struct Ctx {
   int *dcols = nullptr;        // gather index arrays (8 * Rcap ints)
   int *dflags = nullptr;       // device flags / status words (256 ints)
   double *dscal = nullptr;     // device scalars (256 doubles)
+  // fused Cholesky (cholfused.cu): diagonal-block inverses, inter-CTA flags, epoch word
+  double *cf_linv = nullptr, *cf_diag0 = nullptr;
+  int *cf_flags = nullptr, *cf_ctrl = nullptr;
+  int cf_maxT = 0;
+  bool use_fused_chol = true; // false: multi-kernel blocked Cholesky (kept for A/B timing)
   int max_meas_rows = 0;
   double *dHs = nullptr;       // stacked [H_x | H_cp | res], max_meas_rows x (Rcap) col-major
   size_t Hs_elems = 0;
@@ -136,6 +141,8 @@ int fail(Ctx *c, int status, const char *fmt, ...);
   } while (0)
 
 // ---- linalg.cu ---------------------------------------------------------------------------------------------------
+int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const double *M, int ldm, int mrows, const double *z, double *Y,
+               int ldy, double *w, long long *dbg = nullptr);
 void launch_gemm(Ctx *c, const GemmBatch &b);
 void launch_gemm1(Ctx *c, const GemmProblem &p, const int *flag = nullptr);
 // In-place blocked Cholesky of the leading `npiv` pivots of the symmetric (lower-stored) matrix A (size n x n, ld):

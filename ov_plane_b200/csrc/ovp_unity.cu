@@ -1,6 +1,8 @@
 // Unity translation unit of libovp.so (one TU: kernels defined in one file are launched from another).
 #include "linalg.cu"
+#include "cholfused.cu"
 #include "ekf.cu"
 #include "features.cu"
 #include "capi.cu"
 #include "capi2.cu"
+#include "debug_potrf.cu"

@@ -12,6 +12,7 @@ print("first panel (c0=0) clocks: [diag done, barrier, trsm done, barrier, trail
 print("second panel (c0=8): start(=end of panel 0) %d, regs loaded %d, pivots done %d, stored %d, panel end %d" % (us[17], us[18], us[19], us[11], us[10]))
 for n in (512, 1024, 2048, 4096):
     print("own DMMA gemm n=%d: %.2f TFLOP/s" % (n, ctx.selftest_dgemm_tflops(n, 5)))
-lat = np.zeros(8)
+lat = np.zeros(16)
 ctx._ck(ctx.lib.ovp_debug_fp64_latency(ctx.h, lat.ctypes.data_as(C.c_void_p)))
 print("dependent-chain cycles/op: dfma %.1f  rsqrt(double)+add %.1f  1/x+add %.1f  sqrt+add %.1f  shfl(double) %.1f  lds chain %.1f  rsqrtf+2 Newton %.1f" % tuple(lat[:7]))
+print("DMMA m8n8k4 one warp: dependent chain %.1f cycles/op, 8 independent accumulators %.1f cycles/op" % (lat[8], lat[9]))

@@ -1,0 +1,40 @@
+"""Timeline of the fused Cholesky kernel (cholfused.cu) on a synthetic SPD system: per-CTA globaltimer stamps."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from ov_plane_b200 import api, synth
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 474
+mrows = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+S = synth.make_scenario("tiny_points")
+ctx = api.Context(S.options, device=0, max_state=576, max_meas_rows=4096)
+for (nn, mm) in ((n, 0), (n, mrows), (128, 0), (64, 0)):
+    T = (nn + 63) // 64
+    cap = 3 + 16 * (T * (T + 1) // 2 + 40) + 64
+    out = np.zeros(cap)
+    ctx._ck(ctx.lib.ovp_debug_chol_fused(ctx.h, nn, mm, 50, out.ctypes.data_as(C.c_void_p), cap))
+    print("n=%d mrows=%d: fused chol %.1f us (fill+factor %.1f, fill %.1f)" % (nn, mm, out[0] - out[1], out[0], out[1]))
+    ncta = int(out[2])
+    ts = out[3:3 + 16 * ncta].reshape(ncta, 16) / 1e3  # us
+    def bidx(i, j):
+        return sum(T - q for q in range(j)) + (i - j)
+    if nn == n:
+        sp = ts[0]
+        print("  spine: start %.1f" % sp[0])
+        for k in range(min(3, T)):
+            s0, s1 = sp[1 + 2 * k], sp[2 + 2 * k]
+            nxt = sp[3 + 2 * k] if k + 1 < min(3, T) else float("nan")
+            print("  k=%d potrf %6.1f -> %6.1f (%.1f us)   until next potrf (trinv, publish, panel, update): %.1f us" % (k, s0, s1, s1 - s0, nxt - s1))
+        print("  last CTA end %.1f us" % ts[:, 15].max())
+        ph = out[3 + 16 * ncta:3 + 16 * ncta + 29]
+        names = ["potrf start"] + [x for b in range(4) for x in ("chain%d" % b, "sync%d" % b, "trail%d+sync" % b)] + ["trinv zero", "trinv base16", "merge16 T", "merge16 X", "merge32 T", "merge32 X",
+                 "store Linv", "signal D", "store L", "(unused)", "cp.async wait", "sync", "panel mma", "store panel", "signal P", "update mma"]
+        prev = 0.0
+        line = []
+        for nm, v in zip(names, ph):
+            if v >= 0:
+                line.append("%s %d" % (nm, v - prev))
+                prev = v
+        print("  spine k=1 phase cycles: " + " | ".join(line))
+        if mm:
+            print("  row-block CTAs end: min %.1f max %.1f" % (ts[T * (T + 1) // 2:, 15].min(), ts[T * (T + 1) // 2:, 15].max()))

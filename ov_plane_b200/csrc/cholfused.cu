@@ -86,103 +86,177 @@ __device__ __forceinline__ void cf_signal(int *flag, int e) {
   }
 }
 
-// idx in [0, 4096) -> (r, c) of a 64x64 tile such that a warp touches 8 columns x 4 consecutive rows: full 32-byte sectors in
-// global memory (column-major) and conflict-free 8-byte banks in shared memory ([r][c], stride CF_LD)
-__device__ __forceinline__ void cf_map(int idx, int &r, int &c) {
-  r = ((idx >> 5) & 15) * 4 + (idx & 3);
-  c = (idx >> 9) * 8 + ((idx >> 2) & 7);
+// Tiles sit in shared memory COLUMN-major like the global matrix (element (r, c) at c * CF_LD + r): global <-> shared copies
+// are 16-byte chunks of two consecutive rows (a warp moves one full 512-byte column), and the DMMA fragments (8 rows x 4 k)
+// still hit 16 distinct 8-byte banks per half warp because CF_LD mod 16 == 4.
+#define CF_AT(r, c) ((c) * CF_LD + (r))
+__device__ __forceinline__ void cf_chunk(int q, int &r2, int &c) {
+  c = q >> 5;
+  r2 = (q & 31) * 2;
 }
 
-// tile (rows r0.., cols c0..) of a column-major matrix -> smem [r][c]; entries outside (rv, cv) are zero
+// tile of a column-major matrix (g = its top-left element, ld even, 16-byte aligned) -> smem; entries outside (rv, cv), and above
+// the diagonal when lower_only, are zero
 __device__ __noinline__ void cf_load_tile(double *s, const double *g, int ld, int rv, int cv, bool lower_only) {
-  double v[16]; // all 16 loads of a thread are in flight before the first shared-memory store
+  double2 v[8]; // all loads of a thread are in flight before the first shared-memory store
 #pragma unroll
-  for (int q = 0; q < 16; q++) {
-    int r, c;
-    cf_map(threadIdx.x + 256 * q, r, c);
-    v[q] = (r < rv && c < cv && (!lower_only || r >= c)) ? __ldcg(g + (size_t)c * ld + r) : 0.0;
+  for (int q = 0; q < 8; q++) {
+    int r2, c;
+    cf_chunk(threadIdx.x + 256 * q, r2, c);
+    const bool v0 = r2 < rv && c < cv && (!lower_only || r2 >= c), v1 = r2 + 1 < rv && c < cv && (!lower_only || r2 + 1 >= c);
+    const double *src = g + (size_t)c * ld + r2;
+    if (v0 && v1) {
+      v[q] = __ldcg(reinterpret_cast<const double2 *>(src));
+    } else {
+      v[q].x = v0 ? __ldcg(src) : 0.0;
+      v[q].y = v1 ? __ldcg(src + 1) : 0.0;
+    }
   }
 #pragma unroll
-  for (int q = 0; q < 16; q++) {
-    int r, c;
-    cf_map(threadIdx.x + 256 * q, r, c);
-    s[r * CF_LD + c] = v[q];
+  for (int q = 0; q < 8; q++) {
+    int r2, c;
+    cf_chunk(threadIdx.x + 256 * q, r2, c);
+    *reinterpret_cast<double2 *>(s + CF_AT(r2, c)) = v[q];
   }
 }
-// asynchronous variant (cp.async, 8 bytes per element: the smem layout is the transpose of the global one): the copy runs
-// while the CTA computes; entries outside (rv, cv) / above the diagonal are zero-filled (src-size 0)
+// asynchronous variant (cp.async): the copy runs while the CTA computes; invalid entries are zero-filled (src-size 0)
 __device__ __noinline__ void cf_cpasync_tile(double *s, const double *g, int ld, int rv, int cv, bool lower_only) {
-#pragma unroll 4
-  for (int q = 0; q < 16; q++) {
-    int r, c;
-    cf_map(threadIdx.x + 256 * q, r, c);
-    const bool valid = r < rv && c < cv && (!lower_only || r >= c);
-    const double *src = valid ? g + (size_t)c * ld + r : g;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(cf_saddr(s + r * CF_LD + c)), "l"(src), "r"(valid ? 8 : 0) : "memory");
+#pragma unroll 2
+  for (int q = 0; q < 8; q++) {
+    int r2, c;
+    cf_chunk(threadIdx.x + 256 * q, r2, c);
+    const bool v0 = r2 < rv && c < cv && (!lower_only || r2 >= c), v1 = r2 + 1 < rv && c < cv && (!lower_only || r2 + 1 >= c);
+    const double *src = g + (size_t)c * ld + r2;
+    const unsigned dst = cf_saddr(s + CF_AT(r2, c));
+    if (v0 && v1) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    } else {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(v0 ? src : g), "r"(v0 ? 8 : 0) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 8), "l"(v1 ? src + 1 : g), "r"(v1 ? 8 : 0) : "memory");
+    }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __noinline__ void cf_store_tile(const double *s, double *g, int ld, int rv, int cv, bool lower_zero_upper) {
-  double v[16]; // all shared-memory reads first, then the 16 stores back to back
+  double2 v[8]; // all shared-memory reads first, then the stores back to back
 #pragma unroll
-  for (int q = 0; q < 16; q++) {
-    int r, c;
-    cf_map(threadIdx.x + 256 * q, r, c);
-    v[q] = (lower_zero_upper && r < c) ? 0.0 : s[r * CF_LD + c];
+  for (int q = 0; q < 8; q++) {
+    int r2, c;
+    cf_chunk(threadIdx.x + 256 * q, r2, c);
+    v[q] = *reinterpret_cast<const double2 *>(s + CF_AT(r2, c));
+    if (lower_zero_upper && r2 < c)
+      v[q].x = 0.0;
+    if (lower_zero_upper && r2 + 1 < c)
+      v[q].y = 0.0;
   }
 #pragma unroll
-  for (int q = 0; q < 16; q++) {
-    int r, c;
-    cf_map(threadIdx.x + 256 * q, r, c);
-    if (r < rv && c < cv)
-      __stcg(g + (size_t)c * ld + r, v[q]);
+  for (int q = 0; q < 8; q++) {
+    int r2, c;
+    cf_chunk(threadIdx.x + 256 * q, r2, c);
+    double *dst = g + (size_t)c * ld + r2;
+    if (c < cv) {
+      if (r2 + 1 < rv)
+        __stcg(reinterpret_cast<double2 *>(dst), v[q]);
+      else if (r2 < rv)
+        __stcg(dst, v[q].x);
+    }
   }
 }
 
-// C (64x64) = (ACC ? C : 0) + alpha * A (64 x 64) * B^T, all [row][k] in smem.  TRI: B is lower triangular (k <= column).
-// Warp tile 16 x 32.  When C aliases A or B the caller passes inplace = true (barrier between the last read and the first write).
-template <bool TRI> __device__ __noinline__ void cf_mma_64(double *C, const double *A, const double *B, double alpha, bool acc_c, bool inplace) {
+// C (64x64) = (acc_c ? C : 0) + alpha * A (64 x 64) * B^T, all tiles in smem (column-major: X(row, k) at k * CF_LD + row).
+// MODE 0: full.  MODE 1: B is lower triangular (B(j, k) = 0 for k > j): column block jb only needs k < 8 jb + 8; the 8 warps take
+// 32 rows x the column-block PAIR {cp, 7 - cp}, which balances the triangle (72 instead of 128 DMMA per warp).  MODE 2: only the
+// lower triangle of C is wanted (symmetric update of a diagonal tile): the 36 lower 8x8 blocks are dealt 5/4 per warp.
+// When C aliases A or B the caller passes inplace = true (barrier between the last read and the first write).
+template <int MODE> __device__ __noinline__ void cf_mma_64(double *C, const double *A, const double *B, double alpha, bool acc_c, bool inplace) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int rb = (warp & 3) * 16, cb = (warp >> 2) * 32;
-  double acc[2][4][2];
+  if (MODE != 2) {
+    const int rb = (warp & 1) * 32, cp = warp >> 1;
+    const int cb0 = 8 * cp, cb1 = 8 * (7 - cp);
+    const int kend1 = (MODE == 1) ? cb1 + 8 : CF_B, kend0 = (MODE == 1) ? cb0 + 8 : CF_B;
+    double acc[4][2][2];
 #pragma unroll
-  for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-      acc[i][j][0] = acc[i][j][1] = 0.0;
-  const double *pa0 = A + (rb + g) * CF_LD + t, *pa1 = pa0 + 8 * CF_LD;
-  const double *pb = B + (cb + g) * CF_LD + t;
-#pragma unroll 4
-  for (int k4 = 0; k4 < CF_B; k4 += 4) {
-    if (TRI && k4 > cb + 31)
-      break;
-    const double a0 = pa0[k4], a1 = pa1[k4];
+      for (int j = 0; j < 2; j++)
+        acc[i][j][0] = acc[i][j][1] = 0.0;
+    const double *pa = A + t * CF_LD + rb + g;
+    const double *pb0 = B + t * CF_LD + cb0 + g, *pb1 = B + t * CF_LD + cb1 + g;
+#pragma unroll 2
+    for (int k4 = 0; k4 < kend1; k4 += 4) {
+      double af[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      if (TRI && k4 > cb + 8 * j + 7)
-        continue;
-      const double b = pb[j * 8 * CF_LD + k4];
-      dmma_m8n8k4(acc[0][j][0], acc[0][j][1], a0, b);
-      dmma_m8n8k4(acc[1][j][0], acc[1][j][1], a1, b);
-    }
-  }
-  if (inplace)
-    __syncthreads();
+      for (int i = 0; i < 4; i++)
+        af[i] = pa[k4 * CF_LD + 8 * i];
+      const double b1v = pb1[k4 * CF_LD];
 #pragma unroll
-  for (int i = 0; i < 2; i++)
+      for (int i = 0; i < 4; i++)
+        dmma_m8n8k4(acc[i][1][0], acc[i][1][1], af[i], b1v);
+      if (k4 < kend0) {
+        const double b0v = pb0[k4 * CF_LD];
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        double *p = C + (rb + 8 * i + g) * CF_LD + cb + 8 * j + 2 * t + h;
-        *p = (acc_c ? *p : 0.0) + alpha * acc[i][j][h];
+        for (int i = 0; i < 4; i++)
+          dmma_m8n8k4(acc[i][0][0], acc[i][0][1], af[i], b0v);
       }
+    }
+    if (inplace)
+      __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          double *pc = C + CF_AT(rb + 8 * i + g, (j ? cb1 : cb0) + 2 * t + h);
+          *pc = (acc_c ? *pc : 0.0) + alpha * acc[i][j][h];
+        }
+  } else {
+    // row-block pair {rp, 7 - rp} owns 9 lower blocks; the even warp of the pair takes (7-rp, 0..4), the odd one the other 4
+    const int rp = warp >> 1, odd = warp & 1;
+    int bi[5], bj[5];
+    const int nb = odd ? 4 : 5;
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+      if (!odd) {
+        bi[q] = 7 - rp;
+        bj[q] = q;
+      } else if (q < 3 - rp) {
+        bi[q] = 7 - rp;
+        bj[q] = 5 + q;
+      } else {
+        bi[q] = rp;
+        bj[q] = q - (3 - rp);
+      }
+    }
+    double acc[5][2];
+#pragma unroll
+    for (int q = 0; q < 5; q++)
+      acc[q][0] = acc[q][1] = 0.0;
+#pragma unroll 2
+    for (int k4 = 0; k4 < CF_B; k4 += 4) {
+      const double *pk = A + (k4 + t) * CF_LD + g, *qk = B + (k4 + t) * CF_LD + g;
+#pragma unroll
+      for (int q = 0; q < 5; q++)
+        if (q < nb)
+          dmma_m8n8k4(acc[q][0], acc[q][1], pk[8 * bi[q]], qk[8 * bj[q]]);
+    }
+    if (inplace)
+      __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 5; q++)
+      if (q < nb)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          double *pc = C + CF_AT(8 * bi[q] + g, 8 * bj[q] + 2 * t + h);
+          *pc = (acc_c ? *pc : 0.0) + alpha * acc[q][h];
+        }
+  }
 }
 
 // Batched small products on 8x8 output blocks, round-robin over the 8 warps:
 //   C_b[mb*8 x nb*8] = beta * C_b + alpha * A_b[. x K] * op(B_b),  b = 0..nbatch-1, operand b at pointer + b * bstride
-// NN: B indexed [k][col]; otherwise [col][k].  lower: skip blocks above the block diagonal.
+// NN: B is K x N (B(k, col)); otherwise N x K (B(col, k)).  lower: skip blocks above the block diagonal.  Pointers address element (0,0).
 template <bool NN>
 __device__ __noinline__ void cf_mma_blocks(double *C, const double *A, const double *B, int mb, int nb, int K, double alpha, double beta,
                                               bool lower, int nbatch, int bstride) {
@@ -194,17 +268,17 @@ __device__ __noinline__ void cf_mma_blocks(double *C, const double *A, const dou
     const int bi = q % mb, bj = q / mb;
     if (lower && bj > bi)
       continue;
-    const double *pa = A + b * bstride + (8 * bi + g) * CF_LD + t;
-    const double *pb = NN ? (B + b * bstride + t * CF_LD + 8 * bj + g) : (B + b * bstride + (8 * bj + g) * CF_LD + t);
+    const double *pa = A + b * bstride + CF_AT(8 * bi + g, t);
+    const double *pb = NN ? (B + b * bstride + CF_AT(t, 8 * bj + g)) : (B + b * bstride + CF_AT(8 * bj + g, t));
     double c0 = 0.0, c1 = 0.0;
     for (int k4 = 0; k4 < K; k4 += 4) {
-      const double a = pa[k4];
-      const double bb = NN ? pb[k4 * CF_LD] : pb[k4];
+      const double a = pa[k4 * CF_LD];
+      const double bb = NN ? pb[k4] : pb[k4 * CF_LD];
       dmma_m8n8k4(c0, c1, a, bb);
     }
-    double *pc = C + b * bstride + (8 * bi + g) * CF_LD + 8 * bj + 2 * t;
+    double *pc = C + b * bstride + CF_AT(8 * bi + g, 8 * bj + 2 * t);
     pc[0] = (beta != 0.0 ? beta * pc[0] : 0.0) + alpha * c0;
-    pc[1] = (beta != 0.0 ? beta * pc[1] : 0.0) + alpha * c1;
+    pc[CF_LD] = (beta != 0.0 ? beta * pc[CF_LD] : 0.0) + alpha * c1;
   }
 }
 
@@ -236,8 +310,8 @@ __device__ __noinline__ void cf_trail16(double *a, int c0) {
     if (bi[s] >= 0) {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        fa[s][k] = a[(o + 8 * bi[s] + g) * CF_LD + c0 + 4 * k + t];
-        fb[s][k] = a[(o + 8 * bj[s] + g) * CF_LD + c0 + 4 * k + t];
+        fa[s][k] = a[CF_AT(o + 8 * bi[s] + g, c0 + 4 * k + t)];
+        fb[s][k] = a[CF_AT(o + 8 * bj[s] + g, c0 + 4 * k + t)];
       }
     }
   }
@@ -250,9 +324,9 @@ __device__ __noinline__ void cf_trail16(double *a, int c0) {
 #pragma unroll
   for (int s = 0; s < 3; s++)
     if (bi[s] >= 0) {
-      double *pc = a + (o + 8 * bi[s] + g) * CF_LD + o + 8 * bj[s] + 2 * t;
+      double *pc = a + CF_AT(o + 8 * bi[s] + g, o + 8 * bj[s] + 2 * t);
       pc[0] -= acc[s][0];
-      pc[1] -= acc[s][1];
+      pc[CF_LD] -= acc[s][1];
     }
 }
 
@@ -293,19 +367,19 @@ __device__ void cf_potrf64(double *a, int bs, const double *thr, bool strict, do
       double q[16];
 #pragma unroll
       for (int c = 0; c < 16; c++)
-        q[c] = (rok && (lower || c <= lane)) ? a[row * CF_LD + c0 + c] : 0.0;
+        q[c] = (rok && (lower || c <= lane)) ? a[CF_AT(row, c0 + c)] : 0.0;
       double e0 = q[0], e1 = q[1];
       double *lb = bcast + warp * 96; // [0,32) and [32,64): l(., j) by column parity (16 values + 16 zeros); [64,96): zeros
       lb[lane] = 0.0;
       lb[32 + lane] = 0.0;
       lb[64 + lane] = 0.0;
-      double mydiag = (lane < 16 && rok) ? a[row * CF_LD + c0 + lane] : 0.0;
+      double mydiag = (lane < 16 && rok) ? a[CF_AT(row, c0 + lane)] : 0.0;
       double dcur = __shfl_sync(0xffffffffu, mydiag, 0);
       double ediag = __shfl_sync(0xffffffffu, mydiag, 1);
       double lprev = 0.0;
       // loop-invariant addresses and predicates, pinned in registers
       const unsigned thr_a = cf_saddr(thr + c0), piv_a = cf_saddr(pivinv + c0), lb_a = cf_saddr(lb);
-      const unsigned row_a = cf_saddr(a + (rok ? row : 0) * CF_LD + c0), lst_a = lb_a + 8 * lane;
+      const unsigned row_a = cf_saddr(a + CF_AT(rok ? row : 0, c0)), lst_a = lb_a + 8 * lane;
       unsigned lq_a = lb_a + 64 * 8;
       int lane_r = lane;
       asm volatile("" : "+r"(lane_r));
@@ -339,7 +413,7 @@ __device__ void cf_potrf64(double *a, int bs, const double *thr, bool strict, do
         e1 = fma(-l, l2, x2);
         const unsigned par = (j & 1) * 256;
         cf_sts_if(lst_a + par, l, p_lo16);
-        cf_sts_if(row_a + 8 * j, l, p_row | (p_diag & (lane_r >= j)));
+        cf_sts_if(row_a + j * (CF_LD * 8), l, p_row | (p_diag & (lane_r >= j)));
         cf_sts_if(piv_a + 8 * j, invp, p_w0 & (lane_r == j));
         e0 = e0n;
         lprev = l;
@@ -369,7 +443,7 @@ __device__ void cf_trinv64(const double *a, double *x, double *t, const double *
   if (warp < 4) { // 16x16 diagonal blocks: lane c (< 16) owns column c of the inverse; forward substitution with the solved
                   // entries in a SHIFTING register window (xs[m] = x(i-1-m)), so the row loop stays rolled
     const int o = 16 * warp, c = lane & 15;
-    const unsigned a_o = cf_saddr(a + o * CF_LD + o), x_c = cf_saddr(x + o * CF_LD + o + c), pv = cf_saddr(pivinv + o);
+    const unsigned a_o = cf_saddr(a + CF_AT(o, o)), x_c = cf_saddr(x + CF_AT(o, o + c)), pv = cf_saddr(pivinv + o);
     const int act = lane < 16;
     double xs[15];
 #pragma unroll
@@ -377,16 +451,16 @@ __device__ void cf_trinv64(const double *a, double *x, double *t, const double *
       xs[m] = 0.0;
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
-      const unsigned ai = a_o + i * (CF_LD * 8) + 8 * (i - 1); // &L(i, i-1); L(i, i-1-m) pairs with xs[m] (m < i)
+      const unsigned ai = a_o + 8 * i + (i - 1) * (CF_LD * 8); // &L(i, i-1); L(i, i-1-m) pairs with xs[m] (m < i)
       double s0 = 0.0, s1 = 0.0;
 #pragma unroll
       for (int m = 0; m < 14; m += 2) {
-        s0 = fma(cf_lds_if(ai - 8 * m, m < i), xs[m], s0);
-        s1 = fma(cf_lds_if(ai - 8 * m - 8, m + 1 < i), xs[m + 1], s1);
+        s0 = fma(cf_lds_if(ai - m * (CF_LD * 8), m < i), xs[m], s0);
+        s1 = fma(cf_lds_if(ai - (m + 1) * (CF_LD * 8), m + 1 < i), xs[m + 1], s1);
       }
-      s0 = fma(cf_lds_if(ai - 8 * 14, 14 < i), xs[14], s0);
+      s0 = fma(cf_lds_if(ai - 14 * (CF_LD * 8), 14 < i), xs[14], s0);
       const double v = ((i == c) ? 1.0 : -(s0 + s1)) * cf_lds(pv + 8 * i);
-      cf_sts_if(x_c + i * (CF_LD * 8), v, act);
+      cf_sts_if(x_c + 8 * i, v, act);
 #pragma unroll
       for (int m = 14; m > 0; m--)
         xs[m] = xs[m - 1];
@@ -398,10 +472,10 @@ __device__ void cf_trinv64(const double *a, double *x, double *t, const double *
   // merges: X21 = -X22 (L21 X11) at block sizes 16 and 32
   for (int s = 16; s < CF_B; s *= 2) {
     const int nbat = CF_B / (2 * s), bstr = 2 * s * CF_LD + 2 * s, nb8 = s / 8;
-    cf_mma_blocks<true>(t + s * CF_LD, a + s * CF_LD, x, nb8, nb8, s, 1.0, 0.0, false, nbat, bstr);
+    cf_mma_blocks<true>(t + CF_AT(s, 0), a + CF_AT(s, 0), x, nb8, nb8, s, 1.0, 0.0, false, nbat, bstr);
     __syncthreads();
     PT(s == 16 ? 15 : 17)
-    cf_mma_blocks<true>(x + s * CF_LD, x + s * CF_LD + s, t + s * CF_LD, nb8, nb8, s, -1.0, 0.0, false, nbat, bstr);
+    cf_mma_blocks<true>(x + CF_AT(s, 0), x + CF_AT(s, s), t + CF_AT(s, 0), nb8, nb8, s, -1.0, 0.0, false, nbat, bstr);
     __syncthreads();
     PT(s == 16 ? 16 : 18)
   }
@@ -429,7 +503,7 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
     cf_load_tile(a, p.A, p.ld, min(CF_B, p.n), min(CF_B, p.n), true);
     __syncthreads();
     if (tid < CF_B)
-      thr[tid] = p.tol * a[tid * CF_LD + tid];
+      thr[tid] = p.tol * a[CF_AT(tid, tid)];
     for (int k = 0; k < Tp; k++) {
       const int bs = min(CF_B, p.npiv - CF_B * k), rv = min(CF_B, p.n - CF_B * k);
       double *gA = p.A + (size_t)(CF_B * k) * p.ld + CF_B * k;
@@ -458,9 +532,9 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       cf_trinv64(a, b1, b2, pivinv, dbgp);
       cf_store_tile(b1, p.LinvD + (size_t)k * CF_B * CF_B, CF_B, CF_B, CF_B, false);
       PT(19)
-      cf_signal(fdiag + k, e);
+      cf_store_tile(a, gA, p.ld, rv, bs, true); // L(k,k): read only after the kernel; gives the Linv stores time to land
       PT(20)
-      cf_store_tile(a, gA, p.ld, rv, bs, true); // L(k,k): read only after the kernel
+      cf_signal(fdiag + k, e);
       PT(21)
       if (has_panel) {
         if (next_diag && tid < CF_B)
@@ -469,20 +543,20 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
         PT(23)
         __syncthreads();
         PT(24)
-        cf_mma_64<true>(b3, b3, b1, 1.0, false, true); // L(k+1,k) = U(k+1,k) Linv(k)^T
+        cf_mma_64<1>(b3, b3, b1, 1.0, false, true); // L(k+1,k) = U(k+1,k) Linv(k)^T
         __syncthreads();
         PT(25)
         cf_store_tile(b3, gP, p.ld, rv1, bs, false);
         PT(26)
-        cf_signal(fpan + (k + 1) * Tp + k, e);
-        PT(27)
         if (next_diag) {
-          cf_mma_64<false>(b4, b3, b3, -1.0, true, false);
+          cf_mma_64<2>(b4, b3, b3, -1.0, true, false); // lower triangle of the next diagonal tile
           __syncthreads();
           double *tmp = a;
           a = b4;
           b4 = tmp;
         }
+        PT(27)
+        cf_signal(fpan + (k + 1) * Tp + k, e); // after the update: the panel stores have landed, the release costs nothing
         PT(28)
       }
     }
@@ -502,7 +576,7 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
     __syncthreads();
     CF_TS(1)
     if (i == j && tid < CF_B)
-      __stcg(p.diag0 + CF_B * j + tid, a[tid * CF_LD + tid]); // original diagonal: reference of the zero-pivot rule
+      __stcg(p.diag0 + CF_B * j + tid, a[CF_AT(tid, tid)]); // original diagonal: reference of the zero-pivot rule
     const int kmax = (i == j) ? j - 1 : j; // the spine applies the last update of a diagonal tile itself
     for (int k = 0; k < kmax; k++) {
       cf_wait(fpan + i * Tp + k, e);
@@ -512,7 +586,10 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       if (i != j)
         cf_load_tile(b2, p.A + (size_t)(CF_B * k) * p.ld + CF_B * j, p.ld, cv, CF_B, false);
       __syncthreads();
-      cf_mma_64<false>(a, b1, (i != j) ? b2 : b1, -1.0, true, false);
+      if (i != j)
+        cf_mma_64<0>(a, b1, b2, -1.0, true, false);
+      else
+        cf_mma_64<2>(a, b1, b1, -1.0, true, false);
       __syncthreads();
     }
     CF_TS(3)
@@ -528,7 +605,7 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       cf_load_tile(b1, p.LinvD + (size_t)j * CF_B * CF_B, CF_B, CF_B, CF_B, false);
       __syncthreads();
       CF_TS(5)
-      cf_mma_64<true>(a, a, b1, 1.0, false, true);
+      cf_mma_64<1>(a, a, b1, 1.0, false, true);
       __syncthreads();
       CF_TS(6)
       cf_store_tile(a, gA, p.ld, rv, bs, false);
@@ -565,9 +642,9 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       { // yk (16 x 64) = mrow[:, 64k ..] * Linv^T (lower triangular: k4 <= column)
         double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
         const double *pa = mrow + g * ms + CF_B * k + t;
-        const double *pb = Lt + (8 * warp + g) * CF_LD + t;
+        const double *pb = Lt + CF_AT(8 * warp + g, t);
         for (int k4 = 0; k4 <= 8 * warp + 7; k4 += 4) {
-          const double b = pb[k4];
+          const double b = pb[k4 * CF_LD];
           dmma_m8n8k4(c00, c01, pa[k4], b);
           dmma_m8n8k4(c10, c11, pa[8 * ms + k4], b);
         }
@@ -593,10 +670,10 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
         __syncthreads();
         double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
         const double *pa = yk + g * CF_LD + t;
-        const double *pb = Lt + (8 * warp + g) * CF_LD + t;
+        const double *pb = Lt + CF_AT(8 * warp + g, t);
 #pragma unroll 4
         for (int k4 = 0; k4 < CF_B; k4 += 4) {
-          const double b = pb[k4];
+          const double b = pb[k4 * CF_LD];
           dmma_m8n8k4(c00, c01, pa[k4], b);
           dmma_m8n8k4(c10, c11, pa[8 * CF_LD + k4], b);
         }
@@ -630,8 +707,8 @@ int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const dou
                int ldy, double *w, long long *dbg) {
   if (npiv <= 0)
     return OVP_OK;
-  if (npiv > n || n > ld)
-    return fail(c, OVP_ERR_BAD_ARGS, "chol_fused: bad sizes n=%d npiv=%d ld=%d", n, npiv, ld);
+  if (npiv > n || n > ld || (ld & 1) || ((uintptr_t)A & 15))
+    return fail(c, OVP_ERR_BAD_ARGS, "chol_fused: bad sizes / alignment n=%d npiv=%d ld=%d", n, npiv, ld);
   CholFusedArgs p;
   p.A = A;
   p.ld = ld;

@@ -447,7 +447,7 @@ class Context(object):
     def profile_report(self):
         ms, cnt, work = np.zeros(5), np.zeros(5, dtype=np.int64), np.zeros(5)
         self._ck(self.lib.ovp_profile_report(self.h, _p(ms), _p(cnt), _p(work)))
-        names = ["gemm_f64_kernel", "gram_kernel", "potrf_diag_kernel", "feature_kernel", "other"]
+        names = ["gemm_f64_kernel", "gram_kernel", "chol_fused_kernel", "feature_kernel", "other"]
         return {n: dict(ms=float(ms[i]), launches=int(cnt[i]), work=float(work[i])) for i, n in enumerate(names)}
 
     def transfer_bytes(self):

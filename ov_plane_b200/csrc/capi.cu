@@ -329,8 +329,6 @@ int ovp_create(const ovp_state_options *opt, int device, int max_state, int max_
   st = ws_alloc(c, c->wsS, c->Rcap);
   if (st)
     return st;
-  if (const char *ev = getenv("OVP_FUSED_CHOL")) // A/B switch for timing the two Cholesky paths
-    c->use_fused_chol = atoi(ev) != 0;
   c->cf_maxT = c->Rcap / 64 + 1;
   OVP_CUDA(cudaMalloc(&c->cf_linv, (size_t)c->cf_maxT * 4096 * sizeof(double)));
   OVP_CUDA(cudaMalloc(&c->cf_diag0, (size_t)c->cf_maxT * 64 * sizeof(double)));

@@ -682,7 +682,7 @@ static int compress_common(Ctx *c, double *H_x, int cols, double *H_cp, double *
   int st = gram_of_stacked(c, rows, nc1, ld);
   if (st)
     return st;
-  st = chol_partial(c, c->wsG, c->wsG.S, c->wsG.cap, nc1, cols, 1e-11, false);
+  st = chol_partial(c, c->wsG.S, c->wsG.cap, nc1, cols, 1e-11);
   if (st)
     return st;
   // R = L[0:cols,0:cols]^T ; carried columns = L[cols.., 0:cols]^T
@@ -782,7 +782,7 @@ int ovp_msckf_update_gathered(ovp_ctx *h, const double *d_blocks, int G, const i
   st = gram_of_stacked(c, rows, nc1, ld);
   if (st)
     return st;
-  st = chol_partial(c, c->wsG, c->wsG.S, c->wsG.cap, nc1, n, 1e-11, false);
+  st = chol_partial(c, c->wsG.S, c->wsG.cap, nc1, n, 1e-11);
   if (st)
     return st;
   double *d_z = c->dvec + c->Rcap;
@@ -1162,7 +1162,6 @@ int ovp_selftest_dgemm_tflops(ovp_ctx *h, int n, int iters, double *tflops) {
   dmma_selftest_fill<<<(unsigned)((e + 255) / 256), 256, 0, c->stream>>>(A, e, 1.0);
   dmma_selftest_fill<<<(unsigned)((e + 255) / 256), 256, 0, c->stream>>>(B, e, 0.5);
   GemmProblem p = make_problem(n, n, n, mv(A, n), mv(B, n), C, n);
-  c->force_tile64 = (iters > 0);
   for (int i = 0; i < 3; i++)
     launch_gemm1(c, p);
   cudaEventRecord(c->ev[2], c->stream);
@@ -1173,7 +1172,6 @@ int ovp_selftest_dgemm_tflops(ovp_ctx *h, int n, int iters, double *tflops) {
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
   *tflops = 2.0 * (double)n * n * n * iters / (ms * 1e-3) / 1e12;
-  c->force_tile64 = false;
   cudaFree(A);
   cudaFree(B);
   cudaFree(C);
@@ -1266,59 +1264,6 @@ int ovp_transfer_bytes(ovp_ctx *h, int64_t *h2d, int64_t *d2h) {
 } // extern "C"
 
 // ---- micro-benchmarks of single kernels (tools/microbench.py) ------------------------------------------------------------
-namespace ovp {
-__global__ void smem_probe_kernel(double *out) {
-  extern __shared__ double sm[];
-  if (threadIdx.x == 0) {
-    sm[0] = 1.0;
-    out[0] = sm[0];
-  }
-}
-} // namespace ovp
-extern "C" int ovp_debug_kernel_times(ovp_ctx *h, int iters, double *us_out /*[4]*/) {
-  Ctx *c = &h->c;
-  const size_t smem = 3 * DB * DLD * sizeof(double);
-  OVP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  OVP_CUDA(cudaFuncSetAttribute(smem_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // SPD 64x64 test block in wsS.S: I * 4 + small off-diagonals
-  std::vector<double> A((size_t)64 * 64);
-  for (int j = 0; j < 64; j++)
-    for (int i = 0; i < 64; i++)
-      A[(size_t)j * 64 + i] = (i == j) ? 4.0 : 0.01 * ((i * 7 + j * 3) % 5);
-  std::vector<double> d0(64, 4.0);
-  OVP_CUDA(cudaMemcpy(c->wsS.diag0, d0.data(), 64 * sizeof(double), cudaMemcpyHostToDevice));
-  float ms;
-  for (int variant = 0; variant < 4; variant++) {
-    for (int rep = 0; rep < 2; rep++) { // rep 0 = warm-up
-      if (rep == 1)
-        cudaEventRecord(c->ev[4], c->stream);
-      for (int it = 0; it < iters; it++) {
-        if (variant == 0) {
-          cudaMemcpy2DAsync(c->wsS.S, (size_t)c->wsS.cap * 8, A.data(), 64 * 8, 64 * 8, 64, cudaMemcpyHostToDevice, c->stream);
-        } else if (variant == 1) {
-          cudaMemcpy2DAsync(c->wsS.S, (size_t)c->wsS.cap * 8, A.data(), 64 * 8, 64 * 8, 64, cudaMemcpyHostToDevice, c->stream);
-          potrf_diag_kernel<<<1, 256, smem, c->stream>>>(c->wsS.S, c->wsS.cap, 64, c->wsS.diag0, 0.0, c->wsS.Linv, c->wsS.cap, c->dflags + 8,
-                                                         (long long *)(c->dscal + 128));
-        } else if (variant == 2) {
-          smem_probe_kernel<<<1, 256, smem, c->stream>>>(c->dscal + 100);
-        } else {
-          smem_probe_kernel<<<1, 256, 1024, c->stream>>>(c->dscal + 100);
-        }
-      }
-      if (rep == 1)
-        cudaEventRecord(c->ev[5], c->stream);
-      OVP_CUDA(cudaStreamSynchronize(c->stream));
-    }
-    cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
-    us_out[variant] = 1e3 * ms / iters;
-  }
-  long long ts[16];
-  OVP_CUDA(cudaMemcpy(ts, c->dscal + 128, sizeof(ts), cudaMemcpyDeviceToHost));
-  for (int i = 0; i < 16; i++)
-    us_out[4 + i] = (double)(ts[i] - ts[0]);
-  return OVP_OK;
-}
-
 namespace ovp {
 // dependent-chain latencies of fp64 operations on this GPU (cycles per op), one warp
 __global__ void fp64_latency_kernel(double *out, double seed) {

@@ -193,23 +193,11 @@ int ekf_update_core(Ctx *c, const int *d_cols, int nc, MatView HT, int rr, const
   }
   double *d_w = c->dvec;                 // [0, Rcap)
   double *d_dx = c->dvec + 2 * c->Rcap;  // [2Rcap, 2Rcap + Nmax)
-  if (c->use_fused_chol) {
-    // 3-5. S = L L^T, Y = M L^-T, w = L^-1 z in one launch (cholfused.cu)
+  // 3-5. S = L L^T, Y = M L^-T, w = L^-1 z in one launch (cholfused.cu)
+  {
     int st = chol_fused(c, c->wsS.S, c->wsS.cap, rr, rr, 0.0, c->dM, c->Nmax, N, d_z, c->dY, c->Nmax, d_w);
     if (st)
       return st;
-  } else {
-    // 3. S = L L^T, L^-1
-    int st = chol_partial(c, c->wsS, c->wsS.S, c->wsS.cap, rr, rr, 0.0, true);
-    if (st)
-      return st;
-    // 4. Y = M * L^-T
-    {
-      GemmProblem p = make_problem(N, rr, rr, mv(c->dM, c->Nmax), mv(c->wsS.Linv, c->wsS.cap, 1), c->dY, c->Nmax);
-      launch_gemm1(c, p);
-    }
-    // 5. w = L^-1 z
-    launch_gemv(c, rr, rr, mv(c->wsS.Linv, c->wsS.cap), d_z, d_w);
   }
   // chi2 = |w|^2 ; gate
   double *chi2 = d_chi2 ? d_chi2 : c->dscal;

@@ -347,15 +347,22 @@ __global__ void __launch_bounds__(128) feature_kernel(FeatArgs a) {
 // -------------------------------------------------------------------------------------------------------------------
 // Gram kernel: partial[z] = Hs[k-chunk z, :]^T Hs[k-chunk z, :]  (lower 64x64 tiles), FP64 DMMA
 // -------------------------------------------------------------------------------------------------------------------
+// Operand tiles are 64 columns of Hs x 16 rows (k), k contiguous in global memory AND in shared memory ([col][k], stride 20
+// doubles: 16-byte vector copies without bank conflicts, DMMA fragment reads (8 cols x 4 k) on 16 distinct 8-byte banks because
+// 20 mod 16 == 4); the next k-step is prefetched into registers while the current one is in the tensor pipe; a diagonal tile
+// loads its operand once.
+#define GRAM_KS 20
 __global__ void __launch_bounds__(128) gram_kernel(const double *Hs, int ld, int rows, int nc, int kchunk, double *part, int ldp) {
   const int tm = blockIdx.y, tn = blockIdx.x;
   if (tm < tn)
     return;
-  __shared__ double As[OVP_GK][OVP_GLD];
-  __shared__ double Bs[OVP_GK][OVP_GLD];
+  __shared__ __align__(16) double As[OVP_GT][GRAM_KS];
+  __shared__ __align__(16) double Bs[OVP_GT][GRAM_KS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;
+  const int g = lane >> 2, t = lane & 3;
   const int m0 = tm * OVP_GT, n0 = tn * OVP_GT;
+  const bool diag = tm == tn;
   const int kbeg = blockIdx.z * kchunk;
   const int kend = min(rows, kbeg + kchunk);
   double acc[4][4][2];
@@ -364,26 +371,54 @@ __global__ void __launch_bounds__(128) gram_kernel(const double *Hs, int ld, int
 #pragma unroll
     for (int j = 0; j < 4; j++)
       acc[i][j][0] = acc[i][j][1] = 0.0;
+  // thread -> 4 chunks of 2 k per operand: chunk e = tid + 128 q: column e >> 3, k offset (e & 7) * 2
+  double2 ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int e = tid + 128 * q, col = e >> 3, k2 = k0 + (e & 7) * 2;
+      const int gi = m0 + col, gj = n0 + col;
+      double2 z = make_double2(0.0, 0.0);
+      ra[q] = z;
+      rb[q] = z;
+      if (gi < nc) {
+        const double *src = Hs + (size_t)gi * ld + k2;
+        if (k2 + 1 < kend)
+          ra[q] = *reinterpret_cast<const double2 *>(src);
+        else if (k2 < kend)
+          ra[q].x = src[0];
+      }
+      if (!diag && gj < nc) {
+        const double *src = Hs + (size_t)gj * ld + k2;
+        if (k2 + 1 < kend)
+          rb[q] = *reinterpret_cast<const double2 *>(src);
+        else if (k2 < kend)
+          rb[q].x = src[0];
+      }
+    }
+  };
+  fetch(kbeg);
+  const double(*Bt)[GRAM_KS] = diag ? As : Bs;
   for (int k0 = kbeg; k0 < kend; k0 += OVP_GK) {
 #pragma unroll
-    for (int t = 0; t < 8; t++) {
-      int e = tid + t * 128;
-      int kk = e & 15, ii = e >> 4;
-      int gk = k0 + kk;
-      int gi = m0 + ii, gj = n0 + ii;
-      As[kk][ii] = (gk < kend && gi < nc) ? Hs[(size_t)gi * ld + gk] : 0.0;
-      Bs[kk][ii] = (gk < kend && gj < nc) ? Hs[(size_t)gj * ld + gk] : 0.0;
+    for (int q = 0; q < 4; q++) {
+      const int e = tid + 128 * q, col = e >> 3, ko = (e & 7) * 2;
+      *reinterpret_cast<double2 *>(&As[col][ko]) = ra[q];
+      if (!diag)
+        *reinterpret_cast<double2 *>(&Bs[col][ko]) = rb[q];
     }
     __syncthreads();
+    if (k0 + OVP_GK < kend)
+      fetch(k0 + OVP_GK);
 #pragma unroll
     for (int kk = 0; kk < OVP_GK; kk += 4) {
       double av[4], bv[4];
 #pragma unroll
       for (int i = 0; i < 4; i++)
-        av[i] = As[kk + (lane & 3)][wm * 32 + i * 8 + (lane >> 2)];
+        av[i] = As[wm * 32 + i * 8 + g][kk + t];
 #pragma unroll
       for (int j = 0; j < 4; j++)
-        bv[j] = Bs[kk + (lane & 3)][wn * 32 + j * 8 + (lane >> 2)];
+        bv[j] = Bt[wn * 32 + j * 8 + g][kk + t];
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -399,8 +434,8 @@ __global__ void __launch_bounds__(128) gram_kernel(const double *Hs, int ld, int
     for (int j = 0; j < 4; j++)
 #pragma unroll
       for (int h = 0; h < 2; h++) {
-        int gi = m0 + wm * 32 + i * 8 + (lane >> 2);
-        int gj = n0 + wn * 32 + j * 8 + (lane & 3) * 2 + h;
+        int gi = m0 + wm * 32 + i * 8 + g;
+        int gj = n0 + wn * 32 + j * 8 + t * 2 + h;
         if (gi < nc && gj < nc)
           out[(size_t)gj * ldp + gi] = acc[i][j][h];
       }

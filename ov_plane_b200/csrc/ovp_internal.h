@@ -26,13 +26,10 @@ struct ImuSample {
   double wm[3], am[3];
 };
 
-// Workspace for one dense system of up to `cap` rows/cols (padded)
+// Workspace for one dense system of up to `cap` rows/cols
 struct DenseWs {
-  int cap = 0;        // max system size (multiple of 64)
-  double *S = nullptr;    // cap x cap (Gram / S, factored in place to lower L)
-  double *Linv = nullptr; // cap x cap
-  double *T = nullptr;    // cap x cap scratch for the inverse merges
-  double *diag0 = nullptr; // cap: original diagonal (pivot threshold reference)
+  int cap = 0;         // max system size (multiple of 64)
+  double *S = nullptr; // cap x cap (Gram / S, factored in place to lower L)
 };
 
 struct Ctx {
@@ -41,7 +38,6 @@ struct Ctx {
   ovp_state_options opt;
   std::string last_error;
   int64_t launches = 0;
-  bool force_tile64 = false; // micro-benchmarks only
   bool use_graphs = true;    // replay the static launch sequence of a prepared batch as a CUDA graph
 
   // --- State mirror -------------------------------------------------------------------------------------------
@@ -78,7 +74,6 @@ struct Ctx {
   double *cf_linv = nullptr, *cf_diag0 = nullptr;
   int *cf_flags = nullptr, *cf_ctrl = nullptr;
   int cf_maxT = 0;
-  bool use_fused_chol = true; // false: multi-kernel blocked Cholesky (kept for A/B timing)
   int max_meas_rows = 0;
   double *dHs = nullptr;       // stacked [H_x | H_cp | res], max_meas_rows x (Rcap) col-major
   size_t Hs_elems = 0;
@@ -146,9 +141,7 @@ int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const dou
 void launch_gemm(Ctx *c, const GemmBatch &b);
 void launch_gemm1(Ctx *c, const GemmProblem &p, const int *flag = nullptr);
 // In-place blocked Cholesky of the leading `npiv` pivots of the symmetric (lower-stored) matrix A (size n x n, ld):
-// on exit A[:, 0:npiv] holds L (all n rows), diagonal-block inverses and the full inverse of L[0:npiv,0:npiv] are in
-// ws.Linv (ld = ws.cap).  Pivots <= tol * original diagonal are treated as exact zeros (rank-deficient Gram matrices).
-int chol_partial(Ctx *c, DenseWs &ws, double *A, int ld, int n, int npiv, double tol, bool want_inverse);
+int chol_partial(Ctx *c, double *A, int ld, int n, int npiv, double tol); // one launch of chol_fused
 int ws_alloc(Ctx *c, DenseWs &ws, int cap);
 void ws_free(DenseWs &ws);
 // y = alpha * A(m x k view) * x  (one warp per row)

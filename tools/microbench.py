@@ -4,12 +4,6 @@ import numpy as np
 from ov_plane_b200 import api, synth
 S = synth.make_scenario("tiny_points")
 ctx = api.Context(S.options, device=0, max_state=576, max_meas_rows=4096)
-us = np.zeros(32)
-ctx._ck(ctx.lib.ovp_debug_kernel_times(ctx.h, 200, us.ctypes.data_as(C.c_void_p)))
-print("per-iteration us: [memcpy2D 32KB H2D only, memcpy+potrf_diag, empty kernel 100KB smem, empty kernel 1KB smem] =", np.round(us[:4], 2))
-print("potrf phase clocks since load-done: [barrier, factor done, inverse bases, inverse merges, stored] =", us[5:10])
-print("first panel (c0=0) clocks: [diag done, barrier, trsm done, barrier, trailing done, barrier] =", us[12:18])
-print("second panel (c0=8): start(=end of panel 0) %d, regs loaded %d, pivots done %d, stored %d, panel end %d" % (us[17], us[18], us[19], us[11], us[10]))
 for n in (512, 1024, 2048, 4096):
     print("own DMMA gemm n=%d: %.2f TFLOP/s" % (n, ctx.selftest_dgemm_tflops(n, 5)))
 lat = np.zeros(16)

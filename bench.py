@@ -317,6 +317,9 @@ def main():
                 "traffic": traffic,
                 "peak_source": "fp64: cuBLAS DGEMM 4096^3 via torch.matmul measured in this run (MEASURED_PEAKS.json has no fp64 entry; "
                                "its bf16 %.0f TF/s does not apply: the path computes in fp64 on DMMA, DESIGN.md)" % peaks.get("bf16_tflops", 0)}
+    if dname == "chol_fused_kernel":
+        roof["note"] = ("latency-bound: one cooperative launch factors a ~470-wide SPD system (and solves Y = M L^-T); the serial pivot chain, "
+                        "not a throughput unit, bounds it (DESIGN.md 4.1) - frac against the tensor peak is reported as measured")
     roof["avg_launch_us"] = 1e3 * dv["ms"] / max(1, dv["launches"])
     roof["share_of_step"] = dv["ms"] / max(1e-9, total_prof_ms)
     roof["per_kernel_ms_per_step"] = {k: v["ms"] / nprof for k, v in prof.items()}

@@ -130,9 +130,12 @@ __device__ __noinline__ void cf_cpasync_tile(double *s, const double *g, int ld,
     const unsigned dst = cf_saddr(s + CF_AT(r2, c));
     if (v0 && v1) {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    } else {
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(v0 ? src : g), "r"(v0 ? 8 : 0) : "memory");
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 8), "l"(v1 ? src + 1 : g), "r"(v1 ? 8 : 0) : "memory");
+    } else { // edge / diagonal-crossing chunk: through registers with L2-only loads (an 8-byte cp.async would have to be .ca, and a
+             // line left in this SM's L1 by an earlier launch on the same buffers must never be served)
+      double2 v;
+      v.x = v0 ? __ldcg(src) : 0.0;
+      v.y = v1 ? __ldcg(src + 1) : 0.0;
+      *reinterpret_cast<double2 *>(s + CF_AT(r2, c)) = v;
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -338,8 +341,8 @@ __device__ __noinline__ void cf_trail16(double *a, int c0) {
 // shuffle -> fma (the next pivot is rebuilt on every lane from a value shuffled one column earlier).  The trailing update
 // inside the tile is DMMA.  Zero-pivot rule: pivot <= thr (= tol * original diagonal) or <= 0 -> column of zeros, pivinv = 0
 // (rank-deficient Gram matrices); strict (tol == 0) flags *info instead (S must be positive definite).
-__device__ void cf_potrf64(double *a, int bs, const double *thr, bool strict, double *pivinv, int *info, double *bcast,
-                           long long *dbgp = nullptr) {
+__device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool strict, double *pivinv, int *info, double *bcast,
+                           const int *poll0, const int *poll1, int epoch, long long *dbgp = nullptr) {
 #define PT(slot)                                                                                                             \
   if (dbgp && threadIdx.x == 0)                                                                                              \
     dbgp[slot] = clock64();
@@ -347,17 +350,32 @@ __device__ void cf_potrf64(double *a, int bs, const double *thr, bool strict, do
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   if (tid < CF_B)
     pivinv[tid] = 0.0;
+  if (bs < CF_B) // partial tile: the chain writes only bs rows of the diagonal blocks of x
+    for (int idx = tid; idx < CF_B * CF_LD; idx += 256)
+      x[idx] = 0.0;
   __syncthreads();
   for (int c0 = 0; c0 < bs; c0 += 16) {
     const int nbp = min(16, bs - c0);
-    const int nw = max(1, (CF_B - c0 - 16) / 16);
-    if (warp_u < nw) {
+    const int vw = (CF_B - c0 - 16) / 16; // warps 0..vw-1 carry the rows below the block, warp vw carries the identity (below)
+    if (warp_u == 7) { // (never a chain warp: vw <= 3) last panel: this idle warp polls the flags of the next step's tiles
+      if (c0 + 16 >= bs && lane == 0) {
+        if (poll0)
+          while (cf_ld_acquire(poll0) != epoch) {
+          }
+        if (poll1)
+          while (cf_ld_acquire(poll1) != epoch) {
+          }
+      }
+    } else if (warp_u <= vw) {
       // warp_u is the warp index broadcast from lane 0 by a shuffle: ptxas then knows the branch is warp-uniform, emits the
       // shuffles below without divergence checks and keeps the loop body one basic block it can schedule as a whole.  Lanes
-      // 0..15 of every chain warp repeat the diagonal block; lanes 16..31 of warp w carry rows c0+16+16w.. of the tile.
+      // 0..15 of every chain warp repeat the diagonal block; lanes 16..31 of warp w < vw carry rows c0+16+16w.. of the tile;
+      // lanes 16..31 of warp vw carry the rows of the 16x16 IDENTITY: what the chain solves for them is E L11^-T, i.e. the
+      // inverse of the diagonal block comes out of the same chain for free (row i, column j -> Linv(j, i), stored into x).
+      const bool virt = warp_u == vw;
       const int row = (lane < 16) ? c0 + lane : c0 + 16 * warp + lane;
       const bool lower = lane >= 16;
-      const bool rok = row < CF_B;
+      const bool rok = virt ? true : row < CF_B;
       // Entry k of a row, relative to the current column j: e0 = a(row, j) (final), e1 = a(row, j+1) (updated through column
       // j-1), q[k] = a(row, j+k), k >= 2 (updated through column j-2: the update with column j-1 is DEFERRED into this
       // iteration, behind the pivot chain - one warp issues in order, and a consumer of a shared-memory load must not sit in
@@ -367,25 +385,31 @@ __device__ void cf_potrf64(double *a, int bs, const double *thr, bool strict, do
       double q[16];
 #pragma unroll
       for (int c = 0; c < 16; c++)
-        q[c] = (rok && (lower || c <= lane)) ? a[CF_AT(row, c0 + c)] : 0.0;
+        q[c] = (virt && lower) ? ((c == lane - 16) ? 1.0 : 0.0) : ((rok && (lower || c <= lane)) ? a[CF_AT(row, c0 + c)] : 0.0);
       double e0 = q[0], e1 = q[1];
       double *lb = bcast + warp * 96; // [0,32) and [32,64): l(., j) by column parity (16 values + 16 zeros); [64,96): zeros
       lb[lane] = 0.0;
       lb[32 + lane] = 0.0;
       lb[64 + lane] = 0.0;
-      double mydiag = (lane < 16 && rok) ? a[CF_AT(row, c0 + lane)] : 0.0;
+      double mydiag = (lane < 16) ? a[CF_AT(row, c0 + lane)] : 0.0;
       double dcur = __shfl_sync(0xffffffffu, mydiag, 0);
       double ediag = __shfl_sync(0xffffffffu, mydiag, 1);
       double lprev = 0.0;
       // loop-invariant addresses and predicates, pinned in registers
       const unsigned thr_a = cf_saddr(thr + c0), piv_a = cf_saddr(pivinv + c0), lb_a = cf_saddr(lb);
-      const unsigned row_a = cf_saddr(a + CF_AT(rok ? row : 0, c0)), lst_a = lb_a + 8 * lane;
+      // where a lane stores its finished entry of column j: real rows a(row, c0 + j); identity row i: x(c0 + j, c0 + i)
+      const unsigned row_a = (virt && lower) ? cf_saddr(x + CF_AT(c0, c0 + lane - 16)) : cf_saddr(a + CF_AT(row < CF_B ? row : 0, c0));
+      const unsigned row_s = (virt && lower) ? 8u : (unsigned)(CF_LD * 8);
+      const unsigned lst_a = lb_a + 8 * lane;
       unsigned lq_a = lb_a + 64 * 8;
       int lane_r = lane;
       asm volatile("" : "+r"(lane_r));
-      const int p_lo16 = lane < 16, p_row = rok && lower, p_diag = rok && !lower && warp == 0, p_w0 = warp == 0;
+      const int p_lo16 = lane < 16, p_row = lower && (virt || row < CF_B), p_diag = !lower && warp == 0, p_w0 = warp == 0;
       int bad = 0;
-      __syncwarp();
+      // every chain warp has read the unfactored diagonal block (and its own rows) from the tile: only now may warp 0 start to
+      // overwrite it.  Named barrier over the vw + 1 chain warps - without it the read races with warp 0's first store whenever a
+      // warp is delayed by a few hundred cycles (seen only with several cooperative launches sharing the GPU).
+      asm volatile("bar.sync 1, %0;" ::"r"((vw + 1) * 32) : "memory");
 #pragma unroll 1
       for (int j = 0; j < nbp; j++) {
         const double d = dcur;
@@ -413,7 +437,7 @@ __device__ void cf_potrf64(double *a, int bs, const double *thr, bool strict, do
         e1 = fma(-l, l2, x2);
         const unsigned par = (j & 1) * 256;
         cf_sts_if(lst_a + par, l, p_lo16);
-        cf_sts_if(row_a + j * (CF_LD * 8), l, p_row | (p_diag & (lane_r >= j)));
+        cf_sts_if(row_a + j * row_s, l, p_row | (p_diag & (lane_r >= j)));
         cf_sts_if(piv_a + 8 * j, invp, p_w0 & (lane_r == j));
         e0 = e0n;
         lprev = l;
@@ -433,41 +457,10 @@ __device__ void cf_potrf64(double *a, int bs, const double *thr, bool strict, do
   }
 }
 
-// x = L^-1 for the 64x64 lower-triangular tile in `a` (zero pivots: pivinv = 0 -> zero row and column); t = scratch tile
-__device__ void cf_trinv64(const double *a, double *x, double *t, const double *pivinv, long long *dbgp = nullptr) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int idx = tid; idx < CF_B * CF_LD; idx += 256)
-    x[idx] = 0.0;
-  __syncthreads();
+// x = L^-1 for the 64x64 lower-triangular tile in `a`: the four 16x16 diagonal blocks of x were produced by the pivot chain
+// (identity rows), the rest of x above the diagonal blocks is zero; here only the merges.  t = scratch tile.
+__device__ void cf_trinv64(const double *a, double *x, double *t, long long *dbgp = nullptr) {
   PT(13)
-  if (warp < 4) { // 16x16 diagonal blocks: lane c (< 16) owns column c of the inverse; forward substitution with the solved
-                  // entries in a SHIFTING register window (xs[m] = x(i-1-m)), so the row loop stays rolled
-    const int o = 16 * warp, c = lane & 15;
-    const unsigned a_o = cf_saddr(a + CF_AT(o, o)), x_c = cf_saddr(x + CF_AT(o, o + c)), pv = cf_saddr(pivinv + o);
-    const int act = lane < 16;
-    double xs[15];
-#pragma unroll
-    for (int m = 0; m < 15; m++)
-      xs[m] = 0.0;
-#pragma unroll 1
-    for (int i = 0; i < 16; i++) {
-      const unsigned ai = a_o + 8 * i + (i - 1) * (CF_LD * 8); // &L(i, i-1); L(i, i-1-m) pairs with xs[m] (m < i)
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-      for (int m = 0; m < 14; m += 2) {
-        s0 = fma(cf_lds_if(ai - m * (CF_LD * 8), m < i), xs[m], s0);
-        s1 = fma(cf_lds_if(ai - (m + 1) * (CF_LD * 8), m + 1 < i), xs[m + 1], s1);
-      }
-      s0 = fma(cf_lds_if(ai - 14 * (CF_LD * 8), 14 < i), xs[14], s0);
-      const double v = ((i == c) ? 1.0 : -(s0 + s1)) * cf_lds(pv + 8 * i);
-      cf_sts_if(x_c + 8 * i, v, act);
-#pragma unroll
-      for (int m = 14; m > 0; m--)
-        xs[m] = xs[m - 1];
-      xs[0] = v;
-    }
-  }
-  __syncthreads();
   PT(14)
   // merges: X21 = -X22 (L21 X11) at block sizes 16 and 32
   for (int s = 16; s < CF_B; s *= 2) {
@@ -504,6 +497,8 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
     __syncthreads();
     if (tid < CF_B)
       thr[tid] = p.tol * a[CF_AT(tid, tid)];
+    for (int idx = tid; idx < CF_B * CF_LD; idx += 256)
+      b1[idx] = 0.0; // the inverse tile: only its lower blocks are ever written
     for (int k = 0; k < Tp; k++) {
       const int bs = min(CF_B, p.npiv - CF_B * k), rv = min(CF_B, p.n - CF_B * k);
       double *gA = p.A + (size_t)(CF_B * k) * p.ld + CF_B * k;
@@ -514,22 +509,15 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
         CF_TS(1 + 2 * k)
       long long *dbgp = (p.dbg && k == 1) ? p.dbg + (size_t)gridDim.x * 16 : nullptr;
       PT(0)
-      cf_potrf64(a, bs, thr, p.tol == 0.0, pivinv, p.info, bcast, dbgp);
+      cf_potrf64(a, b1, bs, thr, p.tol == 0.0, pivinv, p.info, bcast, has_panel ? fus + k + 1 : nullptr, next_diag ? fud + k + 1 : nullptr, e, dbgp);
       if (k < 3)
         CF_TS(2 + 2 * k)
       if (has_panel) { // the two tiles of the next step stream into b3 / b4 while the inverse is computed
-        if (tid == 0)
-          while (cf_ld_acquire(fus + k + 1) != e) {
-          }
-        if (tid == 32 && next_diag)
-          while (cf_ld_acquire(fud + k + 1) != e) {
-          }
-        __syncthreads();
-        cf_cpasync_tile(b3, gP, p.ld, rv1, CF_B, false);
+        cf_cpasync_tile(b3, gP, p.ld, rv1, CF_B, false); // (flags were polled by an idle warp during the last pivot chain)
         if (next_diag)
           cf_cpasync_tile(b4, gP + (size_t)CF_B * p.ld, p.ld, rv1, rv1, true);
       }
-      cf_trinv64(a, b1, b2, pivinv, dbgp);
+      cf_trinv64(a, b1, b2, dbgp);
       cf_store_tile(b1, p.LinvD + (size_t)k * CF_B * CF_B, CF_B, CF_B, CF_B, false);
       PT(19)
       cf_store_tile(a, gA, p.ld, rv, bs, true); // L(k,k): read only after the kernel; gives the Linv stores time to land

@@ -70,7 +70,22 @@ __device__ double gate_chi2(const double *A, int lda, double *T, double *S, int 
     int i0 = ch * 8;
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const double *Pc = P + (size_t)gid[cb + b] * ldP;
-    for (int k = 0; k < ncg; k++) {
+    int k = 0;
+    for (; k + 4 <= ncg; k += 4) { // four covariance entries in flight per trip: the gather is L2-latency bound
+      double p[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        p[u] = Pc[gid[cb + k + u]];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const double *hc = A + (size_t)(cb + k + u) * lda + rb + i0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (i0 + i < nr)
+            acc[i] += hc[i] * p[u];
+      }
+    }
+    for (; k < ncg; k++) {
       double p = Pc[gid[cb + k]];
       const double *hc = A + (size_t)(cb + k) * lda + rb + i0;
 #pragma unroll

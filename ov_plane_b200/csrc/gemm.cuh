@@ -102,19 +102,24 @@ __device__ __forceinline__ void load_tile_regs(double (&r)[TILE / 8], const SVie
     r[t] = ok ? v.p[(long long)gx * v.sx + kphys * v.sk] : 0.0;
   }
 }
+// Staging layout in shared memory: element (k, x) at k * sk + x * sx.  An operand walked x-fastest is stored [k][x] (sk = TILE + 4,
+// sx = 1); one walked k-fastest (k contiguous in global memory) is stored [x][k] with stride 20 (sk = 1, sx = 20): either way the
+// staging stores of a half warp and the DMMA fragment reads (8 x, 4 k) fall on 16 distinct 8-byte banks (TILE + 4 and 20 are 4 mod 16).
+#define OVP_GKS 20
 template <int TILE>
-__device__ __forceinline__ void store_tile_smem(const double (&r)[TILE / 8], double (*sm)[TILE + 4], int kfast, int tid) {
+__device__ __forceinline__ void store_tile_smem(const double (&r)[TILE / 8], double *sm, int kfast, int tid) {
 #pragma unroll
   for (int t = 0; t < TILE / 8; t++) {
     int xx, kk;
     if (kfast) {
       kk = tid & 15;
       xx = (tid >> 4) + 8 * t;
+      sm[xx * OVP_GKS + kk] = r[t];
     } else {
       xx = tid & (TILE - 1);
       kk = tid / TILE + (128 / TILE) * t;
+      sm[kk * (TILE + 4) + xx] = r[t];
     }
-    sm[kk][xx] = r[t];
   }
 }
 
@@ -130,8 +135,9 @@ template <int TILE, bool GA, bool GB> __global__ void __launch_bounds__(128) gem
     return;
   constexpr int WT = TILE / 2;  // warp tile edge
   constexpr int NM = WT / 8;    // mma tiles per warp per dimension
-  __shared__ double As[OVP_GK][TILE + 4];
-  __shared__ double Bs[OVP_GK][TILE + 4];
+  constexpr int SMT = (OVP_GK * (TILE + 4) > TILE * OVP_GKS) ? OVP_GK * (TILE + 4) : TILE * OVP_GKS;
+  __shared__ double As[SMT];
+  __shared__ double Bs[SMT];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;
@@ -139,6 +145,7 @@ template <int TILE, bool GA, bool GB> __global__ void __launch_bounds__(128) gem
   const int M = pb.M, N = pb.N, K = pb.K;
   const SView va = pb.A, vb = pb.B;
   const int akf = pb.a_kfast, bkf = pb.b_kfast;
+  const int ask = akf ? 1 : TILE + 4, asx = akf ? OVP_GKS : 1, bsk = bkf ? 1 : TILE + 4, bsx = bkf ? OVP_GKS : 1;
   double acc[NM][NM][2];
 #pragma unroll
   for (int i = 0; i < NM; i++)
@@ -178,10 +185,10 @@ template <int TILE, bool GA, bool GB> __global__ void __launch_bounds__(128) gem
       double a[NM], b[NM];
 #pragma unroll
       for (int i = 0; i < NM; i++)
-        a[i] = As[kk + (lane & 3)][wm * WT + i * 8 + (lane >> 2)];
+        a[i] = As[(kk + (lane & 3)) * ask + (wm * WT + i * 8 + (lane >> 2)) * asx];
 #pragma unroll
       for (int j = 0; j < NM; j++)
-        b[j] = Bs[kk + (lane & 3)][wn * WT + j * 8 + (lane >> 2)];
+        b[j] = Bs[(kk + (lane & 3)) * bsk + (wn * WT + j * 8 + (lane >> 2)) * bsx];
 #pragma unroll
       for (int i = 0; i < NM; i++)
 #pragma unroll

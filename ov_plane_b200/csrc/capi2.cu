@@ -1558,3 +1558,40 @@ extern "C" int ovp_debug_chol_fused(ovp_ctx *h, int n, int mrows, int iters, dou
   }
   return OVP_OK;
 }
+
+// Test hook for the fused Cholesky (tests/test_gpu_cholfused.py): factor a host matrix (lower triangle of A, n x n, column-major)
+// over its leading npiv columns with pivot tolerance tol and, when M is given, solve Y = M L^-T (mrows x npiv) and w = L^-1 z.
+// Not part of the ABI in include/ovp.h.
+extern "C" int ovp_debug_chol_solve(ovp_ctx *h, const double *A, int n, int npiv, double tol, const double *M, int mrows, const double *z,
+                                    double *L_out, double *Y_out, double *w_out) {
+  Ctx *c = &h->c;
+  if (n > c->wsS.cap || mrows > c->Nmax || npiv > n)
+    return fail(c, OVP_ERR_CAPACITY, "debug_chol_solve: too large");
+  const int ld = c->wsS.cap;
+  OVP_CUDA(cudaMemsetAsync(c->wsS.S, 0, (size_t)ld * ld * sizeof(double), c->stream));
+  OVP_CUDA(cudaMemcpy2DAsync(c->wsS.S, (size_t)ld * sizeof(double), A, (size_t)n * sizeof(double), (size_t)n * sizeof(double), n,
+                             cudaMemcpyHostToDevice, c->stream));
+  if (M) {
+    OVP_CUDA(cudaMemcpy2DAsync(c->dM, (size_t)c->Nmax * sizeof(double), M, (size_t)mrows * sizeof(double), (size_t)mrows * sizeof(double),
+                               npiv, cudaMemcpyHostToDevice, c->stream));
+    OVP_CUDA(cudaMemcpyAsync(c->dvec + c->Rcap, z, (size_t)npiv * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  int st = chol_fused(c, c->wsS.S, ld, n, npiv, tol, M ? c->dM : nullptr, c->Nmax, mrows, M ? c->dvec + c->Rcap : nullptr, c->dY, c->Nmax, c->dvec);
+  if (st)
+    return st;
+  OVP_CUDA(cudaMemcpy2DAsync(L_out, (size_t)n * sizeof(double), c->wsS.S, (size_t)ld * sizeof(double), (size_t)n * sizeof(double), n,
+                             cudaMemcpyDeviceToHost, c->stream));
+  if (M) {
+    OVP_CUDA(cudaMemcpy2DAsync(Y_out, (size_t)mrows * sizeof(double), c->dY, (size_t)c->Nmax * sizeof(double), (size_t)mrows * sizeof(double),
+                               npiv, cudaMemcpyDeviceToHost, c->stream));
+    OVP_CUDA(cudaMemcpyAsync(w_out, c->dvec, (size_t)npiv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
+  int info = 0;
+  OVP_CUDA(cudaMemcpy(&info, c->dflags + 1, sizeof(int), cudaMemcpyDeviceToHost));
+  if (info) {
+    cudaMemset(c->dflags + 1, 0, sizeof(int));
+    return fail(c, OVP_ERR_NOT_POSITIVE_DEFINITE, "debug_chol_solve: matrix not positive definite (strict mode)");
+  }
+  return OVP_OK;
+}

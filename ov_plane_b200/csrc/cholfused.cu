@@ -341,8 +341,14 @@ __device__ __noinline__ void cf_trail16(double *a, int c0) {
 // shuffle -> fma (the next pivot is rebuilt on every lane from a value shuffled one column earlier).  The trailing update
 // inside the tile is DMMA.  Zero-pivot rule: pivot <= thr (= tol * original diagonal) or <= 0 -> column of zeros, pivinv = 0
 // (rank-deficient Gram matrices); strict (tol == 0) flags *info instead (S must be positive definite).
+struct CfPrefetch { // the flags of the next step's two tiles, polled by the spine's idle warp during the last pivot chain
+  const int *flag0, *flag1;
+  double *s0, *s1;
+  const double *g0, *g1;
+  int ld, rv;
+};
 __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool strict, double *pivinv, int *info, double *bcast,
-                           const int *poll0, const int *poll1, int epoch, long long *dbgp = nullptr) {
+                           const CfPrefetch &pf, int epoch, long long *dbgp = nullptr) {
 #define PT(slot)                                                                                                             \
   if (dbgp && threadIdx.x == 0)                                                                                              \
     dbgp[slot] = clock64();
@@ -358,13 +364,15 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
     const int nbp = min(16, bs - c0);
     const int vw = (CF_B - c0 - 16) / 16; // warps 0..vw-1 carry the rows below the block, warp vw carries the identity (below)
     if (warp_u == 7) { // (never a chain warp: vw <= 3) last panel: this idle warp polls the flags of the next step's tiles
-      if (c0 + 16 >= bs && lane == 0) {
-        if (poll0)
-          while (cf_ld_acquire(poll0) != epoch) {
-          }
-        if (poll1)
-          while (cf_ld_acquire(poll1) != epoch) {
-          }
+      if (c0 + 16 >= bs) {
+        if (lane == 0) {
+          if (pf.flag0)
+            while (cf_ld_acquire(pf.flag0) != epoch) {
+            }
+          if (pf.flag1)
+            while (cf_ld_acquire(pf.flag1) != epoch) {
+            }
+        }
       }
     } else if (warp_u <= vw) {
       // warp_u is the warp index broadcast from lane 0 by a shuffle: ptxas then knows the branch is warp-uniform, emits the
@@ -457,20 +465,46 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
   }
 }
 
-// x = L^-1 for the 64x64 lower-triangular tile in `a`: the four 16x16 diagonal blocks of x were produced by the pivot chain
-// (identity rows), the rest of x above the diagonal blocks is zero; here only the merges.  t = scratch tile.
-__device__ void cf_trinv64(const double *a, double *x, double *t, long long *dbgp = nullptr) {
-  PT(13)
-  PT(14)
-  // merges: X21 = -X22 (L21 X11) at block sizes 16 and 32
-  for (int s = 16; s < CF_B; s *= 2) {
-    const int nbat = CF_B / (2 * s), bstr = 2 * s * CF_LD + 2 * s, nb8 = s / 8;
-    cf_mma_blocks<true>(t + CF_AT(s, 0), a + CF_AT(s, 0), x, nb8, nb8, s, 1.0, 0.0, false, nbat, bstr);
-    __syncthreads();
-    PT(s == 16 ? 15 : 17)
-    cf_mma_blocks<true>(x + CF_AT(s, 0), x + CF_AT(s, s), t + CF_AT(s, 0), nb8, nb8, s, -1.0, 0.0, false, nbat, bstr);
-    __syncthreads();
-    PT(s == 16 ? 16 : 18)
+// U <- U L^-T for a 64-row tile U, given the factor tile Lkk and the 16x16 inverses of ITS diagonal blocks (X, from the pivot
+// chain): a right-side triangular solve is independent per row, so warp w owns rows 8w..8w+7 through all four 16-column steps
+//   S = U[:, b] - U[:, <b] Lkk[b, <b]^T      (U[:, <b] already holds the result)
+//   U[:, b] = S X_bb^T
+// with a private 8 x 16 scratch (S) and no CTA barrier at all.  No 64x64 inverse is ever formed.
+__device__ __noinline__ void cf_bsolve64(double *U, const double *Lkk, const double *X, double *S) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int r = 8 * warp + g;
+#pragma unroll 1
+  for (int b = 0; b < 4; b++) {
+    const int cb = 16 * b;
+    double a0[2] = {0.0, 0.0}, a1[2] = {0.0, 0.0};
+#pragma unroll 4
+    for (int k4 = 0; k4 < cb; k4 += 4) {
+      const double av = U[CF_AT(r, k4 + t)];
+      dmma_m8n8k4(a0[0], a0[1], av, Lkk[CF_AT(cb + g, k4 + t)]);
+      dmma_m8n8k4(a1[0], a1[1], av, Lkk[CF_AT(cb + 8 + g, k4 + t)]);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      S[CF_AT(r, 2 * t + h)] = U[CF_AT(r, cb + 2 * t + h)] - a0[h];
+      S[CF_AT(r, 8 + 2 * t + h)] = U[CF_AT(r, cb + 8 + 2 * t + h)] - a1[h];
+    }
+    __syncwarp();
+    double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k4 = 0; k4 < 16; k4 += 4) {
+      const double sv = S[CF_AT(r, k4 + t)];
+      if (k4 < 8) // X_bb lower triangular: columns 0..7 only need k < 8
+        dmma_m8n8k4(c0[0], c0[1], sv, X[CF_AT(cb + g, cb + k4 + t)]);
+      dmma_m8n8k4(c1[0], c1[1], sv, X[CF_AT(cb + 8 + g, cb + k4 + t)]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      U[CF_AT(r, cb + 2 * t + h)] = c0[h];
+      U[CF_AT(r, cb + 8 + 2 * t + h)] = c1[h];
+    }
+    __syncwarp();
   }
 }
 
@@ -509,29 +543,38 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
         CF_TS(1 + 2 * k)
       long long *dbgp = (p.dbg && k == 1) ? p.dbg + (size_t)gridDim.x * 16 : nullptr;
       PT(0)
-      cf_potrf64(a, b1, bs, thr, p.tol == 0.0, pivinv, p.info, bcast, has_panel ? fus + k + 1 : nullptr, next_diag ? fud + k + 1 : nullptr, e, dbgp);
+      CfPrefetch pf;
+      pf.flag0 = has_panel ? fus + k + 1 : nullptr;
+      pf.flag1 = next_diag ? fud + k + 1 : nullptr;
+      pf.s0 = b3;
+      pf.s1 = b4;
+      pf.g0 = gP;
+      pf.g1 = gP + (size_t)CF_B * p.ld;
+      pf.ld = p.ld;
+      pf.rv = rv1;
+      cf_potrf64(a, b1, bs, thr, p.tol == 0.0, pivinv, p.info, bcast, pf, e, dbgp);
       if (k < 3)
         CF_TS(2 + 2 * k)
-      if (has_panel) { // the two tiles of the next step stream into b3 / b4 while the inverse is computed
-        cf_cpasync_tile(b3, gP, p.ld, rv1, CF_B, false); // (flags were polled by an idle warp during the last pivot chain)
-        if (next_diag)
-          cf_cpasync_tile(b4, gP + (size_t)CF_B * p.ld, p.ld, rv1, rv1, true);
-      }
-      cf_trinv64(a, b1, b2, dbgp);
-      cf_store_tile(b1, p.LinvD + (size_t)k * CF_B * CF_B, CF_B, CF_B, CF_B, false);
+      PT(13)
+      cf_store_tile(b1, p.LinvD + (size_t)k * CF_B * CF_B, CF_B, CF_B, CF_B, false); // the four 16x16 inverses (rest of the tile is zero)
       PT(19)
-      cf_store_tile(a, gA, p.ld, rv, bs, true); // L(k,k): read only after the kernel; gives the Linv stores time to land
+      cf_store_tile(a, gA, p.ld, rv, bs, true);
       PT(20)
       cf_signal(fdiag + k, e);
       PT(21)
       if (has_panel) {
+        // the two tiles of the next step (their flags were polled by the idle warp during the last pivot chain); issued after the
+        // release above: a fence with copies in flight waits for them
+        cf_cpasync_tile(b3, gP, p.ld, rv1, CF_B, false);
+        if (next_diag)
+          cf_cpasync_tile(b4, gP + (size_t)CF_B * p.ld, p.ld, rv1, rv1, true);
         if (next_diag && tid < CF_B)
           thr[tid] = p.tol * __ldcg(p.diag0 + CF_B * (k + 1) + tid);
         asm volatile("cp.async.wait_all;" ::: "memory");
         PT(23)
         __syncthreads();
         PT(24)
-        cf_mma_64<1>(b3, b3, b1, 1.0, false, true); // L(k+1,k) = U(k+1,k) Linv(k)^T
+        cf_bsolve64(b3, a, b1, b2); // L(k+1,k) = U(k+1,k) L(k,k)^-T
         __syncthreads();
         PT(25)
         cf_store_tile(b3, gP, p.ld, rv1, bs, false);
@@ -590,10 +633,11 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
     } else {
       cf_wait(fdiag + j, e);
       CF_TS(4)
-      cf_load_tile(b1, p.LinvD + (size_t)j * CF_B * CF_B, CF_B, CF_B, CF_B, false);
+      cf_load_tile(b1, p.A + (size_t)(CF_B * j) * p.ld + CF_B * j, p.ld, min(CF_B, p.n - CF_B * j), bs, true); // L(j,j)
+      cf_load_tile(b2, p.LinvD + (size_t)j * CF_B * CF_B, CF_B, CF_B, CF_B, false);                           // its 16x16 inverses
       __syncthreads();
       CF_TS(5)
-      cf_mma_64<1>(a, a, b1, 1.0, false, true);
+      cf_bsolve64(a, b1, b2, sm + 3 * CF_B * CF_LD);
       __syncthreads();
       CF_TS(6)
       cf_store_tile(a, gA, p.ld, rv, bs, false);
@@ -606,7 +650,9 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
     const int ms = p.mstride;
     double *mrow = sm;                 // CF_RB x ms
     double *Lt = sm + CF_RB * ms;      // 64 x CF_LD
-    double *yk = Lt + CF_B * CF_LD;    // CF_RB x CF_LD
+    double *yk = Lt + CF_B * CF_LD;    // CF_RB x CF_LD (row-major)
+    double *Xt = yk + CF_RB * CF_LD;   // 64 x CF_LD: the 16x16 inverses of L(k,k)'s diagonal blocks
+    double *sb = Xt + CF_B * CF_LD;    // 2 warps x 8 x 20 scratch
     const int row0 = rb * CF_RB;
     const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     for (int idx = tid; idx < CF_RB * Tp * CF_B; idx += 256) {
@@ -625,21 +671,43 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
     for (int k = 0; k < Tp; k++) {
       const int bs = min(CF_B, p.npiv - CF_B * k);
       cf_wait(fdiag + k, e);
-      cf_load_tile(Lt, p.LinvD + (size_t)k * CF_B * CF_B, CF_B, CF_B, CF_B, false);
+      cf_load_tile(Lt, p.A + (size_t)(CF_B * k) * p.ld + CF_B * k, p.ld, min(CF_B, p.n - CF_B * k), bs, true);
+      cf_load_tile(Xt, p.LinvD + (size_t)k * CF_B * CF_B, CF_B, CF_B, CF_B, false);
       __syncthreads();
-      { // yk (16 x 64) = mrow[:, 64k ..] * Linv^T (lower triangular: k4 <= column)
-        double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-        const double *pa = mrow + g * ms + CF_B * k + t;
-        const double *pb = Lt + CF_AT(8 * warp + g, t);
-        for (int k4 = 0; k4 <= 8 * warp + 7; k4 += 4) {
-          const double b = pb[k4 * CF_LD];
-          dmma_m8n8k4(c00, c01, pa[k4], b);
-          dmma_m8n8k4(c10, c11, pa[8 * ms + k4], b);
+      if (warp < 2) { // yk (16 x 64) = mrow[:, 64k ..] L(k,k)^-T: rows are independent, warp w owns rows 8w..8w+7 (cf_bsolve64 in row-major)
+        const int r = 8 * warp + g;
+        double *sw = sb + warp * 160;
+#pragma unroll 1
+        for (int b = 0; b < 4; b++) {
+          const int cb = 16 * b;
+          double a0[2] = {0.0, 0.0}, a1[2] = {0.0, 0.0};
+          for (int k4 = 0; k4 < cb; k4 += 4) {
+            const double av = yk[r * CF_LD + k4 + t];
+            dmma_m8n8k4(a0[0], a0[1], av, Lt[CF_AT(cb + g, k4 + t)]);
+            dmma_m8n8k4(a1[0], a1[1], av, Lt[CF_AT(cb + 8 + g, k4 + t)]);
+          }
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            sw[g * 20 + 2 * t + h] = mrow[r * ms + CF_B * k + cb + 2 * t + h] - a0[h];
+            sw[g * 20 + 8 + 2 * t + h] = mrow[r * ms + CF_B * k + cb + 8 + 2 * t + h] - a1[h];
+          }
+          __syncwarp();
+          double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+#pragma unroll
+          for (int k4 = 0; k4 < 16; k4 += 4) {
+            const double sv = sw[g * 20 + k4 + t];
+            if (k4 < 8)
+              dmma_m8n8k4(c0[0], c0[1], sv, Xt[CF_AT(cb + g, cb + k4 + t)]);
+            dmma_m8n8k4(c1[0], c1[1], sv, Xt[CF_AT(cb + 8 + g, cb + k4 + t)]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            yk[r * CF_LD + cb + 2 * t + h] = c0[h];
+            yk[r * CF_LD + cb + 8 + 2 * t + h] = c1[h];
+          }
+          __syncwarp();
         }
-        yk[g * CF_LD + 8 * warp + 2 * t] = c00;
-        yk[g * CF_LD + 8 * warp + 2 * t + 1] = c01;
-        yk[(g + 8) * CF_LD + 8 * warp + 2 * t] = c10;
-        yk[(g + 8) * CF_LD + 8 * warp + 2 * t + 1] = c11;
       }
       __syncthreads();
       for (int idx = tid; idx < CF_RB * CF_B; idx += 256) {
@@ -727,7 +795,7 @@ int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const dou
   p.nrb = (vrows + CF_RB - 1) / CF_RB;
   p.mstride = p.Tp * CF_B + 4;
   size_t smem_tile = ((size_t)5 * CF_B * CF_LD + 2 * CF_B + 8 * 96) * sizeof(double);
-  size_t smem_rows = ((size_t)CF_RB * p.mstride + (size_t)CF_B * CF_LD + (size_t)CF_RB * CF_LD) * sizeof(double);
+  size_t smem_rows = ((size_t)CF_RB * p.mstride + 2 * (size_t)CF_B * CF_LD + (size_t)CF_RB * CF_LD + 320) * sizeof(double);
   size_t smem = std::max(smem_tile, p.nrb ? smem_rows : 0);
   if (smem > 220 * 1024)
     return fail(c, OVP_ERR_CAPACITY, "chol_fused: %d columns need %zu B of shared memory", npiv, smem);

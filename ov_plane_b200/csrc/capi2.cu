@@ -785,10 +785,7 @@ int ovp_msckf_update_gathered(ovp_ctx *h, const double *d_blocks, int G, const i
   st = chol_partial(c, c->wsG.S, c->wsG.cap, nc1, n, 1e-11);
   if (st)
     return st;
-  double *d_z = c->dvec + c->Rcap;
-  extract_row_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->wsG.S, c->wsG.cap, nc1 - 1, n, d_z);
-  c->launches++;
-  st = ekf_update_core(c, c->dcols, n, mv(c->wsG.S, c->wsG.cap), n, d_z, nullptr, -1.0, nullptr, nullptr);
+  st = ekf_update_core(c, c->dcols, n, mv(c->wsG.S, c->wsG.cap), n, c->wsG.S + (nc1 - 1), nullptr, -1.0, nullptr, nullptr, true, c->wsG.cap);
   if (st)
     return st;
   return check_status_flags(c);
@@ -1520,8 +1517,8 @@ extern "C" int ovp_debug_chol_fused(ovp_ctx *h, int n, int mrows, int iters, dou
       for (int it = 0; it < iters; it++) {
         spd_fill_kernel<<<(n * n + 255) / 256, 256, 0, c->stream>>>(c->wsS.S, c->wsS.cap, n);
         if (variant == 0) {
-          int st = chol_fused(c, c->wsS.S, c->wsS.cap, n, n, 0.0, mrows ? c->dM : nullptr, c->Nmax, mrows, mrows ? c->dvec + c->Rcap : nullptr,
-                              c->dY, c->Nmax, c->dvec, dbg);
+          int st = chol_fused(c, c->wsS.S, c->wsS.cap, n, n, 0.0, mrows ? c->dM : nullptr, c->Nmax, mrows, mrows ? c->dvec + c->Rcap : nullptr, 1,
+                              c->dY, c->Nmax, c->dvec, -1.0, nullptr, nullptr, dbg);
           if (st)
             return st;
         }
@@ -1576,7 +1573,8 @@ extern "C" int ovp_debug_chol_solve(ovp_ctx *h, const double *A, int n, int npiv
                                npiv, cudaMemcpyHostToDevice, c->stream));
     OVP_CUDA(cudaMemcpyAsync(c->dvec + c->Rcap, z, (size_t)npiv * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   }
-  int st = chol_fused(c, c->wsS.S, ld, n, npiv, tol, M ? c->dM : nullptr, c->Nmax, mrows, M ? c->dvec + c->Rcap : nullptr, c->dY, c->Nmax, c->dvec);
+  int st = chol_fused(c, c->wsS.S, ld, n, npiv, tol, M ? c->dM : nullptr, c->Nmax, mrows, M ? c->dvec + c->Rcap : nullptr, 1, c->dY, c->Nmax, c->dvec, -1.0,
+                      c->dscal + 8, nullptr);
   if (st)
     return st;
   OVP_CUDA(cudaMemcpy2DAsync(L_out, (size_t)n * sizeof(double), c->wsS.S, (size_t)ld * sizeof(double), (size_t)n * sizeof(double), n,

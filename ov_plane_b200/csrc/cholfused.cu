@@ -32,10 +32,14 @@ struct CholFusedArgs {
   int T, Tp, ntile;
   const double *M; // optional tall right-hand side (mrows x npiv, ld ldm); row `mrows` of the virtual matrix is z
   int ldm, mrows;
-  const double *z;
+  const double *z; // element k at z[k * zstride]
+  int zstride;
   double *Y;
   int ldy;
   double *w;
+  double gate_thresh; // chi2 = |w|^2 and the gate flag (thresh < 0 or chi2 <= thresh) are produced by the CTA that owns the z row
+  double *chi2;
+  int *gate_flag;
   int nrb, mstride;
   long long *dbg; // optional: 16 globaltimer stamps per CTA (tools/microbench.py)
 };
@@ -655,6 +659,7 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
     double *sb = Xt + CF_B * CF_LD;    // 2 warps x 8 x 20 scratch
     const int row0 = rb * CF_RB;
     const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    double wsq = 0.0;
     for (int idx = tid; idx < CF_RB * Tp * CF_B; idx += 256) {
       const int r = idx & (CF_RB - 1), k = idx >> 4;
       const int row = row0 + r;
@@ -663,7 +668,7 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
         if (row < p.mrows)
           v = __ldcg(p.M + (size_t)k * p.ldm + row);
         else if (row == p.mrows && p.z)
-          v = __ldcg(p.z + k);
+          v = __ldcg(p.z + (size_t)k * p.zstride);
       }
       mrow[r * ms + k] = v;
     }
@@ -716,8 +721,11 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
         if (cc < bs) {
           if (row < p.mrows)
             __stcg(p.Y + (size_t)(CF_B * k + cc) * p.ldy + row, yk[r * CF_LD + cc]);
-          else if (row == p.mrows && p.w)
-            __stcg(p.w + CF_B * k + cc, yk[r * CF_LD + cc]);
+          else if (row == p.mrows && p.w) {
+            const double wv = yk[r * CF_LD + cc];
+            __stcg(p.w + CF_B * k + cc, wv);
+            wsq += wv * wv; // (one z row per launch: exactly one thread per column lands here)
+          }
         }
       }
       for (int j = k + 1; j < Tp; j++) {
@@ -741,6 +749,23 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
         __syncthreads();
       }
     }
+    if (p.z && p.mrows >= row0 && p.mrows < row0 + CF_RB && p.chi2) {
+      // chi2 = |L^-1 z|^2 in a fixed order (per-thread partial sums by column, then a tree), and the gate of the update
+      double *red = sb; // sb is 320 doubles; 256 needed
+      __syncthreads();
+      red[tid] = wsq;
+      __syncthreads();
+      for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o)
+          red[tid] += red[tid + o];
+        __syncthreads();
+      }
+      if (tid == 0) {
+        p.chi2[0] = red[0];
+        if (p.gate_flag)
+          *p.gate_flag = (p.gate_thresh < 0.0 || !(red[0] > p.gate_thresh)) ? 1 : 0;
+      }
+    }
   }
   // ---- epoch bookkeeping: the last CTA to finish opens the next epoch ----
   CF_TS(15)
@@ -759,8 +784,8 @@ static bool g_cf_attr_set = false;
 
 // Factor the leading npiv columns of the n x n lower-stored matrix A in place (rows npiv..n-1 are solved along) and, when M is
 // given, solve Y = M L^-T (mrows x npiv) and w = L^-1 z in the same launch.
-int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const double *M, int ldm, int mrows, const double *z, double *Y,
-               int ldy, double *w, long long *dbg) {
+int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const double *M, int ldm, int mrows, const double *z, int zstride,
+               double *Y, int ldy, double *w, double gate_thresh, double *chi2, int *gate_flag, long long *dbg) {
   if (npiv <= 0)
     return OVP_OK;
   if (npiv > n || n > ld || (ld & 1) || ((uintptr_t)A & 15))
@@ -787,6 +812,10 @@ int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const dou
   p.ldm = ldm;
   p.mrows = M ? mrows : 0;
   p.z = z;
+  p.zstride = zstride;
+  p.gate_thresh = gate_thresh;
+  p.chi2 = chi2;
+  p.gate_flag = gate_flag;
   p.Y = Y;
   p.ldy = ldy;
   p.w = w;

@@ -39,32 +39,59 @@ __device__ __forceinline__ void quat_left_update(double *q, const double *dth) {
   q[3] = r3 / n2;
 }
 
-__global__ void apply_dx_kernel(int nh, const int *var_id, const int *var_size, const int *var_kind, double *val, const double *dx,
-                                const int *flag) {
-  int h = blockIdx.x * blockDim.x + threadIdx.x;
+// Tail of EKFUpdate in one launch, one warp per variable: dx rows of the variable = Y[id : id + size, :] w (lanes over the
+// compressed rows, fixed-order shuffle tree), ov_type::update on the device (StateHelper.cpp:190-193), and the negative-diagonal
+// check of the variable's covariance rows (:176-187).  Skipped when the gate flag says the update was rejected.
+__global__ void __launch_bounds__(128) finish_update_kernel(int nh, const int *var_id, const int *var_size, const int *var_kind, double *val,
+                                                            const double *Y, int ldy, const double *w, int rr, const double *P, int ldP,
+                                                            int *neg_flag, const int *flag) {
+  const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (h >= nh)
     return;
   if (flag && *flag == 0)
     return;
-  int id = var_id[h];
+  const int id = var_id[h];
   if (id < 0)
     return;
-  const double *d = dx + id;
+  const int s = var_size[h];
+  double acc[15];
+#pragma unroll
+  for (int i = 0; i < 15; i++)
+    acc[i] = 0.0;
+  for (int k = lane; k < rr; k += 32) {
+    const double wk = w[k];
+    const double *y = Y + (size_t)k * ldy + id;
+#pragma unroll
+    for (int i = 0; i < 15; i++)
+      if (i < s)
+        acc[i] = fma(y[i], wk, acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 15; i++)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  if (lane < s && P[(size_t)(id + lane) * ldP + id + lane] < 0.0)
+    atomicExch(neg_flag, 1);
+  if (lane != 0)
+    return;
   double *v = val + (size_t)h * OVP_VAL_STRIDE;
-  int kind = var_kind[h];
+  const int kind = var_kind[h];
   if (kind == OVP_KIND_VEC || kind == OVP_KIND_LANDMARK) {
-    int s = var_size[h];
-    for (int i = 0; i < s; i++)
-      v[i] += d[i];
+#pragma unroll
+    for (int i = 0; i < 15; i++)
+      if (i < s)
+        v[i] += acc[i];
     return;
   }
-  quat_left_update(v, d);
-  v[4] += d[3];
-  v[5] += d[4];
-  v[6] += d[5];
+  quat_left_update(v, acc);
+  v[4] += acc[3];
+  v[5] += acc[4];
+  v[6] += acc[5];
   if (kind == OVP_KIND_IMU)
+#pragma unroll
     for (int i = 0; i < 9; i++)
-      v[7 + i] += d[6 + i];
+      v[7 + i] += acc[6 + i];
 }
 
 __global__ void diag_check_kernel(const double *P, int ld, int N, int *flag_out, const int *flag) {
@@ -73,11 +100,6 @@ __global__ void diag_check_kernel(const double *P, int ld, int N, int *flag_out,
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N && P[(size_t)i * ld + i] < 0.0)
     atomicExch(flag_out, 1);
-}
-
-__global__ void gate_kernel(const double *chi2, double thresh, int *flag) {
-  if (threadIdx.x == 0 && blockIdx.x == 0)
-    *flag = (thresh < 0.0 || !(chi2[0] > thresh)) ? 1 : 0;
 }
 
 int upload_var_table(Ctx *c) {
@@ -165,7 +187,7 @@ int check_status_flags(Ctx *c) {
 // algebraically the reference's K = M S^-1, P -= K M^T, dx = K res (StateHelper.cpp:165-171,190).
 // -------------------------------------------------------------------------------------------------------------------
 int ekf_update_core(Ctx *c, const int *d_cols, int nc, MatView HT, int rr, const double *d_z, const double *d_Rdiag, double gate_thresh,
-                    int *d_gate_flag, double *d_chi2, bool apply) {
+                    int *d_gate_flag, double *d_chi2, bool apply, int zstride) {
   if (rr <= 0 || nc <= 0)
     return OVP_OK;
   if (rr > c->wsS.cap || nc > c->Rcap)
@@ -191,20 +213,15 @@ int ekf_update_core(Ctx *c, const int *d_cols, int nc, MatView HT, int rr, const
     p.tri = TRI_LOWER;
     launch_gemm1(c, p);
   }
-  double *d_w = c->dvec;                 // [0, Rcap)
-  double *d_dx = c->dvec + 2 * c->Rcap;  // [2Rcap, 2Rcap + Nmax)
-  // 3-5. S = L L^T, Y = M L^-T, w = L^-1 z in one launch (cholfused.cu)
+  double *d_w = c->dvec; // [0, Rcap)
+  double *chi2 = d_chi2 ? d_chi2 : c->dscal;
+  int *flag = d_gate_flag ? d_gate_flag : (c->dflags + 2);
+  // 3-5. S = L L^T, Y = M L^-T, w = L^-1 z, chi2 = |w|^2 and the gate flag in one launch (cholfused.cu)
   {
-    int st = chol_fused(c, c->wsS.S, c->wsS.cap, rr, rr, 0.0, c->dM, c->Nmax, N, d_z, c->dY, c->Nmax, d_w);
+    int st = chol_fused(c, c->wsS.S, c->wsS.cap, rr, rr, 0.0, c->dM, c->Nmax, N, d_z, zstride, c->dY, c->Nmax, d_w, gate_thresh, chi2, flag);
     if (st)
       return st;
   }
-  // chi2 = |w|^2 ; gate
-  double *chi2 = d_chi2 ? d_chi2 : c->dscal;
-  launch_sumsq(c, d_w, rr, chi2);
-  int *flag = d_gate_flag ? d_gate_flag : (c->dflags + 2);
-  gate_kernel<<<1, 32, 0, c->stream>>>(chi2, gate_thresh, flag);
-  c->launches++;
   if (!apply)
     return OVP_OK;
   // 6. P -= Y Y^T (lower tiles, mirrored)  [skipped on the device when the gate failed]
@@ -213,12 +230,10 @@ int ekf_update_core(Ctx *c, const int *d_cols, int nc, MatView HT, int rr, const
     p.tri = TRI_LOWER_MIRROR;
     launch_gemm1(c, p, flag);
   }
-  // 7. dx = Y w ; update every variable ; negative-diagonal check
-  launch_gemv(c, N, rr, mv(c->dY, c->Nmax), d_w, d_dx, flag);
+  // 7. dx = Y w, update of every variable, negative-diagonal check: one launch
   int nh = (int)c->vars.size();
-  apply_dx_kernel<<<(nh + 127) / 128, 128, 0, c->stream>>>(nh, c->d_var_id, c->d_var_size, c->d_var_kind, c->d_val, d_dx, flag);
-  c->launches++;
-  diag_check_kernel<<<(N + 127) / 128, 128, 0, c->stream>>>(c->dP, c->ldP, N, c->dflags, flag);
+  finish_update_kernel<<<(nh * 32 + 127) / 128, 128, 0, c->stream>>>(nh, c->d_var_id, c->d_var_size, c->d_var_kind, c->d_val, c->dY, c->Nmax, d_w, rr,
+                                                                      c->dP, c->ldP, c->dflags, flag);
   c->launches++;
   c->host_values_stale = true;
   return OVP_OK;

@@ -472,12 +472,6 @@ __global__ void gram_reduce_kernel(const double *part, int ldp, int nsplit, int 
   G[(size_t)j * ldg + i] = s;
 }
 
-__global__ void extract_row_kernel(const double *A, int ld, int row, int n, double *out) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n)
-    out[j] = A[(size_t)j * ld + row];
-}
-
 // Gram + reduce of the stacked system Hs (rows x nc) into ws.S (lower)
 static int gram_of_stacked(Ctx *c, int rows, int nc, int ldHs) {
   int tiles = (nc + OVP_GT - 1) / OVP_GT;

@@ -116,55 +116,6 @@ void launch_fill(Ctx *c, double *p, size_t n, double v) {
   c->launches++;
 }
 
-__global__ void gemv_kernel(int M, int K, MatView A, const double *x, double *y, const int *flag) {
-  if (flag && *flag == 0)
-    return;
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (warp >= M)
-    return;
-  double s = 0.0;
-  for (int k = lane; k < K; k += 32)
-    s += A.at(warp, k) * x[k];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0)
-    y[warp] = s;
-}
-void launch_gemv(Ctx *c, int M, int K, MatView A, const double *x, double *y, const int *flag) {
-  if (M <= 0)
-    return;
-  int threads = 128;
-  int blocks = (M * 32 + threads - 1) / threads;
-  gemv_kernel<<<blocks, threads, 0, c->stream>>>(M, K, A, x, y, flag);
-  c->launches++;
-}
-
-__global__ void sumsq_kernel(const double *x, int n, double *out) {
-  __shared__ double sh[32];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-    s += x[i] * x[i];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0)
-    sh[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0)
-      out[0] = s;
-  }
-}
-void launch_sumsq(Ctx *c, const double *x, int n, double *out) {
-  sumsq_kernel<<<1, 256, 0, c->stream>>>(x, n, out);
-  c->launches++;
-}
 
 int ws_alloc(Ctx *c, DenseWs &ws, int cap) {
   ws.cap = cap;
@@ -181,7 +132,7 @@ void ws_free(DenseWs &ws) {
 // Cholesky of the leading npiv columns of the n x n lower-stored matrix A in place (rows npiv..n-1 are solved along): one launch
 // of the fused kernel (cholfused.cu).  Pivots <= tol * original diagonal are treated as exact zeros (rank-deficient Gram matrices).
 int chol_partial(Ctx *c, double *A, int ld, int n, int npiv, double tol) {
-  return chol_fused(c, A, ld, n, npiv, tol, nullptr, 0, 0, nullptr, nullptr, 0, nullptr);
+  return chol_fused(c, A, ld, n, npiv, tol, nullptr, 0, 0, nullptr, 1, nullptr, 0, nullptr, -1.0, nullptr, nullptr);
 }
 
 // stand-alone Householder left-nullspace projection on a global-memory matrix (col-major, ld): reflectors from the first

@@ -136,8 +136,8 @@ int fail(Ctx *c, int status, const char *fmt, ...);
   } while (0)
 
 // ---- linalg.cu ---------------------------------------------------------------------------------------------------
-int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const double *M, int ldm, int mrows, const double *z, double *Y,
-               int ldy, double *w, long long *dbg = nullptr);
+int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const double *M, int ldm, int mrows, const double *z, int zstride,
+               double *Y, int ldy, double *w, double gate_thresh, double *chi2, int *gate_flag, long long *dbg = nullptr);
 void launch_gemm(Ctx *c, const GemmBatch &b);
 void launch_gemm1(Ctx *c, const GemmProblem &p, const int *flag = nullptr);
 // In-place blocked Cholesky of the leading `npiv` pivots of the symmetric (lower-stored) matrix A (size n x n, ld):
@@ -145,9 +145,7 @@ int chol_partial(Ctx *c, double *A, int ld, int n, int npiv, double tol); // one
 int ws_alloc(Ctx *c, DenseWs &ws, int cap);
 void ws_free(DenseWs &ws);
 // y = alpha * A(m x k view) * x  (one warp per row)
-void launch_gemv(Ctx *c, int M, int K, MatView A, const double *x, double *y, const int *flag = nullptr);
 // sum of squares of x[0:n] -> out[0]
-void launch_sumsq(Ctx *c, const double *x, int n, double *out);
 void launch_fill(Ctx *c, double *p, size_t n, double v);
 
 // ---- ekf.cu ------------------------------------------------------------------------------------------------------
@@ -155,7 +153,7 @@ void launch_fill(Ctx *c, double *p, size_t n, double v);
 // nc state indices).  z: rr.  Rdiag: rr or nullptr (identity).  If gate_thresh >= 0, chi2 = z^T S^-1 z is compared with
 // it on the device and the update is skipped when larger (flag written to d_gate_flag, chi2 to d_chi2).
 int ekf_update_core(Ctx *c, const int *d_cols, int nc, MatView HT, int rr, const double *d_z, const double *d_Rdiag, double gate_thresh,
-                    int *d_gate_flag, double *d_chi2, bool apply = true);
+                    int *d_gate_flag, double *d_chi2, bool apply = true, int zstride = 1);
 int upload_var_table(Ctx *c);
 int sync_host_values(Ctx *c);
 int push_host_values(Ctx *c, int handle);

@@ -377,6 +377,37 @@ def main():
     except Exception as e:
         line["concurrent_filters"] = {"error": repr(e)}
 
+    # ---- propagation + clone as its own line: Propagator::propagate_and_clone then marginalisation of the oldest
+    #      clone (the per-frame pair that keeps N constant), same N = 512 state, 20 IMU samples per frame ----
+    try:
+        Sp = synth.make_scenario(WORKLOAD, seed=7)
+        cp = api.Context(Sp.options, device=local, max_state=576, max_meas_rows=4096)
+        cp.set_chi2_table(chi2)
+        chp = list(synth.load_scenario_into(cp, Sp))
+        cp.propagator_set_noise(1.6968e-04, 1.9393e-05, 2.0e-3, 3.0e-3, 9.81)
+        tcur, dt_frame, nfr = Sp.timestamp, 0.05, 40
+        rng = np.random.RandomState(1)
+        for k in range(int((nfr + 2) * dt_frame / 0.0025) + 8):
+            tt = tcur - 0.01 + 0.0025 * k
+            cp.feed_imu(tt, np.array([0.05, -0.02, 0.1]) + 0.01 * rng.randn(3), np.array([0.1, 9.75, 0.3]) + 0.05 * rng.randn(3))
+        for warm in (True, False):
+            cp.synchronize()
+            tw0 = time.perf_counter()
+            for _ in range(4 if warm else nfr):
+                tcur += dt_frame
+                hnew = cp.propagate_and_clone(tcur)[0]
+                cp.marginalize(chp.pop(0))
+                chp.append(hnew)
+            cp.synchronize()
+            tw1 = time.perf_counter()
+        line["propagation"] = {"ms_per_frame": 1e3 * (tw1 - tw0) / nfr, "frames_per_s": nfr / (tw1 - tw0), "state_N": cp.cov_rows(),
+                               "imu_samples_per_frame": 20,
+                               "note": "propagate_and_clone (host 15x15 IMU integration + EKFPropagation + augment_clone on the device) "
+                                       "+ marginalize(oldest clone), wall clock through the C ABI"}
+        cp.close()
+    except Exception as e:
+        line["propagation"] = {"error": repr(e)}
+
     # ---- sharded large update (cfg5: 4000 features sharded over the ranks, one NCCL all-gather of [R z]) ----
     if world > 1 and not args.no_sharded:
         try:

@@ -215,6 +215,10 @@ int ovp_propagator_feed_imu(ovp_ctx *ctx, double timestamp, const double wm[3], 
 /* propagate_and_clone (:37-126): IMU selection + mean (RK4 / discrete) + summed Phi, Qd on the host, then ONE device pass:
  * EKFPropagation + augment_clone.  Phi15 / Q15 (optional, 15x15 col-major) return the summed transition for parity tests. */
 int ovp_propagate_and_clone(ovp_ctx *ctx, double timestamp, double *Phi15, double *Q15, int *new_handle);
+/* fast_state_propagate (:128-224): IMU-rate odometry prediction on a copy of the IMU marginal; the state is not touched.
+ * state_plus13 = [q_GtoI(4) p_IinG(3) v_IinI(3) w_IinI(3)], cov144 = 12 x 12 column-major over [theta p v_local w];
+ * *ok = 0 when fewer than two IMU samples cover [state time, timestamp] (the reference returns false). */
+int ovp_fast_state_propagate(ovp_ctx *ctx, double timestamp, double *state_plus13, double *cov144, int *ok);
 
 /* Split form of ovp_msckf_update for callers that keep one feature batch resident on the device: prepare = validation,
  * planning and the single host->device copy; launch = kernels only (asynchronous, repeatable: the state changes, the plan

@@ -1981,6 +1981,71 @@ struct Propagator {
   }
 
   // Propagator.cpp:37-126; returns Phi_summed / Qd_summed for stage-level parity tests
+  // Propagator.cpp:128-224: IMU-rate prediction of (q, p, v_local, w) and of the 12x12 pose/velocity covariance on a COPY of the IMU
+  // marginal; the state is not touched.  Zero-order quaternion, constant-acceleration discrete model with averaged measurements.
+  bool fast_state_propagate(StateP state, double timestamp, Mat &state_plus, Mat &covariance) {
+    Mat est = state->_imu->vecvalue();                                        // 16 x 1 (:133)
+    Mat cov = StateHelper::get_marginal_covariance(state, {state->_imu});    // 15 x 15 (:134)
+    const double t_off = state->_calib_dt_CAMtoIMU->value[0];
+    std::vector<ImuData> prop = select_imu_readings(imu_data, state->_timestamp + t_off, timestamp + t_off);
+    if (prop.size() < 2)
+      return false; // (:147-148)
+    const Mat bg = est.block(10, 0, 3, 1), ba = est.block(13, 0, 3, 1);
+    for (size_t i = 0; i + 1 < prop.size(); i++) {
+      const double dt = prop[i + 1].timestamp - prop[i].timestamp;
+      const Mat w_hat = 0.5 * (prop[i + 1].wm + prop[i].wm) - bg, a_hat = 0.5 * (prop[i + 1].am + prop[i].am) - ba; // (:160-161)
+      const Mat R = quat_2_Rot(est.block(0, 0, 4, 1)), RT = R.T();
+      const Mat v = est.block(7, 0, 3, 1), pp = est.block(4, 0, 3, 1);
+      const Mat E = exp_so3((-dt) * w_hat), EJ = (-dt) * (E * Jr_so3((-dt) * w_hat));
+      Mat F(15, 15), G(15, 12);
+      F.setBlock(0, 0, E);                                   // (:169-181)
+      F.setBlock(0, 9, EJ);
+      F.setBlock(9, 9, Mat::Identity(3));
+      F.setBlock(6, 0, (-1.0) * (RT * skew_x(dt * a_hat)));
+      F.setBlock(6, 6, Mat::Identity(3));
+      F.setBlock(6, 12, (-dt) * RT);
+      F.setBlock(12, 12, Mat::Identity(3));
+      F.setBlock(3, 0, (-0.5) * (RT * skew_x((dt * dt) * a_hat)));
+      F.setBlock(3, 6, dt * Mat::Identity(3));
+      F.setBlock(3, 12, (-0.5 * dt * dt) * RT);
+      F.setBlock(3, 3, Mat::Identity(3));
+      G.setBlock(0, 0, EJ);                                  // (:182-187)
+      G.setBlock(6, 3, (-dt) * RT);
+      G.setBlock(3, 3, (-0.5 * dt * dt) * RT);
+      G.setBlock(9, 6, Mat::Identity(3));
+      G.setBlock(12, 9, Mat::Identity(3));
+      Mat Qc(12, 12);                                        // (:192-196)
+      for (int k = 0; k < 3; k++) {
+        Qc(k, k) = _noises.sigma_w_2() / dt;
+        Qc(3 + k, 3 + k) = _noises.sigma_a_2() / dt;
+        Qc(6 + k, 6 + k) = _noises.sigma_wb_2() * dt;
+        Qc(9 + k, 9 + k) = _noises.sigma_ab_2() * dt;
+      }
+      Mat Qd = G * Qc * G.T();
+      Qd = 0.5 * (Qd + Qd.T());
+      cov = F * cov * F.T() + Qd;                            // (:199)
+      est.setBlock(0, 0, rot_2_quat(E * R));                 // (:202-204)
+      est.setBlock(4, 0, pp + dt * v + (0.5 * dt * dt) * (RT * a_hat) - (0.5 * dt * dt) * _gravity);
+      est.setBlock(7, 0, v + dt * (RT * a_hat) - dt * _gravity);
+    }
+    const Mat q = est.block(0, 0, 4, 1);
+    state_plus = Mat(13, 1);                                 // (:208-215)
+    state_plus.setBlock(0, 0, q);
+    state_plus.setBlock(4, 0, est.block(4, 0, 3, 1));
+    state_plus.setBlock(7, 0, quat_2_Rot(q) * est.block(7, 0, 3, 1));
+    const size_t n = prop.size();
+    state_plus.setBlock(10, 0, 0.5 * (prop[n - 1].wm + prop[n - 2].wm) - bg);
+    Mat Phi = Mat::Identity(15);                             // (:220-226)
+    Phi.setBlock(6, 6, quat_2_Rot(q));
+    cov = Phi * cov * Phi.T();
+    covariance = Mat(12, 12);
+    covariance.setBlock(0, 0, cov.block(0, 0, 9, 9));
+    const double dtl = prop[n - 1].timestamp - prop[n - 2].timestamp;
+    for (int k = 0; k < 3; k++)
+      covariance(9 + k, 9 + k) = _noises.sigma_w_2() / dtl;
+    return true;
+  }
+
   void propagate_and_clone(StateP state, double timestamp, Mat *Phi_out = nullptr, Mat *Qd_out = nullptr) {
     if (state->_timestamp == timestamp)
       ref_exit("propagate_and_clone: same timestep");

@@ -578,6 +578,18 @@ int orc_prop_propagate_and_clone(void *p, double timestamp, double *Phi15, doubl
   });
 }
 
+int orc_prop_fast_state_propagate(void *p, double timestamp, double *state_plus13, double *cov144, int *ok) {
+  Ctx *c = (Ctx *)p;
+  return guarded(c, [&] {
+    Mat sp, cv;
+    *ok = c->prop.fast_state_propagate(c->state, timestamp, sp, cv) ? 1 : 0;
+    if (*ok) {
+      std::memcpy(state_plus13, sp.a.data(), sizeof(double) * 13);
+      std::memcpy(cov144, cv.a.data(), sizeof(double) * 144);
+    }
+  });
+}
+
 // ---- small math exports for unit tests of the restated ov_core pieces ------------------------------------------
 void orc_quat_2_Rot(const double *q, double *R) {
   Mat r = quat_2_Rot(from_colmajor(q, 4, 1));

@@ -950,6 +950,116 @@ static void predict_mean_discrete(const ImuMean &x, const V3 &g, bool imu_avg, d
 
 extern "C" {
 
+// Propagator::fast_state_propagate (Propagator.cpp:128-224): IMU-rate odometry prediction on a COPY of the IMU marginal (15 x 15
+// read back from the device covariance); nothing in the state changes.  state_plus = [q(4) p(3) v_local(3) w(3)], covariance 12 x 12
+// (column-major) over [theta p v_local w].  *ok = 0 when fewer than two IMU samples cover the interval (:147-148).
+int ovp_fast_state_propagate(ovp_ctx *h, double timestamp, double *state_plus13, double *cov144, int *ok) {
+  using namespace ovp::hm;
+  Ctx *c = &h->c;
+  *ok = 0;
+  int st = sync_host_values(c);
+  if (st)
+    return st;
+  const double *iv = &c->h_val[(size_t)c->h_imu * OVP_VAL_STRIDE];
+  const double t_off = c->h_val[(size_t)c->h_dt * OVP_VAL_STRIDE];
+  double P15[225];
+  st = ovp_get_marginal_covariance(h, &c->h_imu, 1, P15); // column-major, symmetric
+  if (st)
+    return st;
+  std::vector<ImuSample> prop = select_imu_readings(c->imu_data, c->timestamp + t_off, timestamp + t_off);
+  if (prop.size() < 2)
+    return OVP_OK;
+  M15 cov;
+  for (int i = 0; i < 15; i++)
+    for (int j = 0; j < 15; j++)
+      cov(i, j) = P15[15 * j + i];
+  V4 q = {{iv[0], iv[1], iv[2], iv[3]}};
+  V3 p = v3(iv[4], iv[5], iv[6]), v = v3(iv[7], iv[8], iv[9]);
+  const V3 bg = v3(iv[10], iv[11], iv[12]), ba = v3(iv[13], iv[14], iv[15]);
+  const V3 g = v3(c->gravity[0], c->gravity[1], c->gravity[2]);
+  const M3 I3 = eye3();
+  auto smp = [](const double *x) { return v3(x[0], x[1], x[2]); };
+  for (size_t i = 0; i + 1 < prop.size(); i++) {
+    const double dt = prop[i + 1].t - prop[i].t;
+    const V3 w_hat = 0.5 * (smp(prop[i + 1].wm) + smp(prop[i].wm)) - bg, a_hat = 0.5 * (smp(prop[i + 1].am) + smp(prop[i].am)) - ba;
+    const M3 R = quat_2_Rot(q), RT = transpose(R);
+    const M3 E = exp_so3((-dt) * w_hat), EJ = (-dt) * (E * Jr_so3((-dt) * w_hat));
+    M15 F;
+    double G[15][12];
+    std::memset(G, 0, sizeof(G));
+    auto setG = [&](int i0, int j0, const M3 &B) {
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++)
+          G[i0 + a][j0 + b] = B(a, b);
+    };
+    F.setBlock3(0, 0, E);
+    F.setBlock3(0, 9, EJ);
+    F.setBlock3(9, 9, I3);
+    F.setBlock3(6, 0, (-1.0) * (RT * skew(dt * a_hat)));
+    F.setBlock3(6, 6, I3);
+    F.setBlock3(6, 12, (-dt) * RT);
+    F.setBlock3(12, 12, I3);
+    F.setBlock3(3, 0, (-0.5) * (RT * skew((dt * dt) * a_hat)));
+    F.setBlock3(3, 6, dt * I3);
+    F.setBlock3(3, 12, (-0.5 * dt * dt) * RT);
+    F.setBlock3(3, 3, I3);
+    setG(0, 0, EJ);
+    setG(6, 3, (-dt) * RT);
+    setG(3, 3, (-0.5 * dt * dt) * RT);
+    setG(9, 6, I3);
+    setG(12, 9, I3);
+    double qc[12];
+    for (int k = 0; k < 3; k++) {
+      qc[k] = c->sigma_w * c->sigma_w / dt;
+      qc[3 + k] = c->sigma_a * c->sigma_a / dt;
+      qc[6 + k] = c->sigma_wb * c->sigma_wb * dt;
+      qc[9 + k] = c->sigma_ab * c->sigma_ab * dt;
+    }
+    M15 Qd;
+    for (int a = 0; a < 15; a++)
+      for (int b = 0; b < 15; b++) {
+        double s = 0;
+        for (int k = 0; k < 12; k++)
+          s += G[a][k] * qc[k] * G[b][k];
+        Qd(a, b) = s;
+      }
+    M15 FP = mulT(mul(F, cov), F);
+    for (int a = 0; a < 15; a++)
+      for (int b = 0; b < 15; b++)
+        cov(a, b) = FP(a, b) + 0.5 * (Qd(a, b) + Qd(b, a));
+    const V3 Ra = RT * a_hat;
+    const V3 pn = p + dt * v + (0.5 * dt * dt) * Ra - (0.5 * dt * dt) * g, vn = v + dt * Ra - dt * g;
+    q = rot_2_quat(E * R);
+    p = pn;
+    v = vn;
+  }
+  const M3 Rq = quat_2_Rot(q);
+  const V3 vl = Rq * v;
+  const size_t n = prop.size();
+  const V3 wl = 0.5 * (smp(prop[n - 1].wm) + smp(prop[n - 2].wm)) - bg;
+  for (int k = 0; k < 4; k++)
+    state_plus13[k] = q[k];
+  for (int k = 0; k < 3; k++) {
+    state_plus13[4 + k] = p[k];
+    state_plus13[7 + k] = vl[k];
+    state_plus13[10 + k] = wl[k];
+  }
+  M15 Phi;
+  for (int i = 0; i < 15; i++)
+    Phi(i, i) = 1.0;
+  Phi.setBlock3(6, 6, Rq);
+  M15 rc = mulT(mul(Phi, cov), Phi);
+  std::memset(cov144, 0, 144 * sizeof(double));
+  for (int i = 0; i < 9; i++)
+    for (int j = 0; j < 9; j++)
+      cov144[12 * j + i] = rc(i, j);
+  const double dtl = prop[n - 1].t - prop[n - 2].t;
+  for (int k = 0; k < 3; k++)
+    cov144[12 * (9 + k) + 9 + k] = c->sigma_w * c->sigma_w / dtl;
+  *ok = 1;
+  return OVP_OK;
+}
+
 int ovp_propagate_and_clone(ovp_ctx *h, double timestamp, double *Phi15, double *Q15, int *new_handle) {
   using namespace ovp::hm;
   Ctx *c = &h->c;

@@ -76,6 +76,39 @@ inline M3 quat_2_Rot(const V4 &q) {
   double w = q[3];
   return (2 * w * w - 1) * eye3() + (-2 * w) * skew(v) + 2.0 * outer(v, v);
 }
+// rotation matrix -> JPL quaternion (ov_core quat_ops.h rot_2_quat: the largest of {R00, R11, R22, trace} picks the branch)
+inline V4 rot_2_quat(const M3 &R) {
+  V4 q;
+  const double T = R(0, 0) + R(1, 1) + R(2, 2);
+  int br = 3;
+  if (R(0, 0) >= T && R(0, 0) >= R(1, 1) && R(0, 0) >= R(2, 2))
+    br = 0;
+  else if (R(1, 1) >= T && R(1, 1) >= R(0, 0) && R(1, 1) >= R(2, 2))
+    br = 1;
+  else if (R(2, 2) >= T && R(2, 2) >= R(0, 0) && R(2, 2) >= R(1, 1))
+    br = 2;
+  if (br == 3) {
+    q[3] = std::sqrt((1 + T) / 4);
+    const double s = 1 / (4 * q[3]);
+    q[0] = s * (R(1, 2) - R(2, 1));
+    q[1] = s * (R(2, 0) - R(0, 2));
+    q[2] = s * (R(0, 1) - R(1, 0));
+  } else {
+    const int i = br, j = (br + 1) % 3, k = (br + 2) % 3;
+    q[i] = std::sqrt((1 + 2 * R(i, i) - T) / 4);
+    const double s = 1 / (4 * q[i]);
+    q[j] = s * (R(i, j) + R(j, i));
+    q[k] = s * (R(i, k) + R(k, i));
+    q[3] = s * (R(j, k) - R(k, j));
+  }
+  if (q[3] < 0)
+    for (int a = 0; a < 4; a++)
+      q[a] = -q[a];
+  const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int a = 0; a < 4; a++)
+    q[a] /= n;
+  return q;
+}
 inline V4 quatnorm(V4 q) {
   if (q[3] < 0)
     for (int i = 0; i < 4; i++)

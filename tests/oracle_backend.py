@@ -300,6 +300,11 @@ class OracleContext(object):
         w, a = _f64(wm), _f64(am)
         self.lib.orc_prop_feed_imu(self.h, C.c_double(t), _p(w), _p(a))
 
+    def fast_state_propagate(self, t):
+        sp, cv, ok = np.zeros(13), np.zeros((12, 12), order="F"), C.c_int(0)
+        self._ck(self.lib.orc_prop_fast_state_propagate(self.h, C.c_double(t), _p(sp), _p(cv), C.byref(ok)))
+        return (sp, cv) if ok.value else None
+
     def propagate_and_clone(self, t):
         Phi, Q, nh = np.zeros((15, 15), order="F"), np.zeros((15, 15), order="F"), C.c_int(-1)
         self._ck(self.lib.orc_prop_propagate_and_clone(self.h, C.c_double(t), _p(Phi), _p(Q), C.byref(nh)))

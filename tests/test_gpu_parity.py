@@ -258,6 +258,31 @@ def test_propagate_and_clone(chi2_table):
     compare_states(ctx, orc, S, chg + [hg], cho + [ho], 1e-10)
 
 
+def test_fast_state_propagate(chi2_table):
+    """Propagator::fast_state_propagate (Propagator.cpp:128-224): prediction on a copy, state untouched."""
+    S = synth.make_scenario("tiny_points", seed=4)
+    ctx, orc, chg, cho = make_pair(S, chi2_table)
+    rng = np.random.RandomState(5)
+    t0 = S.timestamp
+    for be in (ctx, orc):
+        be.propagator_set_noise(1.6968e-04, 1.9393e-05, 2.0e-3, 3.0e-3, 9.81)
+    assert ctx.fast_state_propagate(t0 + 0.05) is None and orc.fast_state_propagate(t0 + 0.05) is None  # no IMU yet
+    for k in range(60):
+        t = t0 - 0.0123 + 0.0025 * k
+        wm = np.array([0.3, -0.15, 0.2]) + 0.01 * rng.randn(3)
+        am = np.array([0.2, 9.7, 0.4]) + 0.05 * rng.randn(3)
+        ctx.feed_imu(t, wm, am)
+        orc.feed_imu(t, wm, am)
+    P0, v0 = ctx.cov().copy(), ctx.var_get(ctx.handle_imu())[0].copy()
+    for t1 in (t0 + 0.011, t0 + 0.1):
+        sg, cg = ctx.fast_state_propagate(t1)
+        so, co = orc.fast_state_propagate(t1)
+        assert np.allclose(sg, so, rtol=1e-12, atol=1e-13)
+        assert relerr(cg, co) < 1e-11
+        assert np.allclose(cg, cg.T, atol=1e-18) and np.linalg.eigvalsh(cg).min() > 0
+    assert np.array_equal(ctx.cov(), P0) and np.array_equal(ctx.var_get(ctx.handle_imu())[0], v0)  # nothing mutated
+
+
 def test_error_codes(chi2_table):
     from ov_plane_b200 import api
     S = synth.make_scenario("tiny_points", seed=0)

@@ -4,6 +4,7 @@ derivatives, orthogonality, algebraic identities of the Kalman update), (ii) a N
 golden vectors (tests/golden/, regression pin of the oracle itself; regenerate with tests/golden/make_golden.py)."""
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -328,3 +329,13 @@ def test_slam_update_against_numpy_restack(chi2_table):
     P1 = P0 - K @ H @ P0
     assert np.abs(orc.cov() - P1).max() < 1e-9 * np.abs(P0).max()
     assert orc.slam_should_marg(u["featid"][2]) == 1
+
+
+@pytest.mark.parametrize("name,seed,nslam", [("tiny_planes", 0, 6), ("tiny_points", 0, 8)])
+def test_oracle_reproduces_slam_golden_vectors(name, seed, nslam, chi2_table):
+    sys.path.insert(0, GOLD)
+    import make_golden
+    g = np.load(os.path.join(GOLD, "slam_%s_s%d.npz" % (name, seed)))
+    r = make_golden.slam_case(name, seed, nslam, lambda S: ob.OracleContext(S.options), chi2_table)
+    assert np.array_equal(r["init_status"], g["init_status"]) and np.array_equal(r["upd_status"], g["upd_status"])
+    assert np.allclose(r["P_init"], g["P_init"], rtol=1e-12, atol=1e-18) and np.allclose(r["P_upd"], g["P_upd"], rtol=1e-10, atol=1e-16)

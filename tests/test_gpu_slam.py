@@ -95,3 +95,21 @@ def test_slam_update_without_plane_constraint(chi2_table):
     assert (g2["feat_status"] != 3).all() and (g2["feat_status"] == 1).any()
     P = ctx.cov()
     assert np.allclose(P, P.T, rtol=0, atol=1e-12 * np.abs(P).max()) and np.linalg.eigvalsh(P).min() > -1e-12
+
+
+@pytest.mark.parametrize("name,seed,nslam", [("tiny_planes", 0, 6), ("tiny_points", 0, 8)])
+def test_slam_against_committed_golden_vectors(name, seed, nslam, chi2_table):
+    """the CUDA path against the committed fixtures (tests/golden/slam_*.npz, written by the oracle): no oracle at run time"""
+    import os
+    import sys
+    from ov_plane_b200 import api
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold)
+    import make_golden
+    g = np.load(os.path.join(gold, "slam_%s_s%d.npz" % (name, seed)))
+    r = make_golden.slam_case(name, seed, nslam, lambda S: api.Context(S.options, device=0, max_state=S.N + 3 * nslam + 64, max_meas_rows=8192),
+                              chi2_table)
+    assert np.array_equal(r["init_status"], g["init_status"]) and np.array_equal(r["upd_status"], g["upd_status"])
+    assert relerr(r["P_init"], g["P_init"]) < 1e-6 and relerr(r["P_upd"], g["P_upd"]) < 1e-6
+    assert np.allclose(r["upd_chi2"], g["upd_chi2"], rtol=1e-6, atol=1e-8)
+    assert np.allclose(r["imu"], g["imu"], rtol=1e-7, atol=1e-9)

@@ -54,23 +54,28 @@ __global__ void __launch_bounds__(128) finish_update_kernel(int nh, const int *v
   if (id < 0)
     return;
   const int s = var_size[h];
+  // lane -> (row i = lane & 15 of the variable, half kh = lane >> 4 of the compressed rows): the s rows of one column of Y are
+  // contiguous, so a half warp reads one 8 s-byte run per column; four accumulators per lane break the FMA dependency chain
+  const int i = lane & 15, kh = lane >> 4;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (i < s) {
+    const double *y = Y + id + i;
+    int k = kh;
+    for (; k + 6 < rr; k += 8) {
+      a0 = fma(y[(size_t)k * ldy], w[k], a0);
+      a1 = fma(y[(size_t)(k + 2) * ldy], w[k + 2], a1);
+      a2 = fma(y[(size_t)(k + 4) * ldy], w[k + 4], a2);
+      a3 = fma(y[(size_t)(k + 6) * ldy], w[k + 6], a3);
+    }
+    for (; k < rr; k += 2)
+      a0 = fma(y[(size_t)k * ldy], w[k], a0);
+  }
+  double d = (a0 + a1) + (a2 + a3);
+  d += __shfl_xor_sync(0xffffffffu, d, 16);
   double acc[15];
 #pragma unroll
-  for (int i = 0; i < 15; i++)
-    acc[i] = 0.0;
-  for (int k = lane; k < rr; k += 32) {
-    const double wk = w[k];
-    const double *y = Y + (size_t)k * ldy + id;
-#pragma unroll
-    for (int i = 0; i < 15; i++)
-      if (i < s)
-        acc[i] = fma(y[i], wk, acc[i]);
-  }
-#pragma unroll
-  for (int i = 0; i < 15; i++)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  for (int j = 0; j < 15; j++)
+    acc[j] = __shfl_sync(0xffffffffu, d, j); // dx of row j (rows >= s: zero)
   if (lane < s && P[(size_t)(id + lane) * ldP + id + lane] < 0.0)
     atomicExch(neg_flag, 1);
   if (lane != 0)

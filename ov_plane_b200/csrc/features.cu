@@ -62,40 +62,27 @@ __device__ __forceinline__ double warp_sum(double s) {
 // Mahalanobis gate on the sub-block rows [rb, rb+nr) x columns [cb, cb+ncg) of the feature block A:
 // S = H P_marg H^T + I, chi2 = r^T S^-1 r (UpdaterMSCKF.cpp:739-742, UpdaterSLAM.cpp:528-532).  gid[c] = state index of local column c.
 // Returns chi2 (NaN-safe: ok flag in *ok_out).  All 128 threads participate.
-__device__ double gate_chi2(const double *A, int lda, double *T, double *S, int ldt, double *ybuf, int rb, int nr, int cb, int ncg,
-                            const int *gid, const double *P, int ldP, int c_res, int tid, int *s_ok, double *s_chi2) {
-  const int nchunk = (nr + 7) / 8;
-  for (int w = tid; w < ncg * nchunk; w += 128) {
-    int b = w % ncg, ch = w / ncg;
-    int i0 = ch * 8;
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const double *Pc = P + (size_t)gid[cb + b] * ldP;
-    int k = 0;
-    for (; k + 4 <= ncg; k += 4) { // four covariance entries in flight per trip: the gather is L2-latency bound
-      double p[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-        p[u] = Pc[gid[cb + k + u]];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const double *hc = A + (size_t)(cb + k + u) * lda + rb + i0;
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-          if (i0 + i < nr)
-            acc[i] += hc[i] * p[u];
-      }
+__device__ double gate_chi2(const double *A, int lda, double *T, double *S, int ldt, double *ybuf, double *Pp, int ldpp, int rb, int nr, int cb,
+                            int ncg, const int *gid, const double *P, int ldP, int c_res, int tid, int *s_ok, double *s_chi2) {
+  // T = H P_marg by panels of 8 covariance columns: the panel P[gid[:], gid[b0 .. b0+7]] is gathered into shared memory with all
+  // loads of a thread in flight at once (runs of 6-14 contiguous doubles per clone / calibration block), then every thread forms
+  // dot products out of shared memory.  (Gathering P entry by entry inside the dot product left the kernel L2-latency bound.)
+  for (int b0 = 0; b0 < ncg; b0 += 8) {
+    const int nb = min(8, ncg - b0);
+    for (int w = tid; w < nb * ncg; w += 128) {
+      const int b = w / ncg, k = w - b * ncg;
+      Pp[b * ldpp + k] = P[(size_t)gid[cb + b0 + b] * ldP + gid[cb + k]];
     }
-    for (; k < ncg; k++) {
-      double p = Pc[gid[cb + k]];
-      const double *hc = A + (size_t)(cb + k) * lda + rb + i0;
-#pragma unroll
-      for (int i = 0; i < 8; i++)
-        if (i0 + i < nr)
-          acc[i] += hc[i] * p;
+    __syncthreads();
+    for (int w = tid; w < nb * nr; w += 128) {
+      const int b = w / nr, i = w - b * nr;
+      const double *hc = A + (size_t)cb * lda + rb + i, *pc = Pp + b * ldpp;
+      double acc = 0.0;
+      for (int k = 0; k < ncg; k++)
+        acc += hc[(size_t)k * lda] * pc[k];
+      T[(size_t)(b0 + b) * ldt + i] = acc;
     }
-    for (int i = 0; i < 8; i++)
-      if (i0 + i < nr)
-        T[(size_t)b * ldt + i0 + i] = acc[i];
+    __syncthreads();
   }
   __syncthreads();
   for (int w = tid; w < nr * nr; w += 128) {
@@ -184,6 +171,7 @@ __global__ void __launch_bounds__(128) feature_kernel(FeatArgs a) {
   double *T = A + (size_t)lda * a.maxcols;          // ldt * (maxcols)   (gate only)
   double *S = T + (size_t)a.ldt * a.maxcols;        // ldt * ldt         (gate only)
   double *vbuf = (a.mode == 1) ? T : S + (size_t)a.ldt * a.ldt; // reflector / forward-substitution vector
+  double *Pp = vbuf + lda + 1;                                 // 8 x maxcols covariance panel (gate only)
   __shared__ int gid[3 + 14 + 6 * 64 + 3]; // state index of every local column except the residual
   __shared__ double s_beta, s_chi2;
   __shared__ int s_ok;
@@ -314,7 +302,7 @@ __global__ void __launch_bounds__(128) feature_kernel(FeatArgs a) {
     cb0 = 3;
     ncs = cf;
     if (a.mode == 0) {
-      double chi2 = gate_chi2(A, lda, T, S, a.ldt, vbuf, rb, nr, cb0, ncs, gid, a.P, a.ldP, c_res, tid, &s_ok, &s_chi2);
+      double chi2 = gate_chi2(A, lda, T, S, a.ldt, vbuf, Pp, a.maxcols, rb, nr, cb0, ncs, gid, a.P, a.ldP, c_res, tid, &s_ok, &s_chi2);
       double thr = a.chi2_mult * a.chi2_table[nr < a.chi2_n ? nr : a.chi2_n - 1];
       accept = (s_ok && !(chi2 > thr)) ? 1 : 0;
       if (tid == 0) {
@@ -324,14 +312,14 @@ __global__ void __launch_bounds__(128) feature_kernel(FeatArgs a) {
     }
   } else {
     // ---- SLAM landmark: no nullspace; gate with the plane constraint, on failure retry without it (UpdaterSLAM.cpp:528-622) ----
-    double chi2 = gate_chi2(A, lda, T, S, a.ldt, vbuf, 0, nr, 0, ncs, gid, a.P, a.ldP, c_res, tid, &s_ok, &s_chi2);
+    double chi2 = gate_chi2(A, lda, T, S, a.ldt, vbuf, Pp, a.maxcols, 0, nr, 0, ncs, gid, a.P, a.ldP, c_res, tid, &s_ok, &s_chi2);
     double thr = a.chi2_mult * a.chi2_table[nr < a.chi2_n ? nr : a.chi2_n - 1];
     int st = (s_ok && !(chi2 > thr)) ? 1 : 0;
     if (!st && has_plane) {
       __syncthreads();
       nr = 2 * m;
       ncs = 3 + cf;
-      chi2 = gate_chi2(A, lda, T, S, a.ldt, vbuf, 0, nr, 0, ncs, gid, a.P, a.ldP, c_res, tid, &s_ok, &s_chi2);
+      chi2 = gate_chi2(A, lda, T, S, a.ldt, vbuf, Pp, a.maxcols, 0, nr, 0, ncs, gid, a.P, a.ldP, c_res, tid, &s_ok, &s_chi2);
       thr = a.chi2_mult * a.chi2_table[nr < a.chi2_n ? nr : a.chi2_n - 1];
       st = (s_ok && !(chi2 > thr)) ? 3 : 0;
     }

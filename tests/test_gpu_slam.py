@@ -32,7 +32,7 @@ def _slam_case(name, seed, chi2_table, nslam, perturb=0.0):
 
 
 @pytest.mark.parametrize("name,seed,nslam,perturb", [("tiny_planes", 0, 6, 0.0), ("small_planes", 0, 40, 0.0), ("small_planes", 1, 40, 1.0), ("small_planes", 3, 40, 1.0),
-                                                     ("tiny_points", 0, 8, 0.0)])
+                                                     ("tiny_points", 0, 8, 0.0), ("cfg3_n512_f600_p8", 0, 20, 1.0)])
 def test_slam_delayed_init_then_update(name, seed, nslam, perturb, chi2_table):
     S, ctx, orc, bg, bo, chg, cho = _slam_case(name, seed, chi2_table, nslam, perturb)
     n0 = ctx.cov_rows()

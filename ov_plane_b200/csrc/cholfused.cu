@@ -161,12 +161,29 @@ __device__ __noinline__ void cf_store_tile(const double *s, double *g, int ld, i
     int r2, c;
     cf_chunk(threadIdx.x + 256 * q, r2, c);
     double *dst = g + (size_t)c * ld + r2;
+    if (lower_zero_upper && r2 + 1 < c)
+      continue; // strictly upper chunk of a diagonal tile: zero in global memory already (never written by anyone)
     if (c < cv) {
       if (r2 + 1 < rv)
         __stcg(reinterpret_cast<double2 *>(dst), v[q]);
       else if (r2 < rv)
         __stcg(dst, v[q].x);
     }
+  }
+}
+
+// The inverse tile X only carries its four 16x16 diagonal blocks: they travel as 4 x 16 x 16 doubles (block b at g + 256 b,
+// column-major 16 x 16), one 16-byte chunk per thread and block pair
+__device__ __forceinline__ void cf_store_xdiag(const double *s, double *g) {
+  for (int q = threadIdx.x; q < 512; q += 256) {
+    const int b = q >> 7, c = (q >> 3) & 15, r2 = (q & 7) * 2;
+    __stcg(reinterpret_cast<double2 *>(g + 256 * b + 16 * c + r2), *reinterpret_cast<const double2 *>(s + CF_AT(16 * b + r2, 16 * b + c)));
+  }
+}
+__device__ __forceinline__ void cf_load_xdiag(double *s, const double *g) { // the rest of s is not touched (never read by cf_bsolve64)
+  for (int q = threadIdx.x; q < 512; q += 256) {
+    const int b = q >> 7, c = (q >> 3) & 15, r2 = (q & 7) * 2;
+    *reinterpret_cast<double2 *>(s + CF_AT(16 * b + r2, 16 * b + c)) = __ldcg(reinterpret_cast<const double2 *>(g + 256 * b + 16 * c + r2));
   }
 }
 
@@ -560,7 +577,7 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       if (k < 3)
         CF_TS(2 + 2 * k)
       PT(13)
-      cf_store_tile(b1, p.LinvD + (size_t)k * CF_B * CF_B, CF_B, CF_B, CF_B, false); // the four 16x16 inverses (rest of the tile is zero)
+      cf_store_xdiag(b1, p.LinvD + (size_t)k * CF_B * CF_B); // the four 16x16 inverses
       PT(19)
       cf_store_tile(a, gA, p.ld, rv, bs, true);
       PT(20)
@@ -638,7 +655,7 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       cf_wait(fdiag + j, e);
       CF_TS(4)
       cf_load_tile(b1, p.A + (size_t)(CF_B * j) * p.ld + CF_B * j, p.ld, min(CF_B, p.n - CF_B * j), bs, true); // L(j,j)
-      cf_load_tile(b2, p.LinvD + (size_t)j * CF_B * CF_B, CF_B, CF_B, CF_B, false);                           // its 16x16 inverses
+      cf_load_xdiag(b2, p.LinvD + (size_t)j * CF_B * CF_B);                                                   // its 16x16 inverses
       __syncthreads();
       CF_TS(5)
       cf_bsolve64(a, b1, b2, sm + 3 * CF_B * CF_LD);
@@ -677,7 +694,7 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       const int bs = min(CF_B, p.npiv - CF_B * k);
       cf_wait(fdiag + k, e);
       cf_load_tile(Lt, p.A + (size_t)(CF_B * k) * p.ld + CF_B * k, p.ld, min(CF_B, p.n - CF_B * k), bs, true);
-      cf_load_tile(Xt, p.LinvD + (size_t)k * CF_B * CF_B, CF_B, CF_B, CF_B, false);
+      cf_load_xdiag(Xt, p.LinvD + (size_t)k * CF_B * CF_B);
       __syncthreads();
       if (warp < 2) { // yk (16 x 64) = mrow[:, 64k ..] L(k,k)^-T: rows are independent, warp w owns rows 8w..8w+7 (cf_bsolve64 in row-major)
         const int r = 8 * warp + g;

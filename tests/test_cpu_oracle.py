@@ -339,3 +339,80 @@ def test_oracle_reproduces_slam_golden_vectors(name, seed, nslam, chi2_table):
     r = make_golden.slam_case(name, seed, nslam, lambda S: ob.OracleContext(S.options), chi2_table)
     assert np.array_equal(r["init_status"], g["init_status"]) and np.array_equal(r["upd_status"], g["upd_status"])
     assert np.allclose(r["P_init"], g["P_init"], rtol=1e-12, atol=1e-18) and np.allclose(r["P_upd"], g["P_upd"], rtol=1e-10, atol=1e-16)
+
+
+def test_fast_state_propagate_against_numpy():
+    """Propagator::fast_state_propagate of the restatement == a NumPy re-derivation of Propagator.cpp:128-224 (second, independent
+    transcription: Jr_so3 by its series definition, Phi / Qd assembled with np.block), and the state is left untouched."""
+    S = synth.make_scenario("tiny_points", seed=4)
+    orc = ob.OracleContext(S.options)
+    synth.load_scenario_into(orc, S)
+    sw, swb, sa, sab, grav = 1.6968e-04, 1.9393e-05, 2.0e-3, 3.0e-3, 9.81
+    orc.propagator_set_noise(sw, swb, sa, sab, grav)
+    rng = np.random.RandomState(5)
+    t0 = S.timestamp
+    ts, wms, ams = [], [], []
+    for k in range(70):
+        t = t0 - 0.0323 + 0.0025 * k  # the buffer must cover t0 + t_off (t_off = -13 ms in this scenario)
+        wm = np.array([0.3, -0.15, 0.2]) + 0.01 * rng.randn(3)
+        am = np.array([0.2, 9.7, 0.4]) + 0.05 * rng.randn(3)
+        orc.feed_imu(t, wm, am)
+        ts.append(t), wms.append(wm), ams.append(am)
+    P_before = orc.cov().copy()
+    t1 = t0 + 0.1
+    sp, cv = orc.fast_state_propagate(t1)
+    assert np.array_equal(orc.cov(), P_before)
+
+    # ---- NumPy side ----
+    def Jr(phi):  # right Jacobian of SO(3)
+        th = np.linalg.norm(phi)
+        K = jpl.skew(phi)
+        if th < 1e-7:
+            return np.eye(3) - 0.5 * K
+        return np.eye(3) - (1 - np.cos(th)) / th**2 * K + (th - np.sin(th)) / th**3 * K @ K
+
+    x = orc.var_get(orc.handle_imu())[0].copy()
+    cov = orc.get_marginal_covariance([orc.handle_imu()])
+    toff = orc.var_get(orc.handle_dt())[0][0]
+    ts, wms, ams = np.array(ts), np.array(wms), np.array(ams)
+    a, b = t0 + toff, t1 + toff
+
+    def interp(t):
+        i = np.searchsorted(ts, t) - 1
+        lam = (t - ts[i]) / (ts[i + 1] - ts[i])
+        return (1 - lam) * wms[i] + lam * wms[i + 1], (1 - lam) * ams[i] + lam * ams[i + 1]
+
+    inner = [(t, w, am) for t, w, am in zip(ts, wms, ams) if a < t < b]
+    seq = [(a,) + interp(a)] + inner + [(b,) + interp(b)]
+    bg, ba = x[10:13], x[13:16]
+    g = np.array([0, 0, grav])
+    for (ta, wa, aa), (tb, wb, ab) in zip(seq[:-1], seq[1:]):
+        dt = tb - ta
+        w_hat, a_hat = 0.5 * (wa + wb) - bg, 0.5 * (aa + ab) - ba
+        R = jpl.quat_2_Rot(x[0:4])
+        E = jpl.exp_so3(-w_hat * dt)
+        EJ = -E @ Jr(-w_hat * dt) * dt
+        Z, I = np.zeros((3, 3)), np.eye(3)
+        F = np.block([[E, Z, Z, EJ, Z],
+                      [-0.5 * R.T @ jpl.skew(a_hat * dt * dt), I, I * dt, Z, -0.5 * R.T * dt * dt],
+                      [-R.T @ jpl.skew(a_hat * dt), Z, I, Z, -R.T * dt],
+                      [Z, Z, Z, I, Z],
+                      [Z, Z, Z, Z, I]])
+        G = np.block([[EJ, Z, Z, Z], [Z, -0.5 * R.T * dt * dt, Z, Z], [Z, -R.T * dt, Z, Z], [Z, Z, I, Z], [Z, Z, Z, I]])
+        Qc = np.diag([sw**2 / dt] * 3 + [sa**2 / dt] * 3 + [swb**2 * dt] * 3 + [sab**2 * dt] * 3)
+        Qd = G @ Qc @ G.T
+        cov = F @ cov @ F.T + 0.5 * (Qd + Qd.T)
+        p, v = x[4:7].copy(), x[7:10].copy()
+        x[0:4] = jpl.rot_2_quat(E @ R)
+        x[4:7] = p + v * dt + 0.5 * R.T @ a_hat * dt * dt - 0.5 * g * dt * dt
+        x[7:10] = v + R.T @ a_hat * dt - g * dt
+    Rq = jpl.quat_2_Rot(x[0:4])
+    sp_np = np.concatenate([x[0:4], x[4:7], Rq @ x[7:10], 0.5 * (seq[-1][1] + seq[-2][1]) - bg])
+    Phi = np.eye(15)
+    Phi[6:9, 6:9] = Rq
+    c2 = Phi @ cov @ Phi.T
+    cv_np = np.zeros((12, 12))
+    cv_np[:9, :9] = c2[:9, :9]
+    cv_np[9:, 9:] = np.eye(3) * sw**2 / (seq[-1][0] - seq[-2][0])
+    assert np.allclose(sp, sp_np, rtol=1e-10, atol=1e-12)
+    assert np.abs(cv - cv_np).max() < 1e-10 * np.abs(cv_np).max()

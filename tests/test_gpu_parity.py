@@ -267,8 +267,8 @@ def test_fast_state_propagate(chi2_table):
     for be in (ctx, orc):
         be.propagator_set_noise(1.6968e-04, 1.9393e-05, 2.0e-3, 3.0e-3, 9.81)
     assert ctx.fast_state_propagate(t0 + 0.05) is None and orc.fast_state_propagate(t0 + 0.05) is None  # no IMU yet
-    for k in range(60):
-        t = t0 - 0.0123 + 0.0025 * k
+    for k in range(70):
+        t = t0 - 0.0323 + 0.0025 * k  # the buffer must cover t0 + t_off (t_off = -13 ms in this scenario)
         wm = np.array([0.3, -0.15, 0.2]) + 0.01 * rng.randn(3)
         am = np.array([0.2, 9.7, 0.4]) + 0.05 * rng.randn(3)
         ctx.feed_imu(t, wm, am)

@@ -850,6 +850,20 @@ int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const dou
     g_cf_attr_set = true;
   }
   const int grid = p.ntile + p.nrb;
+  {
+    // the grid must be co-resident (the spine and the tile CTAs wait on each other): one CTA per SM at this shared-memory size
+    static int max_coresident = 0;
+    if (!max_coresident) {
+      int per_sm = 0, sms = 0, dev = 0;
+      OVP_CUDA(cudaGetDevice(&dev));
+      OVP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      OVP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_fused_kernel, 256, 220 * 1024));
+      max_coresident = std::max(1, per_sm) * sms;
+    }
+    if (grid > max_coresident)
+      return fail(c, OVP_ERR_CAPACITY, "chol_fused: a %d-wide system with %d right-hand-side rows needs %d co-resident CTAs, the device holds %d", n,
+                  vrows, grid, max_coresident);
+  }
   double flops = (double)npiv * npiv * npiv / 3.0 + (double)(n - npiv) * npiv * npiv + (double)vrows * npiv * npiv;
   prof_begin(c, PROF_POTRF, flops);
   // cooperative launch: the spine waits on tile CTAs that wait on the spine, so the whole grid must be co-resident

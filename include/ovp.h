@@ -124,6 +124,14 @@ int ovp_merge_planes_and_marginalize(ovp_ctx *ctx, const int64_t *f2p_feat, cons
 /* ---- UpdaterHelper / UpdaterPlane static helpers (stateless, host buffers in / out, computed on the GPU) ------------ */
 /* UpdaterHelper::get_feature_jacobian_full (UpdaterHelper.cpp:195-513), mono, GLOBAL_3D.  Outputs col-major with
  * ld = *rows_out; buffers sized for 3*m(+1) rows and (14 + 6*m + 3) columns; x_order receives variable handles. */
+/* UpdaterHelper::get_feature_jacobian_representation (UpdaterHelper.cpp:35-193), context-free host helper.  representation follows
+ * ov_type::LandmarkRepresentation (0 GLOBAL_3D, 1 GLOBAL_FULL_INVERSE_DEPTH, 2 ANCHORED_3D, 3 ANCHORED_FULL_INVERSE_DEPTH,
+ * 4 ANCHORED_MSCKF_INVERSE_DEPTH, 5 ANCHORED_INVERSE_DEPTH_SINGLE); poses are [q (JPL xyzw), p]: anchor = [q_GtoI, p_IinG],
+ * calib = [q_ItoC, p_IinC].  Outputs column-major: H_f 3 x hf_cols (3, or 1 for the single-depth form), and for anchored forms
+ * (has_anchor = 1) H_anc 3 x 6 w.r.t. the anchor clone [theta, p] and H_calib 3 x 6 w.r.t. the extrinsics [theta, p]. */
+int ovp_feature_jacobian_representation(int representation, int do_fej, const double *p_FinG, const double *p_FinG_fej,
+                                        const double *p_FinA, const double *anchor_pose7, const double *anchor_pose_fej7,
+                                        const double *calib7, double *H_f, int *hf_cols, double *H_anc, double *H_calib, int *has_anchor);
 int ovp_feature_jacobian_full(ovp_ctx *ctx, int m, const int *clone_handles, const float *uv, const double *p_FinG,
                               const double *p_FinG_fej, int64_t planeid, const double *cp, const double *cp_fej, double sigma_px,
                               double sigma_c, double *H_f, int *hf_cols, double *H_x, int *hx_cols, double *res, int *rows_out,

@@ -1041,6 +1041,78 @@ struct Feature {
 
 struct UpdaterHelper {
 
+  // UpdaterHelper.cpp:35-193: d p_FinG / d lambda for the six landmark representations (enum order of
+  // ov_type::LandmarkRepresentation: GLOBAL_3D, GLOBAL_FULL_INVERSE_DEPTH, ANCHORED_3D, ANCHORED_FULL_INVERSE_DEPTH,
+  // ANCHORED_MSCKF_INVERSE_DEPTH, ANCHORED_INVERSE_DEPTH_SINGLE) and, for the anchored ones, the Jacobians w.r.t. the anchor
+  // clone (theta, p) and the camera extrinsics.  Plain-value interface: anchor pose / FEJ pose = [q_GtoI (JPL xyzw), p_IinG],
+  // calib = [q_ItoC, p_IinC].  Returns whether anchor Jacobians were produced.
+  static bool get_feature_jacobian_representation(int rep, bool do_fej, const Mat &p_FinG, const Mat &p_FinG_fej, const Mat &p_FinA_in,
+                                                  const Mat &anchor, const Mat &anchor_fej, const Mat &calib, Mat &H_f, Mat &H_anc,
+                                                  Mat &H_calib) {
+    auto spherical = [](const Mat &p) { // :46-72 / :118-140: d p / d (theta, phi, rho) at the spherical coordinates of p
+      double rho = 1.0 / p.norm();
+      double phi = std::acos(rho * p(2, 0)), th = std::atan2(p(1, 0), p(0, 0));
+      double st = std::sin(th), ct = std::cos(th), sp = std::sin(phi), cp = std::cos(phi);
+      Mat J(3, 3);
+      J(0, 0) = -(1.0 / rho) * st * sp;
+      J(0, 1) = (1.0 / rho) * ct * cp;
+      J(0, 2) = -(1.0 / (rho * rho)) * ct * sp;
+      J(1, 0) = (1.0 / rho) * ct * sp;
+      J(1, 1) = (1.0 / rho) * st * cp;
+      J(1, 2) = -(1.0 / (rho * rho)) * st * sp;
+      J(2, 0) = 0.0;
+      J(2, 1) = -(1.0 / rho) * sp;
+      J(2, 2) = -(1.0 / (rho * rho)) * cp;
+      return J;
+    };
+    if (rep == 0) { // GLOBAL_3D (:39-43)
+      H_f = Mat::Identity(3);
+      return false;
+    }
+    if (rep == 1) { // GLOBAL_FULL_INVERSE_DEPTH (:46-72)
+      H_f = spherical(do_fej ? p_FinG_fej : p_FinG);
+      return false;
+    }
+    Mat R_ItoC = quat_2_Rot(calib.block(0, 0, 4, 1)), p_IinC = calib.block(4, 0, 3, 1);
+    Mat R_GtoI = quat_2_Rot(anchor.block(0, 0, 4, 1)), p_IinG = anchor.block(4, 0, 3, 1);
+    Mat p_FinA = p_FinA_in;
+    if (do_fej) { // :88-96: best global point re-expressed in the FEJ anchor frame
+      Mat best = R_GtoI.T() * R_ItoC.T() * (p_FinA - p_IinC) + p_IinG;
+      R_GtoI = quat_2_Rot(anchor_fej.block(0, 0, 4, 1));
+      p_IinG = anchor_fej.block(4, 0, 3, 1);
+      p_FinA = (R_GtoI.T() * R_ItoC.T()).T() * (best - p_IinG) + p_IinC;
+    }
+    Mat R_CtoG = R_GtoI.T() * R_ItoC.T();
+    H_anc = Mat(3, 6); // :100-102
+    H_anc.setBlock(0, 0, (-1.0) * (R_GtoI.T() * skew_x(R_ItoC.T() * (p_FinA - p_IinC))));
+    H_anc.setBlock(0, 3, Mat::Identity(3));
+    H_calib = Mat(3, 6); // :109-115
+    H_calib.setBlock(0, 0, (-1.0) * (R_CtoG * skew_x(p_FinA - p_IinC)));
+    H_calib.setBlock(0, 3, (-1.0) * R_CtoG);
+    if (rep == 2) { // ANCHORED_3D (:118-121)
+      H_f = R_CtoG;
+    } else if (rep == 3) { // ANCHORED_FULL_INVERSE_DEPTH (:124-150)
+      H_f = R_CtoG * spherical(p_FinA);
+    } else if (rep == 4) { // ANCHORED_MSCKF_INVERSE_DEPTH (:153-172)
+      double alpha = p_FinA(0, 0) / p_FinA(2, 0), beta = p_FinA(1, 0) / p_FinA(2, 0), rho = 1.0 / p_FinA(2, 0);
+      Mat J(3, 3);
+      J(0, 0) = 1.0 / rho;
+      J(0, 2) = -(1.0 / (rho * rho)) * alpha;
+      J(1, 1) = 1.0 / rho;
+      J(1, 2) = -(1.0 / (rho * rho)) * beta;
+      J(2, 2) = -(1.0 / (rho * rho));
+      H_f = R_CtoG * J;
+    } else if (rep == 5) { // ANCHORED_INVERSE_DEPTH_SINGLE (:175-186)
+      double rho = 1.0 / p_FinA(2, 0);
+      Mat bearing = rho * p_FinA;
+      H_f = R_CtoG * ((-(1.0 / (rho * rho))) * bearing);
+    } else {
+      ref_exit("get_feature_jacobian_representation: invalid representation");
+    }
+    return true;
+  }
+
+
   // UpdaterHelper.cpp:195-513 (GLOBAL_3D: dpfg_dlambda = I, no anchor terms, :39-43)
   static void get_feature_jacobian_full(StateP state, const Feature &feature, double sigma_px, double sigma_c, Mat &H_f, Mat &H_x,
                                         Mat &res, std::vector<VarP> &x_order) {

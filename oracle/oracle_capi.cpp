@@ -305,6 +305,26 @@ void orc_plane_measurement_compress_inplace(double *H_x, int cols, double *H_cp,
 // ---- UpdaterHelper::get_feature_jacobian_full -----------------------------------------------------------------
 // clone_handles[m] identify the clone of each measurement.  Outputs are written col-major with ld = rows_out;
 // buffers must hold 3*m(+1) rows; x_order receives variable handles.
+int orc_feature_jacobian_representation(int rep, int do_fej, const double *p_FinG, const double *p_FinG_fej, const double *p_FinA,
+                                        const double *anchor7, const double *anchor_fej7, const double *calib7, double *H_f, int *hf_cols,
+                                        double *H_anc, double *H_calib, int *has_anchor) {
+  try {
+    Mat Hf, Ha, Hc;
+    bool anc = UpdaterHelper::get_feature_jacobian_representation(rep, do_fej != 0, from_colmajor(p_FinG, 3, 1), from_colmajor(p_FinG_fej, 3, 1),
+                                                                  from_colmajor(p_FinA, 3, 1), from_colmajor(anchor7, 7, 1),
+                                                                  from_colmajor(anchor_fej7, 7, 1), from_colmajor(calib7, 7, 1), Hf, Ha, Hc);
+    *hf_cols = Hf.cols();
+    std::memcpy(H_f, Hf.a.data(), sizeof(double) * 3 * Hf.cols());
+    *has_anchor = anc ? 1 : 0;
+    if (anc) {
+      std::memcpy(H_anc, Ha.a.data(), sizeof(double) * 18);
+      std::memcpy(H_calib, Hc.a.data(), sizeof(double) * 18);
+    }
+    return 0;
+  } catch (...) {
+    return 1;
+  }
+}
 int orc_feature_jacobian_full(void *p, int m, const int *clone_handles, const float *uv, const double *p_FinG, const double *p_FinG_fej,
                               long long planeid, const double *cp, const double *cp_fej, double sigma_px, double sigma_c, double *H_f,
                               int *hf_cols, double *H_x, int *hx_cols, double *res, int *rows_out, int *x_order, int *x_order_n) {

@@ -591,6 +591,75 @@ static int stage_feature_jacobian(Ctx *c, int m, const int *clone_handles, const
 } // namespace ovp
 extern "C" {
 
+// UpdaterHelper::get_feature_jacobian_representation (UpdaterHelper.cpp:35-193) as a context-free helper (3x3 host algebra, no
+// device work): d p_FinG / d lambda for the six ov_type landmark representations and, for the anchored ones, the Jacobians
+// w.r.t. the anchor clone and the camera extrinsics.  The fused device path itself runs GLOBAL_3D (every shipped config).
+int ovp_feature_jacobian_representation(int representation, int do_fej, const double *p_FinG, const double *p_FinG_fej, const double *p_FinA,
+                                        const double *anchor_pose7, const double *anchor_pose_fej7, const double *calib7, double *H_f,
+                                        int *hf_cols, double *H_anc, double *H_calib, int *has_anchor) {
+  using namespace ovp::hm;
+  if (representation < 0 || representation > 5 || !H_f || !hf_cols || !has_anchor)
+    return OVP_ERR_BAD_ARGS;
+  auto put3 = [](double *dst, int ldrows, int c0, const M3 &B) { // column-major 3 x n target
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+        dst[(size_t)(c0 + j) * ldrows + i] = B(i, j);
+  };
+  // d p / d (theta, phi, rho) of p = (1 / rho) [cos(theta) sin(phi), sin(theta) sin(phi), cos(phi)] evaluated at p
+  auto d_spherical = [](const V3 &p) {
+    const double r = std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    const double rho = 1.0 / r, phi = std::acos(rho * p[2]), th = std::atan2(p[1], p[0]);
+    const double st = std::sin(th), ct = std::cos(th), sp = std::sin(phi), cp = std::cos(phi), ir = 1.0 / rho, ir2 = 1.0 / (rho * rho);
+    return M3{{-ir * st * sp, ir * ct * cp, -ir2 * ct * sp, ir * ct * sp, ir * st * cp, -ir2 * st * sp, 0.0, -ir * sp, -ir2 * cp}};
+  };
+  *has_anchor = 0;
+  *hf_cols = 3;
+  if (representation == 0) {
+    put3(H_f, 3, 0, eye3());
+    return OVP_OK;
+  }
+  if (representation == 1) {
+    const double *p = do_fej ? p_FinG_fej : p_FinG;
+    put3(H_f, 3, 0, d_spherical(v3(p[0], p[1], p[2])));
+    return OVP_OK;
+  }
+  if (!p_FinA || !anchor_pose7 || !anchor_pose_fej7 || !calib7 || !H_anc || !H_calib)
+    return OVP_ERR_BAD_ARGS;
+  const M3 R_ItoC = quat_2_Rot(V4{{calib7[0], calib7[1], calib7[2], calib7[3]}});
+  const V3 p_IinC = v3(calib7[4], calib7[5], calib7[6]);
+  M3 R_GtoI = quat_2_Rot(V4{{anchor_pose7[0], anchor_pose7[1], anchor_pose7[2], anchor_pose7[3]}});
+  V3 p_IinG = v3(anchor_pose7[4], anchor_pose7[5], anchor_pose7[6]);
+  V3 pA = v3(p_FinA[0], p_FinA[1], p_FinA[2]);
+  if (do_fej) { // the best global estimate seen from the first-estimate anchor frame
+    const V3 best = transpose(R_GtoI) * (transpose(R_ItoC) * (pA - p_IinC)) + p_IinG;
+    R_GtoI = quat_2_Rot(V4{{anchor_pose_fej7[0], anchor_pose_fej7[1], anchor_pose_fej7[2], anchor_pose_fej7[3]}});
+    p_IinG = v3(anchor_pose_fej7[4], anchor_pose_fej7[5], anchor_pose_fej7[6]);
+    pA = R_ItoC * (R_GtoI * (best - p_IinG)) + p_IinC;
+  }
+  const M3 R_ItoG = transpose(R_GtoI), R_CtoG = R_ItoG * transpose(R_ItoC);
+  const V3 dA = pA - p_IinC;
+  put3(H_anc, 3, 0, (-1.0) * (R_ItoG * skew(transpose(R_ItoC) * dA)));
+  put3(H_anc, 3, 3, eye3());
+  put3(H_calib, 3, 0, (-1.0) * (R_CtoG * skew(dA)));
+  put3(H_calib, 3, 3, (-1.0) * R_CtoG);
+  *has_anchor = 1;
+  if (representation == 2) {
+    put3(H_f, 3, 0, R_CtoG);
+  } else if (representation == 3) {
+    put3(H_f, 3, 0, R_CtoG * d_spherical(pA));
+  } else if (representation == 4) { // lambda = (x/z, y/z, 1/z)
+    const double rho = 1.0 / pA[2], al = pA[0] / pA[2], be = pA[1] / pA[2], ir = 1.0 / rho, ir2 = 1.0 / (rho * rho);
+    put3(H_f, 3, 0, R_CtoG * M3{{ir, 0.0, -ir2 * al, 0.0, ir, -ir2 * be, 0.0, 0.0, -ir2}});
+  } else { // lambda = 1/z along the fixed initial bearing
+    const double rho = 1.0 / pA[2];
+    const V3 d = R_CtoG * ((-(1.0 / (rho * rho))) * (rho * pA));
+    for (int i = 0; i < 3; i++)
+      H_f[i] = d[i];
+    *hf_cols = 1;
+  }
+  return OVP_OK;
+}
+
 int ovp_feature_jacobian_full(ovp_ctx *h, int m, const int *clone_handles, const float *uv, const double *p_FinG, const double *p_FinG_fej,
                               int64_t planeid, const double *cp, const double *cp_fej, double sigma_px, double sigma_c, double *H_f,
                               int *hf_cols, double *H_x, int *hx_cols, double *res, int *rows_out, int *x_order, int *x_order_n) {

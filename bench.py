@@ -269,7 +269,9 @@ def main():
     h1, d1 = ctx.transfer_bytes()
     n_var_bytes = 0
     e2e_ms = max_over_ranks(1e3 * float(np.mean(e2e_t)))
-    e2e = {"value": world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+    sys.stderr.write("e2e per-step ms: %s\n" % " ".join("%.2f" % (1e3 * t) for t in e2e_t))
+    e2e = {"value": world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "ms_per_step_median": 1e3 * float(np.median(e2e_t)),
+           "ms_per_step_max": 1e3 * float(np.max(e2e_t)),
            "h2d_bytes_per_step": int((h1 - h0) / args.steps), "d2h_bytes_per_step": int((d1 - d0) / args.steps) + n_var_bytes}
 
     # ---- roofline of the dominant kernel: per-kernel CUDA events on the launch stream (separate pass, not the timed region) ----

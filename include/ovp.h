@@ -253,6 +253,10 @@ int ovp_set_profiling(ovp_ctx *ctx, int on);
 int ovp_profile_report(ovp_ctx *ctx, double *ms5, int64_t *count5, double *work5);
 /* 1 (default): the static launch sequence of a prepared batch is captured into a CUDA graph and replayed */
 int ovp_set_use_graphs(ovp_ctx *ctx, int on);
+/* Zero-pivot rule of the measurement compression (Cholesky of the stacked Gram matrix): a pivot <= tol * (the
+ * column's original diagonal entry) marks a rank-deficient (gauge) direction and is dropped.  Default 1e-11; the posterior is
+ * invariant over 1e-9 .. 1e-13 on every scenario in tests/ (tests/test_gpu_numerics.py). */
+int ovp_set_rank_tolerance(ovp_ctx *ctx, double tol);
 /* bytes this ctx copied host->device / device->host since creation */
 int ovp_transfer_bytes(ovp_ctx *ctx, int64_t *h2d, int64_t *d2h);
 /* measured FP64 tensor-core (DMMA) throughput of this device with the library's own GEMM kernel: returns TFLOP/s */

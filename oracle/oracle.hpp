@@ -589,6 +589,32 @@ struct OracleExit : std::runtime_error {
 // reference prints + std::exit(EXIT_FAILURE); the oracle throws so the tests can observe it
 [[noreturn]] inline void ref_exit(const char *what) { throw OracleExit(what); }
 
+// TEST INSTRUMENTATION, NOT PART OF THE REFERENCE.  UpdaterPlane::measurement_compress_inplace keeps the top n rows of the Givens
+// sweep over a stacked H_x that is exactly rank deficient on the plane paths (gauge directions); the n - rank kept
+// rows whose H part is round-off still carry arbitrary, round-off defined unit projections of the stacked residual.  They do not
+// move the posterior (zero Jacobian) but each adds its square to the plane chi2 the reference gates on, so that chi2 is not
+// reproducible by the reference itself under a different FMA contraction (tools/oracle_sensitivity.py).  The probe lets a test
+// split every gated chi2 into the well-defined part and that remainder: fn(rows, cols, H col-major, z) returns
+// |projection of z onto the left null space of H|^2 (the test supplies an SVD).  With gate_without set the gate is evaluated on
+// chi2 minus that remainder - the quantity the CUDA path computes; the default (fn == nullptr) is the unmodified reference.
+struct GaugeProbe {
+  double (*fn)(int rows, int cols, const double *H, const double *z) = nullptr;
+  bool gate_without = false;
+  std::vector<double> junk; // one entry per gated stacked system, in call order
+  double probe(const struct Mat &H, const struct Mat &z);
+};
+inline GaugeProbe &gauge_probe() {
+  static GaugeProbe g;
+  return g;
+}
+inline double GaugeProbe::probe(const Mat &H, const Mat &z) {
+  if (!fn)
+    return 0.0;
+  double j = fn(H.rows(), H.cols(), H.a.data(), z.a.data());
+  junk.push_back(j);
+  return gate_without ? j : 0.0;
+}
+
 // chi-squared 0.95 quantile: table injected by the test harness (scipy.stats.chi2.ppf; boost::math::quantile in
 // the reference, UpdaterMSCKF.cpp:59-62).  Index = dof.
 struct Chi2Table {
@@ -944,6 +970,7 @@ struct StateHelper {
       Mat y = resup;
       chol_solve_inplace(L, y);
       chi2 = dot(resup, y);
+      chi2 -= gauge_probe().probe(Hup, resup); // instrumentation only (see GaugeProbe); default: subtracts 0
     }
     double chi2_check = chi2tab.at(res.rows()); // dof = full r, not r-s (:471-472)
     if (chi2 > chi_2_mult * chi2_check)
@@ -1475,7 +1502,8 @@ struct UpdaterMSCKF {
         handles.push_back(v->handle);
       out.plane_Hx_order_handles.push_back(handles);
       out.plane_chi2.push_back(chi2);
-      if (chi2 > chi2_multipler * chi2_check) {
+      const double chi2_gate = chi2 - gauge_probe().probe(Hx_big, res_big); // instrumentation only (see GaugeProbe); default: chi2
+      if (chi2_gate > chi2_multipler * chi2_check) {
         out.plane_status.push_back({planeid, 0});
         continue;
       }

@@ -42,6 +42,21 @@ template <class F> int guarded(Ctx *c, F f) {
 
 extern "C" {
 
+// test instrumentation (oracle.hpp GaugeProbe): process-global, like the reference's single-threaded update path
+void orc_set_gauge_probe(double (*fn)(int, int, const double *, const double *), int gate_without) {
+  gauge_probe().fn = fn;
+  gauge_probe().gate_without = gate_without != 0;
+  gauge_probe().junk.clear();
+}
+int orc_gauge_probe_values(double *out, int cap) {
+  auto &j = gauge_probe().junk;
+  int n = (int)j.size();
+  for (int i = 0; i < n && i < cap; i++)
+    out[i] = j[i];
+  j.clear();
+  return n;
+}
+
 void *orc_create(int do_fej, int use_rk4, int imu_avg, int calib_pose, int calib_intr, int calib_dt, int max_clone_size,
                  double sigma_constraint, double const_init_multi, double const_init_chi2) {
   StateOptions o;

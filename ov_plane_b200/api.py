@@ -38,11 +38,15 @@ class UpdaterOptions(C.Structure):
     _fields_ = [("sigma_pix", C.c_double), ("chi2_multipler", C.c_double)]
 
 
-def load_library():
-    if not os.path.exists(LIB_PATH):
+DEBUG_LIB_PATH = os.path.join(_HERE, "lib", "libovp_debug.so")  # product sources + include/ovp_debug.h hooks (tools/, kernel unit tests)
+
+
+def load_library(path=None):
+    path = path or LIB_PATH
+    if not os.path.exists(path):
         raise ImportError("ov_plane_b200: %s is missing. Build the CUDA library first: "
-                          "python -c 'import __graft_entry__ as g; g.build()'  (no CPU fallback exists)" % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+                          "python -c 'import __graft_entry__ as g; g.build()'  (no CPU fallback exists)" % path)
+    lib = C.CDLL(path)
     lib.ovp_last_error.restype = C.c_char_p
     lib.ovp_status_string.restype = C.c_char_p
     lib.ovp_get_timestamp.restype = C.c_double
@@ -55,8 +59,15 @@ def load_library():
 _lib = None
 
 
-def lib():
-    global _lib
+_debug_lib = None
+
+
+def lib(debug=False):
+    global _lib, _debug_lib
+    if debug:
+        if _debug_lib is None:
+            _debug_lib = load_library(DEBUG_LIB_PATH)
+        return _debug_lib
     if _lib is None:
         _lib = load_library()
     return _lib
@@ -81,8 +92,8 @@ def _i32(a):
 class Context(object):
     """One device-resident filter state (the reference's `State` + `StateHelper` + `Propagator` seam)."""
 
-    def __init__(self, options, device=0, max_state=640, max_meas_rows=40000):
-        self.lib = lib()
+    def __init__(self, options, device=0, max_state=640, max_meas_rows=40000, debug=False):
+        self.lib = lib(debug)  # debug=True: libovp_debug.so (exports the include/ovp_debug.h hooks as well)
         self.opt = StateOptions(**{k: options[k] for k, _ in StateOptions._fields_})
         self.h = C.c_void_p()
         st = self.lib.ovp_create(C.byref(self.opt), int(device), int(max_state), int(max_meas_rows), C.byref(self.h))
@@ -445,6 +456,12 @@ class Context(object):
 
     def restore(self):
         self._ck(self.lib.ovp_restore(self.h))
+
+    def set_rank_tolerance(self, tol):
+        self._ck(self.lib.ovp_set_rank_tolerance(self.h, C.c_double(tol)))
+
+    def set_use_graphs(self, on):
+        self._ck(self.lib.ovp_set_use_graphs(self.h, int(on)))
 
     def set_profiling(self, on):
         self._ck(self.lib.ovp_set_profiling(self.h, int(on)))

@@ -180,18 +180,17 @@ __global__ void dmma_selftest_fill(double *p, size_t n, double scale) {
     p[i] = scale * (double)((i * 2654435761u) % 1024) / 1024.0;
 }
 
+// host <-> device staging buffer for small dense transfers: grows on demand.  Only the staging buffer itself is replaced
+// (after the stream has drained: kernels in flight may still read it); snapshots, profiling events and the prepared batch
+// belong to other owners and are released in ovp_destroy.
 static int ensure_stage(Ctx *c, size_t elems) {
   if (elems <= c->d_stage_elems)
     return OVP_OK;
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
   if (c->d_stage)
     cudaFree(c->d_stage);
-  cudaFree(c->snapP);
-  cudaFree(c->snap_val);
-  cudaFree(c->snap_fej);
-  free_prepared(c);
-  for (auto e : c->ev_pool)
-    cudaEventDestroy(e);
   c->d_stage = nullptr;
+  c->d_stage_elems = 0;
   size_t n = std::max<size_t>(elems * 2, 1 << 16);
   OVP_CUDA(cudaMalloc(&c->d_stage, n * sizeof(double)));
   c->d_stage_elems = n;
@@ -240,6 +239,7 @@ static int do_marginalize(Ctx *c, int h) {
       o.id -= ms;
   v.id = -1;
   v.alive = false;
+  c->free_handles.push_back(h);
   c->order.erase(std::remove(c->order.begin(), c->order.end(), h), c->order.end());
   c->N = N - ms;
   c->var_table_dirty = true;
@@ -301,7 +301,7 @@ int ovp_create(const ovp_state_options *opt, int device, int max_state, int max_
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev)
     return OVP_ERR_CUDA; // no CPU fallback: the path needs a CUDA device
   ovp_ctx *h = new ovp_ctx();
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   c->device = device;
   c->opt = *opt;
   *out = h;
@@ -313,7 +313,7 @@ int ovp_create(const ovp_state_options *opt, int device, int max_state, int max_
   c->ldP = c->Nmax;
   c->Rcap = c->Nmax + 64;
   c->max_meas_rows = std::max(max_meas_rows, 64);
-  c->max_handles = 8192;
+  c->max_handles = 8192; // live variables + reuse lag; slots are recycled (state_append_variable)
   OVP_CUDA(cudaMalloc(&c->dP, (size_t)c->ldP * c->Nmax * sizeof(double)));
   OVP_CUDA(cudaMemset(c->dP, 0, (size_t)c->ldP * c->Nmax * sizeof(double)));
   OVP_CUDA(cudaMalloc(&c->d_val, (size_t)c->max_handles * OVP_VAL_STRIDE * sizeof(double)));
@@ -331,6 +331,8 @@ int ovp_create(const ovp_state_options *opt, int device, int max_state, int max_
     return st;
   c->cf_maxT = c->Rcap / 64 + 1;
   OVP_CUDA(cudaMalloc(&c->cf_linv, (size_t)c->cf_maxT * 4096 * sizeof(double)));
+  // exchange slots of the fused Cholesky (cholfused.cu): T*T panel tiles + 2T hand-off tiles, 64 x 68 doubles each
+  OVP_CUDA(cudaMalloc(&c->cf_xch, ((size_t)c->cf_maxT * c->cf_maxT + 2 * c->cf_maxT) * 64 * 68 * sizeof(double)));
   OVP_CUDA(cudaMalloc(&c->cf_diag0, (size_t)c->cf_maxT * 64 * sizeof(double)));
   OVP_CUDA(cudaMemset(c->cf_diag0, 0, (size_t)c->cf_maxT * 64 * sizeof(double)));
   OVP_CUDA(cudaMalloc(&c->cf_flags, (size_t)(3 * c->cf_maxT + c->cf_maxT * c->cf_maxT) * sizeof(int)));
@@ -439,7 +441,7 @@ int ovp_create(const ovp_state_options *opt, int device, int max_state, int max_
 void ovp_destroy(ovp_ctx *h) {
   if (!h)
     return;
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   cudaSetDevice(c->device);
   if (c->stream)
     cudaStreamSynchronize(c->stream);
@@ -450,6 +452,7 @@ void ovp_destroy(ovp_ctx *h) {
   cudaFree(c->d_var_size);
   cudaFree(c->d_var_kind);
   cudaFree(c->cf_linv);
+  cudaFree(c->cf_xch);
   cudaFree(c->cf_diag0);
   cudaFree(c->cf_flags);
   cudaFree(c->cf_ctrl);
@@ -467,6 +470,15 @@ void ovp_destroy(ovp_ctx *h) {
   cudaFree(c->d_chi2_table);
   cudaFree(c->d_batch);
   cudaFree(c->d_stage);
+  cudaFree(c->snapP);
+  cudaFree(c->snap_val);
+  cudaFree(c->snap_fej);
+  c->snapP = c->snap_val = c->snap_fej = nullptr;
+  free_prepared(c);
+  for (auto e : c->ev_pool)
+    cudaEventDestroy(e);
+  c->ev_pool.clear();
+  c->ev_used = 0;
   if (c->h_pinned)
     cudaFreeHost(c->h_pinned);
   for (int i = 0; i < 8; i++)
@@ -479,12 +491,17 @@ void ovp_destroy(ovp_ctx *h) {
 const char *ovp_last_error(ovp_ctx *h) { return h ? h->c.last_error.c_str() : "null ctx"; }
 
 int ovp_set_chi2_table(ovp_ctx *h, const double *q, int n) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (!q || n < 2)
     return fail(c, OVP_ERR_BAD_ARGS, "chi2 table needs >= 2 entries");
+  OVP_CUDA(cudaSetDevice(c->device));
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
+  // a prepared batch (and its captured graph) holds the old table pointer and host-side thresholds by value: drop it
+  free_prepared(c);
   c->chi2_table.assign(q, q + n);
   if (c->d_chi2_table)
     cudaFree(c->d_chi2_table);
+  c->d_chi2_table = nullptr;
   OVP_CUDA(cudaMalloc(&c->d_chi2_table, n * sizeof(double)));
   OVP_CUDA(cudaMemcpy(c->d_chi2_table, q, n * sizeof(double), cudaMemcpyHostToDevice));
   c->chi2_table_n = n;
@@ -493,7 +510,7 @@ int ovp_set_chi2_table(ovp_ctx *h, const double *q, int n) {
 
 int ovp_cov_rows(ovp_ctx *h) { return h->c.N; }
 int ovp_cov_download(ovp_ctx *h, double *out, int ld) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (ld < c->N)
     return fail(c, OVP_ERR_BAD_ARGS, "ld < rows");
   OVP_CUDA(cudaMemcpy2DAsync(out, (size_t)ld * sizeof(double), c->dP, (size_t)c->ldP * sizeof(double), (size_t)c->N * sizeof(double), c->N,
@@ -502,7 +519,7 @@ int ovp_cov_download(ovp_ctx *h, double *out, int ld) {
   return OVP_OK;
 }
 int ovp_cov_upload(ovp_ctx *h, const double *in, int n, int ld) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (n != c->N || ld < n)
     return fail(c, OVP_ERR_BAD_ARGS, "cov_upload: n=%d but the state has %d rows", n, c->N);
   OVP_CUDA(cudaMemcpy2DAsync(c->dP, (size_t)c->ldP * sizeof(double), in, (size_t)ld * sizeof(double), (size_t)n * sizeof(double), n,
@@ -518,7 +535,7 @@ int ovp_var_id(ovp_ctx *h, int v) { return valid_handle(&h->c, v) ? h->c.vars[v]
 int ovp_var_size(ovp_ctx *h, int v) { return (v >= 0 && v < (int)h->c.vars.size()) ? h->c.vars[v].size : -1; }
 int ovp_var_value_size(ovp_ctx *h, int v) { return (v >= 0 && v < (int)h->c.vars.size()) ? h->c.vars[v].nvalue : -1; }
 int ovp_var_set(ovp_ctx *h, int v, const double *value, const double *fej) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (v < 0 || v >= (int)c->vars.size())
     return fail(c, OVP_ERR_BAD_ARGS, "invalid handle %d", v);
   int st = sync_host_values(c);
@@ -533,7 +550,7 @@ int ovp_var_set(ovp_ctx *h, int v, const double *value, const double *fej) {
   return push_host_values(c, v);
 }
 int ovp_var_get(ovp_ctx *h, int v, double *value, double *fej) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (v < 0 || v >= (int)c->vars.size())
     return fail(c, OVP_ERR_BAD_ARGS, "invalid handle %d", v);
   int st = sync_host_values(c);
@@ -582,7 +599,7 @@ static int add_raw(Ctx *c, Var v, const double *value, const double *fej, int *h
   return OVP_OK;
 }
 int ovp_add_clone_raw(ovp_ctx *h, double timestamp, const double *value7, const double *fej7, int *handle) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (c->clones.count(timestamp))
     return fail(c, OVP_ERR_TIME, "clone at this timestamp already exists");
   Var v;
@@ -596,7 +613,7 @@ int ovp_add_clone_raw(ovp_ctx *h, double timestamp, const double *value7, const 
   return OVP_OK;
 }
 int ovp_add_plane_raw(ovp_ctx *h, int64_t planeid, const double *cp, const double *cp_fej, int *handle) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (c->planes.count(planeid))
     return fail(c, OVP_ERR_ALREADY_IN_STATE, "plane already in the state");
   Var v;
@@ -611,7 +628,7 @@ int ovp_add_plane_raw(ovp_ctx *h, int64_t planeid, const double *cp, const doubl
   return OVP_OK;
 }
 int ovp_add_slam_raw(ovp_ctx *h, int64_t featid, const double *p, const double *p_fej, int *handle) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (c->slam.count(featid))
     return fail(c, OVP_ERR_ALREADY_IN_STATE, "landmark already in the state");
   Var v;
@@ -628,7 +645,7 @@ int ovp_add_slam_raw(ovp_ctx *h, int64_t featid, const double *p, const double *
 
 // ---- StateHelper -----------------------------------------------------------------------------------------------------
 int ovp_get_marginal_covariance(ovp_ctx *h, const int *handles, int k, double *out) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   int n = 0;
   int st = upload_cols(c, handles, k, 0, &n);
   if (st)
@@ -645,7 +662,7 @@ int ovp_get_marginal_covariance(ovp_ctx *h, const int *handles, int k, double *o
   return OVP_OK;
 }
 int ovp_set_initial_covariance(ovp_ctx *h, const double *cov, int n_in, const int *handles, int k) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   int n = 0;
   int st = upload_cols(c, handles, k, 0, &n);
   if (st)
@@ -666,7 +683,7 @@ int ovp_set_initial_covariance(ovp_ctx *h, const double *cov, int n_in, const in
 
 int ovp_ekf_propagation(ovp_ctx *h, const int *new_h, int kn, const int *old_h, int ko, const double *Phi, int phi_rows, int phi_cols,
                         const double *Q) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (kn <= 0 || ko <= 0)
     return fail(c, OVP_ERR_BAD_ARGS, "EKFPropagation called with empty variable arrays (reference: std::exit, StateHelper.cpp:46-49)");
   for (int i = 0; i < kn; i++)

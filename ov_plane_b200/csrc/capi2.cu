@@ -171,7 +171,7 @@ static int stage_init_system(Ctx *c, const double *H_R, const double *H_L, const
 extern "C" {
 
 int ovp_ekf_update(ovp_ctx *h, const int *handles, int k, const double *H, int rows, const double *res, const double *Rdiag) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   int n = 0;
   int st = upload_cols(c, handles, k, 0, &n);
   if (st)
@@ -197,7 +197,7 @@ int ovp_ekf_update(ovp_ctx *h, const int *handles, int k, const double *H, int r
 int ovp_marginalize(ovp_ctx *h, int handle) { return do_marginalize(&h->c, handle); }
 
 int ovp_clone(ovp_ctx *h, int handle, int *new_handle) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (!valid_handle(c, handle) || c->vars[handle].id < 0)
     return fail(c, OVP_ERR_NOT_IN_STATE, "clone: variable %d not in the state (StateHelper.cpp:387-391)", handle);
   int st = sync_host_values(c);
@@ -227,7 +227,7 @@ int ovp_clone(ovp_ctx *h, int handle, int *new_handle) {
 }
 
 int ovp_augment_clone(ovp_ctx *h, double timestamp, const double last_w[3], int *new_handle) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (c->clones.count(timestamp))
     return fail(c, OVP_ERR_TIME, "augment_clone: a clone at this timestamp exists (StateHelper.cpp:591-594)");
   c->timestamp = timestamp;
@@ -253,7 +253,7 @@ int ovp_augment_clone(ovp_ctx *h, double timestamp, const double last_w[3], int 
 }
 
 int ovp_marginalize_old_clone(ovp_ctx *h) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if ((int)c->clones.size() > c->opt.max_clone_size) {
     int hh = c->clones.begin()->second; // State::margtimestep(): the oldest clone
     return do_marginalize(c, hh);
@@ -262,7 +262,7 @@ int ovp_marginalize_old_clone(ovp_ctx *h) {
 }
 
 int ovp_marginalize_slam(ovp_ctx *h) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   std::vector<int> todo;
   for (auto &kv : c->slam)
     if (c->vars[kv.second].should_marg && (int)kv.first > 4 * c->opt.max_aruco_features)
@@ -277,7 +277,7 @@ int ovp_marginalize_slam(ovp_ctx *h) {
 
 int ovp_initialize_invertible(ovp_ctx *h, int kind, int s, const double *value, const double *fej, int64_t tag, const int *handles, int k,
                               const double *H_R, const double *H_L, const double *res, double sigma2, int *new_handle) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (s < 1 || s > 3)
     return fail(c, OVP_ERR_BAD_ARGS, "initialize_invertible: new variable size %d not in 1..3", s);
   if ((kind == OVP_KIND_LANDMARK && c->slam.count(tag)) || (kind == OVP_KIND_VEC && c->planes.count(tag)))
@@ -326,7 +326,7 @@ int initialize_core(Ctx *c, int kind, int s, const double *value, const double *
   int st = check_status_flags(c);
   if (st)
     return st;
-  if (chi2 > chi2_mult * c->chi2_table[dof_rows])
+  if (chi2 > chi2_mult * chi2_q95(c, dof_rows))
     return OVP_OK; // accepted = 0, state untouched
   st = init_invertible_core(c, kind, s, value, fej, tag, d_cols, n, W, ldW, sigma2, new_handle);
   if (st)
@@ -347,7 +347,7 @@ extern "C" {
 int ovp_initialize(ovp_ctx *h, int kind, int s, const double *value, const double *fej, int64_t tag, const int *handles, int k,
                    const double *H_R, const double *H_L, const double *res, int rows, double sigma2, double chi2_mult, int do_update,
                    int *accepted, int *new_handle) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   *accepted = 0;
   *new_handle = -1;
   if (s < 1 || s > 3 || rows < s)
@@ -371,7 +371,7 @@ int ovp_initialize(ovp_ctx *h, int kind, int s, const double *value, const doubl
 // StateHelper::initialize(plane Vec(3), ..., const_init_chi2) (:436-446).  plane_status[i]: 1 initialised, 0 chi2-rejected,
 // -1 not attempted; new_handles[i]: handle of the new plane variable or -1.
 int ovp_plane_init(ovp_ctx *h, const ovp_feature_batch *batch, const ovp_updater_options *opt, int *plane_status, int *new_handles) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (!batch || !opt || !batch->plane_cp)
     return fail(c, OVP_ERR_BAD_ARGS, "plane_init: null batch / options / plane_cp");
   std::vector<std::pair<int64_t, int>> ps;
@@ -396,9 +396,10 @@ int ovp_plane_init(ovp_ctx *h, const ovp_feature_batch *batch, const ovp_updater
     int st = msckf_prepare(c, batch, opt, &ex);
     if (st)
       return st;
+    const bool graphs_before = c->use_graphs;
     c->use_graphs = false; // one-shot system
     st = msckf_launch(c);
-    c->use_graphs = true;
+    c->use_graphs = graphs_before; // ovp_set_use_graphs(0) must survive this call
     if (st)
       return st;
     int rowsW, ncx, rows_ref;
@@ -421,7 +422,7 @@ int ovp_plane_init(ovp_ctx *h, const ovp_feature_batch *batch, const ovp_updater
 
 int ovp_merge_planes_and_marginalize(ovp_ctx *h, const int64_t *f2p_feat, const int64_t *f2p_plane, int nf, const int64_t *merge_new,
                                      const int64_t *merge_old, int nm) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   (void)f2p_feat;
   if (c->planes.empty())
     return OVP_OK;
@@ -495,7 +496,7 @@ int ovp_merge_planes_and_marginalize(ovp_ctx *h, const int64_t *f2p_feat, const 
     for (int i = 0; i < 3; i++)
       for (int j = 0; j < 3; j++)
         chi2 += res[i] * Sinv[j * 3 + i] * res[j];
-    double chi2_check = c->opt.plane_merge_chi2 * c->chi2_table[3];
+    double chi2_check = c->opt.plane_merge_chi2 * chi2_q95(c, 3);
     if (chi2 < chi2_check && norm_angle < c->opt.plane_merge_deg_max) {
       st = ovp_ekf_update(h, hs, 2, H, 3, res, nullptr);
       if (st)
@@ -663,7 +664,7 @@ int ovp_feature_jacobian_representation(int representation, int do_fej, const do
 int ovp_feature_jacobian_full(ovp_ctx *h, int m, const int *clone_handles, const float *uv, const double *p_FinG, const double *p_FinG_fej,
                               int64_t planeid, const double *cp, const double *cp_fej, double sigma_px, double sigma_c, double *H_f,
                               int *hf_cols, double *H_x, int *hx_cols, double *res, int *rows_out, int *x_order, int *x_order_n) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   const bool has_plane = planeid != 0;
   const bool in_state = has_plane && c->planes.count(planeid);
   int rows, hfc, hxc;
@@ -751,7 +752,7 @@ static int compress_common(Ctx *c, double *H_x, int cols, double *H_cp, double *
   int st = gram_of_stacked(c, rows, nc1, ld);
   if (st)
     return st;
-  st = chol_partial(c, c->wsG.S, c->wsG.cap, nc1, cols, 1e-11);
+  st = chol_partial(c, c->wsG.S, c->wsG.cap, nc1, cols, c->gram_tol);
   if (st)
     return st;
   // R = L[0:cols,0:cols]^T ; carried columns = L[cols.., 0:cols]^T
@@ -782,7 +783,7 @@ int ovp_plane_measurement_compress_inplace(ovp_ctx *h, double *H_x, int cols, do
 // ---- UpdaterMSCKF ------------------------------------------------------------------------------------------------------
 int ovp_msckf_update(ovp_ctx *h, const ovp_feature_batch *batch, const ovp_updater_options *opt, int *feat_status, double *feat_chi2,
                      int *plane_status, double *plane_chi2, int *hx_order, int *hx_order_n) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (!batch || !opt)
     return fail(c, OVP_ERR_BAD_ARGS, "null batch / options");
   return msckf_update_impl(c, batch, opt, feat_status, feat_chi2, plane_status, plane_chi2, hx_order, hx_order_n, nullptr);
@@ -817,7 +818,7 @@ int ovp_msckf_shard_columns(ovp_ctx *h, const int *all_clone_handles, int n_clon
 }
 int ovp_msckf_shard_compress(ovp_ctx *h, const ovp_feature_batch *batch, const ovp_updater_options *opt, const int *all_clone_handles,
                              int n_clones, double *d_out, int *feat_status, double *feat_chi2) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   std::vector<int> cols;
   int st = shard_cols(c, all_clone_handles, n_clones, cols);
   if (st)
@@ -834,7 +835,7 @@ int ovp_msckf_shard_compress(ovp_ctx *h, const ovp_feature_batch *batch, const o
   return msckf_update_impl(c, batch, opt, feat_status, feat_chi2, nullptr, nullptr, nullptr, nullptr, &ex);
 }
 int ovp_msckf_update_gathered(ovp_ctx *h, const double *d_blocks, int G, const int *all_clone_handles, int n_clones) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   std::vector<int> cols;
   int st = shard_cols(c, all_clone_handles, n_clones, cols);
   if (st)
@@ -851,7 +852,7 @@ int ovp_msckf_update_gathered(ovp_ctx *h, const double *d_blocks, int G, const i
   st = gram_of_stacked(c, rows, nc1, ld);
   if (st)
     return st;
-  st = chol_partial(c, c->wsG.S, c->wsG.cap, nc1, n, 1e-11);
+  st = chol_partial(c, c->wsG.S, c->wsG.cap, nc1, n, c->gram_tol);
   if (st)
     return st;
   st = ekf_update_core(c, c->dcols, n, mv(c->wsG.S, c->wsG.cap), n, c->wsG.S + (nc1 - 1), nullptr, -1.0, nullptr, nullptr, true, c->wsG.cap);
@@ -862,7 +863,7 @@ int ovp_msckf_update_gathered(ovp_ctx *h, const double *d_blocks, int G, const i
 
 // ---- Propagator ----------------------------------------------------------------------------------------------------------
 int ovp_propagator_set_noise(ovp_ctx *h, double sigma_w, double sigma_wb, double sigma_a, double sigma_ab, double gravity_mag) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   c->sigma_w = sigma_w;
   c->sigma_wb = sigma_wb;
   c->sigma_a = sigma_a;
@@ -1024,7 +1025,7 @@ extern "C" {
 // (column-major) over [theta p v_local w].  *ok = 0 when fewer than two IMU samples cover the interval (:147-148).
 int ovp_fast_state_propagate(ovp_ctx *h, double timestamp, double *state_plus13, double *cov144, int *ok) {
   using namespace ovp::hm;
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   *ok = 0;
   int st = sync_host_values(c);
   if (st)
@@ -1131,7 +1132,7 @@ int ovp_fast_state_propagate(ovp_ctx *h, double timestamp, double *state_plus13,
 
 int ovp_propagate_and_clone(ovp_ctx *h, double timestamp, double *Phi15, double *Q15, int *new_handle) {
   using namespace ovp::hm;
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (c->timestamp == timestamp)
     return fail(c, OVP_ERR_TIME, "propagate_and_clone: same timestep as the last update (Propagator.cpp:41-44)");
   if (c->timestamp > timestamp)
@@ -1322,12 +1323,12 @@ int ovp_last_timing(ovp_ctx *h, double *ms4) {
   return OVP_OK;
 }
 int ovp_synchronize(ovp_ctx *h) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   OVP_CUDA(cudaStreamSynchronize(c->stream));
   return OVP_OK;
 }
 int ovp_selftest_dgemm_tflops(ovp_ctx *h, int n, int iters, double *tflops) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (n < 64 || iters < 1)
     return fail(c, OVP_ERR_BAD_ARGS, "selftest: bad sizes");
   double *A, *B, *C;
@@ -1360,7 +1361,7 @@ int ovp_selftest_dgemm_tflops(ovp_ctx *h, int n, int iters, double *tflops) {
 extern "C" {
 
 int ovp_msckf_prepare(ovp_ctx *h, const ovp_feature_batch *batch, const ovp_updater_options *opt) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (!batch || !opt)
     return fail(c, OVP_ERR_BAD_ARGS, "null batch / options");
   return msckf_prepare(c, batch, opt, nullptr);
@@ -1373,7 +1374,7 @@ int ovp_msckf_finish(ovp_ctx *h, int *feat_status, double *feat_chi2, int *plane
 }
 
 int ovp_snapshot(ovp_ctx *h) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   size_t pe = (size_t)c->ldP * c->Nmax, ve = (size_t)c->max_handles * OVP_VAL_STRIDE;
   if (!c->snapP) {
     OVP_CUDA(cudaMalloc(&c->snapP, pe * sizeof(double)));
@@ -1387,7 +1388,7 @@ int ovp_snapshot(ovp_ctx *h) {
   return OVP_OK;
 }
 int ovp_restore(ovp_ctx *h) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (c->snapN != c->N)
     return fail(c, OVP_ERR_BAD_ARGS, "restore: no snapshot of a %d-row state", c->N);
   OVP_CUDA(cudaMemcpyAsync(c->dP, c->snapP, (size_t)c->ldP * c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -1399,7 +1400,7 @@ int ovp_restore(ovp_ctx *h) {
 }
 
 int ovp_set_profiling(ovp_ctx *h, int on) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   cudaStreamSynchronize(c->stream);
   c->profiling = on != 0;
   c->prof_recs.clear();
@@ -1409,7 +1410,7 @@ int ovp_set_profiling(ovp_ctx *h, int on) {
 }
 // per kernel class [gemm, gram, potrf, feature, other]: total ms, launch count, algorithmic work (flops or bytes)
 int ovp_profile_report(ovp_ctx *h, double *ms, int64_t *count, double *work) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   OVP_CUDA(cudaStreamSynchronize(c->stream));
   for (int i = 0; i < PROF_N; i++) {
     ms[i] = 0;
@@ -1431,6 +1432,15 @@ int ovp_set_use_graphs(ovp_ctx *h, int on) {
   h->c.use_graphs = on != 0;
   return OVP_OK;
 }
+int ovp_set_rank_tolerance(ovp_ctx *h, double tol) {
+  Ctx *c = ovp::enter(h);
+  if (!(tol > 0.0 && tol < 1e-3))
+    return fail(c, OVP_ERR_BAD_ARGS, "rank tolerance %g outside (0, 1e-3)", tol);
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
+  free_prepared(c); // the captured graph holds the tolerance by value
+  c->gram_tol = tol;
+  return OVP_OK;
+}
 int ovp_transfer_bytes(ovp_ctx *h, int64_t *h2d, int64_t *d2h) {
   *h2d = h->c.h2d_bytes;
   *d2h = h->c.d2h_bytes;
@@ -1439,118 +1449,7 @@ int ovp_transfer_bytes(ovp_ctx *h, int64_t *h2d, int64_t *d2h) {
 
 } // extern "C"
 
-// ---- micro-benchmarks of single kernels (tools/microbench.py) ------------------------------------------------------------
-namespace ovp {
-// dependent-chain latencies of fp64 operations on this GPU (cycles per op), one warp
-__global__ void fp64_latency_kernel(double *out, double seed) {
-  double x = seed + threadIdx.x * 1e-9;
-  long long t0, t1;
-  const int N = 256;
-  t0 = clock64();
-#pragma unroll 16
-  for (int i = 0; i < N; i++)
-    x = fma(x, 1.0000001, 1e-9);
-  t1 = clock64();
-  if (threadIdx.x == 0)
-    out[0] = (double)(t1 - t0) / N;
-  double y = x;
-  t0 = clock64();
-#pragma unroll 4
-  for (int i = 0; i < N; i++)
-    y = rsqrt(y) + 1.5;
-  t1 = clock64();
-  if (threadIdx.x == 0)
-    out[1] = (double)(t1 - t0) / N;
-  double z = y;
-  t0 = clock64();
-#pragma unroll 4
-  for (int i = 0; i < N; i++)
-    z = 1.0 / z + 1.5;
-  t1 = clock64();
-  if (threadIdx.x == 0)
-    out[2] = (double)(t1 - t0) / N;
-  double w = z;
-  t0 = clock64();
-#pragma unroll 4
-  for (int i = 0; i < N; i++)
-    w = sqrt(w) + 1.5;
-  t1 = clock64();
-  if (threadIdx.x == 0)
-    out[3] = (double)(t1 - t0) / N;
-  // shuffle of a double, dependent
-  double s = w;
-  t0 = clock64();
-#pragma unroll 16
-  for (int i = 0; i < N; i++)
-    s = __shfl_sync(0xffffffffu, s, (threadIdx.x + 1) & 31);
-  t1 = clock64();
-  if (threadIdx.x == 0)
-    out[4] = (double)(t1 - t0) / N;
-  // shared-memory dependent load chain
-  __shared__ double sh[64];
-  sh[threadIdx.x] = (double)((threadIdx.x * 7 + 3) & 31);
-  __syncwarp();
-  int idx = threadIdx.x;
-  t0 = clock64();
-#pragma unroll 16
-  for (int i = 0; i < N; i++)
-    idx = (int)sh[idx];
-  t1 = clock64();
-  if (threadIdx.x == 0)
-    out[5] = (double)(t1 - t0) / N;
-  // float rsqrt + 2 Newton steps in fp64 (candidate fast path)
-  double q = s + 2.0 + idx;
-  t0 = clock64();
-#pragma unroll 4
-  for (int i = 0; i < N; i++) {
-    double y0 = (double)rsqrtf((float)q);
-    y0 = y0 * fma(-0.5 * q * y0, y0, 1.5);
-    y0 = y0 * fma(-0.5 * q * y0, y0, 1.5);
-    q = y0 + 1.5;
-  }
-  t1 = clock64();
-  if (threadIdx.x == 0) {
-    out[6] = (double)(t1 - t0) / N;
-    out[7] = x + y + z + w + s + q;
-  }
-  // DMMA m8n8k4: dependent chain (latency) and 8 independent accumulators (issue rate of one warp)
-  double c0 = 0.0, c1 = 0.0, aa = 1.0 + 1e-9 * threadIdx.x, bb = 1.0 - 1e-9 * threadIdx.x;
-  t0 = clock64();
-#pragma unroll 16
-  for (int i = 0; i < N; i++)
-    dmma_m8n8k4(c0, c1, aa, bb);
-  t1 = clock64();
-  if (threadIdx.x == 0)
-    out[8] = (double)(t1 - t0) / N;
-  double e[8][2];
-#pragma unroll
-  for (int k = 0; k < 8; k++)
-    e[k][0] = e[k][1] = 0.0;
-  t0 = clock64();
-#pragma unroll 4
-  for (int i = 0; i < N / 8; i++)
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-      dmma_m8n8k4(e[k][0], e[k][1], aa, bb);
-  t1 = clock64();
-  double sum = c0 + c1;
-#pragma unroll
-  for (int k = 0; k < 8; k++)
-    sum += e[k][0] + e[k][1];
-  if (threadIdx.x == 0) {
-    out[9] = (double)(t1 - t0) / N;
-    out[10] = sum;
-  }
-}
-} // namespace ovp
-extern "C" int ovp_debug_fp64_latency(ovp_ctx *h, double *out8) {
-  Ctx *c = &h->c;
-  fp64_latency_kernel<<<1, 32, 0, c->stream>>>(c->dscal + 160, 1.2345);
-  OVP_CUDA(cudaStreamSynchronize(c->stream));
-  OVP_CUDA(cudaMemcpy(out8, c->dscal + 160, 10 * sizeof(double), cudaMemcpyDeviceToHost));
-  return OVP_OK;
-}
-
+// ---- UpdaterSLAM entry points (slam_host.inc) ----------------------------------------------------------------------------
 namespace ovp {
 int slam_update_impl(Ctx *c, int F, const int *meas_offset, const int *meas_clone, const float *uv, const int64_t *featid,
                      const int64_t *planeid, const ovp_updater_options *opt, int use_plane, int *feat_status, double *feat_chi2);
@@ -1630,11 +1529,10 @@ static int slam_delayed_init_impl(Ctx *c, int F, const int *meas_offset, const i
   return OVP_OK;
 }
 } // namespace ovp
-
 extern "C" {
 int ovp_slam_update(ovp_ctx *h, int F, const int *meas_offset, const int *meas_clone, const float *uv, const int64_t *featid,
                     const int64_t *planeid, const ovp_updater_options *opt, int use_plane_constraint, int *feat_status, double *feat_chi2) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (F > 0 && (!meas_offset || !meas_clone || !uv || !featid || !opt))
     return fail(c, OVP_ERR_BAD_ARGS, "slam_update: null argument");
   return slam_update_impl(c, F, meas_offset, meas_clone, uv, featid, planeid, opt, use_plane_constraint, feat_status, feat_chi2);
@@ -1642,7 +1540,7 @@ int ovp_slam_update(ovp_ctx *h, int F, const int *meas_offset, const int *meas_c
 int ovp_slam_delayed_init(ovp_ctx *h, int F, const int *meas_offset, const int *meas_clone, const float *uv, const double *p_FinG,
                           const double *p_FinG_original, const int64_t *featid, const int64_t *planeid, const ovp_updater_options *opt,
                           int use_plane_constraint, int *feat_status, int *new_handles) {
-  Ctx *c = &h->c;
+  Ctx *c = ovp::enter(h);
   if (F > 0 && (!meas_offset || !meas_clone || !uv || !featid || !opt || !p_FinG || !feat_status || !new_handles))
     return fail(c, OVP_ERR_BAD_ARGS, "slam_delayed_init: null argument");
   return slam_delayed_init_impl(c, F, meas_offset, meas_clone, uv, p_FinG, p_FinG_original, featid, planeid, opt, use_plane_constraint,
@@ -1662,113 +1560,3 @@ int64_t ovp_slam_plane_of(ovp_ctx *h, int64_t featid) { /* State::_features_SLAM
 }
 }
 
-namespace ovp {
-__global__ void spd_fill_kernel(double *A, int ld, int n) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * n)
-    return;
-  int i = idx % n, j = idx / n;
-  double v = (i == j) ? 4.0 + 0.001 * i : 0.3 / (1.0 + abs(i - j)) + 0.01 * ((i * 7 + j * 3) % 5);
-  if (i < j)
-    v = 0.0;
-  else if (i != j)
-    v = 0.3 / (1.0 + (i - j)) * 0.1 + 0.001 * (((i + j) * 7) % 5);
-  A[(size_t)j * ld + i] = v;
-}
-} // namespace ovp
-// microbenchmark of the fused Cholesky on a synthetic SPD n x n system (+ optional mrows x n right-hand side):
-// out[0] = us per (fill + factor), out[1] = us per fill alone, out[2..] = globaltimer stamps (ns, relative to the earliest) of the
-// last run, 16 per CTA
-extern "C" int ovp_debug_chol_fused(ovp_ctx *h, int n, int mrows, int iters, double *out, int out_cap) {
-  Ctx *c = &h->c;
-  if (n > c->wsS.cap || mrows > c->Nmax)
-    return fail(c, OVP_ERR_CAPACITY, "debug_chol_fused: too large");
-  const int T = (n + 63) / 64;
-  const int ncta = T * (T + 1) / 2 + (mrows ? (mrows + 1 + 15) / 16 : 0);
-  long long *dbg = nullptr;
-  OVP_CUDA(cudaMalloc(&dbg, ((size_t)ncta * 16 + 64) * sizeof(long long)));
-  OVP_CUDA(cudaMemset(dbg, 0, ((size_t)ncta * 16 + 64) * sizeof(long long)));
-  float ms;
-  for (int variant = 0; variant < 2; variant++) {
-    for (int rep = 0; rep < 2; rep++) {
-      if (rep == 1)
-        cudaEventRecord(c->ev[4], c->stream);
-      for (int it = 0; it < iters; it++) {
-        spd_fill_kernel<<<(n * n + 255) / 256, 256, 0, c->stream>>>(c->wsS.S, c->wsS.cap, n);
-        if (variant == 0) {
-          int st = chol_fused(c, c->wsS.S, c->wsS.cap, n, n, 0.0, mrows ? c->dM : nullptr, c->Nmax, mrows, mrows ? c->dvec + c->Rcap : nullptr, 1,
-                              c->dY, c->Nmax, c->dvec, -1.0, nullptr, nullptr, dbg);
-          if (st)
-            return st;
-        }
-      }
-      if (rep == 1)
-        cudaEventRecord(c->ev[5], c->stream);
-      OVP_CUDA(cudaStreamSynchronize(c->stream));
-    }
-    cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
-    out[variant] = 1e3 * ms / iters;
-  }
-  std::vector<long long> ts((size_t)ncta * 16 + 64);
-  OVP_CUDA(cudaMemcpy(ts.data(), dbg, ts.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-  cudaFree(dbg);
-  long long t0 = LLONG_MAX;
-  const size_t nper = (size_t)ncta * 16;
-  for (size_t i = 0; i < nper; i++)
-    if (ts[i] > 0 && ((i & 15) < 8 || (i & 15) == 15)) // slots 8..14 are clock64 stamps, relative to slot 8 of the same CTA
-      t0 = std::min(t0, ts[i]);
-  out[2] = ncta;
-  for (size_t i = 0; i < ts.size() && (int)(3 + i) < out_cap; i++) {
-    if (i >= nper) { // spine phase stamps (clock64), relative to the first one
-      out[3 + i] = ts[i] > 0 ? (double)(ts[i] - ts[nper]) : -1.0;
-      continue;
-    }
-    const bool cyc = (i & 15) >= 8 && (i & 15) < 15;
-    out[3 + i] = ts[i] > 0 ? (double)(ts[i] - (cyc ? ts[(i & ~(size_t)15) + 8] : t0)) : -1.0;
-  }
-  int info = 0;
-  OVP_CUDA(cudaMemcpy(&info, c->dflags + 1, sizeof(int), cudaMemcpyDeviceToHost));
-  if (info) {
-    cudaMemset(c->dflags + 1, 0, sizeof(int));
-    return fail(c, OVP_ERR_NOT_POSITIVE_DEFINITE, "debug_chol_fused: test matrix not positive definite");
-  }
-  return OVP_OK;
-}
-
-// Test hook for the fused Cholesky (tests/test_gpu_cholfused.py): factor a host matrix (lower triangle of A, n x n, column-major)
-// over its leading npiv columns with pivot tolerance tol and, when M is given, solve Y = M L^-T (mrows x npiv) and w = L^-1 z.
-// Not part of the ABI in include/ovp.h.
-extern "C" int ovp_debug_chol_solve(ovp_ctx *h, const double *A, int n, int npiv, double tol, const double *M, int mrows, const double *z,
-                                    double *L_out, double *Y_out, double *w_out) {
-  Ctx *c = &h->c;
-  if (n > c->wsS.cap || mrows > c->Nmax || npiv > n)
-    return fail(c, OVP_ERR_CAPACITY, "debug_chol_solve: too large");
-  const int ld = c->wsS.cap;
-  OVP_CUDA(cudaMemsetAsync(c->wsS.S, 0, (size_t)ld * ld * sizeof(double), c->stream));
-  OVP_CUDA(cudaMemcpy2DAsync(c->wsS.S, (size_t)ld * sizeof(double), A, (size_t)n * sizeof(double), (size_t)n * sizeof(double), n,
-                             cudaMemcpyHostToDevice, c->stream));
-  if (M) {
-    OVP_CUDA(cudaMemcpy2DAsync(c->dM, (size_t)c->Nmax * sizeof(double), M, (size_t)mrows * sizeof(double), (size_t)mrows * sizeof(double),
-                               npiv, cudaMemcpyHostToDevice, c->stream));
-    OVP_CUDA(cudaMemcpyAsync(c->dvec + c->Rcap, z, (size_t)npiv * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  }
-  int st = chol_fused(c, c->wsS.S, ld, n, npiv, tol, M ? c->dM : nullptr, c->Nmax, mrows, M ? c->dvec + c->Rcap : nullptr, 1, c->dY, c->Nmax, c->dvec, -1.0,
-                      c->dscal + 8, nullptr);
-  if (st)
-    return st;
-  OVP_CUDA(cudaMemcpy2DAsync(L_out, (size_t)n * sizeof(double), c->wsS.S, (size_t)ld * sizeof(double), (size_t)n * sizeof(double), n,
-                             cudaMemcpyDeviceToHost, c->stream));
-  if (M) {
-    OVP_CUDA(cudaMemcpy2DAsync(Y_out, (size_t)mrows * sizeof(double), c->dY, (size_t)c->Nmax * sizeof(double), (size_t)mrows * sizeof(double),
-                               npiv, cudaMemcpyDeviceToHost, c->stream));
-    OVP_CUDA(cudaMemcpyAsync(w_out, c->dvec, (size_t)npiv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  }
-  OVP_CUDA(cudaStreamSynchronize(c->stream));
-  int info = 0;
-  OVP_CUDA(cudaMemcpy(&info, c->dflags + 1, sizeof(int), cudaMemcpyDeviceToHost));
-  if (info) {
-    cudaMemset(c->dflags + 1, 0, sizeof(int));
-    return fail(c, OVP_ERR_NOT_POSITIVE_DEFINITE, "debug_chol_solve: matrix not positive definite (strict mode)");
-  }
-  return OVP_OK;
-}

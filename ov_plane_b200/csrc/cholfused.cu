@@ -19,12 +19,23 @@ namespace ovp {
 #define CF_B 64
 #define CF_LD 68 // 68 mod 16 == 4: DMMA fragment reads (8 rows x 4 k) hit 16 distinct 8-byte banks per half warp
 #define CF_RB 16
+// Tiles travel between CTAs as whole shared-memory images (64 columns x CF_LD doubles, padding included) through exchange slots in
+// global memory (L2 resident): ONE cp.async.bulk (TMA bulk copy) per tile and direction, completion on an mbarrier on the loading
+// side, bulk-group wait + release flag on the storing side.  The 16x16 inverses of a diagonal tile's four diagonal blocks travel
+// as a compact image (4 blocks x 16 columns x CF_XLD doubles).
+#define CF_SLOT (CF_B * CF_LD)            // doubles per tile slot
+#define CF_SLOT_BYTES (CF_SLOT * 8)       // 34 816 B
+#define CF_XLD 20                         // 20 mod 16 == 4: same bank property as CF_LD for the DMMA fragment reads of X
+#define CF_XSZ (4 * 16 * CF_XLD)          // 1280 doubles
+#define CF_XBYTES (CF_XSZ * 8)            // 10 240 B
+#define CF_XAT(b, r, c) ((b) * (16 * CF_XLD) + (c) * CF_XLD + (r)) // element (16b + r, 16b + c) of the inverse of diagonal block b
 
 struct CholFusedArgs {
   double *A;
   int ld, n, npiv;
   double tol;
-  double *LinvD; // Tp tiles, 64 x 64 col-major each
+  double *LinvD; // Tp compact inverse images (CF_XSZ doubles each, stride CF_B * CF_B)
+  double *xch;   // exchange slots (CF_SLOT doubles each): L(i,k) at (k * T + i), U(i,i-1) at (T * T + i), U(j,j) at (T * T + T + j)
   double *diag0; // original diagonal (Tp * 64), written by the tile CTAs for the spine
   int *flags;    // [Tp] D, [T * Tp] P (i * Tp + k), [T] U(j,j), [T] U(i,i-1)
   int *ctrl;     // [0] epoch, [1] finished-CTA counter
@@ -87,6 +98,59 @@ __device__ __forceinline__ void cf_signal(int *flag, int e) {
   if (threadIdx.x == 0) {
     __threadfence();
     cf_st_release(flag, e);
+  }
+}
+
+// ---- TMA bulk copies + mbarrier (async proxy) ---------------------------------------------------------------------------------
+__device__ __forceinline__ void cf_mbar_init(unsigned mb, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cf_mbar_expect_tx(unsigned mb, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ unsigned cf_mbar_try(unsigned mb, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(mb), "r"(parity)
+               : "memory");
+  return ok;
+}
+__device__ __forceinline__ void cf_mbar_wait(unsigned mb, unsigned parity) {
+  while (!cf_mbar_try(mb, parity)) {
+  }
+}
+// global -> shared, completes `bytes` on the mbarrier (bytes multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void cf_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mb) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mb)
+               : "memory");
+}
+// shared -> global, joins the thread's current bulk async-group
+__device__ __forceinline__ void cf_bulk_s2g(void *dst, unsigned src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cf_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cf_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); } // writes performed
+// generic-proxy shared-memory writes -> visible to the async proxy (before a bulk store reads them)
+__device__ __forceinline__ void cf_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// generic-proxy acquire of a flag -> ordered before async-proxy reads of the data it guards
+__device__ __forceinline__ void cf_fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Publish a shared-memory image through an exchange slot: called by ONE thread after a CTA barrier that follows the last
+// generic-proxy write (each writer ran cf_fence_async_smem before the barrier).  Returns with the bulk group committed.
+__device__ __forceinline__ void cf_publish_begin(double *slot, unsigned src, unsigned bytes) {
+  cf_bulk_s2g(slot, src, bytes);
+  cf_bulk_commit();
+}
+// ... and the release of its flag once the bulk writes have been performed
+__device__ __forceinline__ void cf_publish_end(int *flag, int e) {
+  cf_bulk_wait_all();
+  __threadfence();
+  cf_st_release(flag, e);
+}
+// One thread: wait for the producer's flag, then start the bulk load(s) of the guarded slot(s) onto the mbarrier
+__device__ __forceinline__ void cf_acquire(const int *flag, int e) {
+  while (cf_ld_acquire(flag) != e) {
   }
 }
 
@@ -169,21 +233,6 @@ __device__ __noinline__ void cf_store_tile(const double *s, double *g, int ld, i
       else if (r2 < rv)
         __stcg(dst, v[q].x);
     }
-  }
-}
-
-// The inverse tile X only carries its four 16x16 diagonal blocks: they travel as 4 x 16 x 16 doubles (block b at g + 256 b,
-// column-major 16 x 16), one 16-byte chunk per thread and block pair
-__device__ __forceinline__ void cf_store_xdiag(const double *s, double *g) {
-  for (int q = threadIdx.x; q < 512; q += 256) {
-    const int b = q >> 7, c = (q >> 3) & 15, r2 = (q & 7) * 2;
-    __stcg(reinterpret_cast<double2 *>(g + 256 * b + 16 * c + r2), *reinterpret_cast<const double2 *>(s + CF_AT(16 * b + r2, 16 * b + c)));
-  }
-}
-__device__ __forceinline__ void cf_load_xdiag(double *s, const double *g) { // the rest of s is not touched (never read by cf_bsolve64)
-  for (int q = threadIdx.x; q < 512; q += 256) {
-    const int b = q >> 7, c = (q >> 3) & 15, r2 = (q & 7) * 2;
-    *reinterpret_cast<double2 *>(s + CF_AT(16 * b + r2, 16 * b + c)) = __ldcg(reinterpret_cast<const double2 *>(g + 256 * b + 16 * c + r2));
   }
 }
 
@@ -362,14 +411,31 @@ __device__ __noinline__ void cf_trail16(double *a, int c0) {
 // shuffle -> fma (the next pivot is rebuilt on every lane from a value shuffled one column earlier).  The trailing update
 // inside the tile is DMMA.  Zero-pivot rule: pivot <= thr (= tol * original diagonal) or <= 0 -> column of zeros, pivinv = 0
 // (rank-deficient Gram matrices); strict (tol == 0) flags *info instead (S must be positive definite).
-struct CfPrefetch { // the flags of the next step's two tiles, polled by the spine's idle warp during the last pivot chain
+struct CfPrefetch { // the next step's two tiles: their flags are polled by the spine's idle warp during the last pivot chain, which then
+                    // starts the two bulk loads (exchange slot -> shared memory) onto `mbar`
   const int *flag0, *flag1;
   double *s0, *s1;
   const double *g0, *g1;
-  int ld, rv;
+  unsigned mbar;
 };
+// Factor tiles of the previous step that still have to be copied into the matrix A (nobody in this launch reads them there): one idle
+// warp of the spine per tile, during the FIRST pivot chain of the next step (warps 4 and 5 never run a chain).  One 512-byte column per
+// instruction (16 bytes per lane).  (One cp.async.bulk per column was tried first: 128 small bulk copies per step cost ~12 K cycles of
+// issue time; plain vector stores from an idle warp cost nothing on the critical path.)
+struct CfDeferred {
+  const double *src[2];
+  double *dst[2];
+  int n, ld, ncol;
+};
+__device__ __forceinline__ void cf_deferred_store(const CfDeferred &d, int q, int lane) {
+  const double *s = d.src[q] + 2 * lane;
+  double *g = d.dst[q] + 2 * lane;
+#pragma unroll 4
+  for (int c = 0; c < d.ncol; c++)
+    __stcg(reinterpret_cast<double2 *>(g + (size_t)c * d.ld), *reinterpret_cast<const double2 *>(s + c * CF_LD));
+}
 __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool strict, double *pivinv, int *info, double *bcast,
-                           const CfPrefetch &pf, int epoch, long long *dbgp = nullptr) {
+                           const CfPrefetch &pf, const CfDeferred &dfr, int epoch, long long *dbgp = nullptr) {
 #define PT(slot)                                                                                                             \
   if (dbgp && threadIdx.x == 0)                                                                                              \
     dbgp[slot] = clock64();
@@ -377,22 +443,29 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   if (tid < CF_B)
     pivinv[tid] = 0.0;
-  if (bs < CF_B) // partial tile: the chain writes only bs rows of the diagonal blocks of x
-    for (int idx = tid; idx < CF_B * CF_LD; idx += 256)
+  if (bs < CF_B) // partial tile: the chain writes only bs rows of the diagonal blocks of x (compact image, CF_XAT)
+    for (int idx = tid; idx < CF_XSZ; idx += 256)
       x[idx] = 0.0;
   __syncthreads();
   for (int c0 = 0; c0 < bs; c0 += 16) {
     const int nbp = min(16, bs - c0);
     const int vw = (CF_B - c0 - 16) / 16; // warps 0..vw-1 carry the rows below the block, warp vw carries the identity (below)
-    if (warp_u == 7) { // (never a chain warp: vw <= 3) last panel: this idle warp polls the flags of the next step's tiles
-      if (c0 + 16 >= bs) {
-        if (lane == 0) {
+    if ((warp_u == 4 || warp_u == 5) && c0 == 0) { // (never chain warps: vw <= 3) the previous step's factor tiles -> A
+      if (warp_u - 4 < dfr.n)
+        cf_deferred_store(dfr, warp_u - 4, lane);
+    } else if (warp_u == 7) { // the I/O warp
+      if (c0 + 16 >= bs) { // last panel: poll the flags of the next step's tiles, then start their bulk loads
+        if (lane == 0 && (pf.flag0 || pf.flag1)) {
           if (pf.flag0)
-            while (cf_ld_acquire(pf.flag0) != epoch) {
-            }
+            cf_acquire(pf.flag0, epoch);
           if (pf.flag1)
-            while (cf_ld_acquire(pf.flag1) != epoch) {
-            }
+            cf_acquire(pf.flag1, epoch);
+          cf_fence_async_all();
+          cf_mbar_expect_tx(pf.mbar, (pf.flag0 ? CF_SLOT_BYTES : 0) + (pf.flag1 ? CF_SLOT_BYTES : 0));
+          if (pf.flag0)
+            cf_bulk_g2s(cf_saddr(pf.s0), pf.g0, CF_SLOT_BYTES, pf.mbar);
+          if (pf.flag1)
+            cf_bulk_g2s(cf_saddr(pf.s1), pf.g1, CF_SLOT_BYTES, pf.mbar);
         }
       }
     } else if (warp_u <= vw) {
@@ -427,7 +500,7 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
       // loop-invariant addresses and predicates, pinned in registers
       const unsigned thr_a = cf_saddr(thr + c0), piv_a = cf_saddr(pivinv + c0), lb_a = cf_saddr(lb);
       // where a lane stores its finished entry of column j: real rows a(row, c0 + j); identity row i: x(c0 + j, c0 + i)
-      const unsigned row_a = (virt && lower) ? cf_saddr(x + CF_AT(c0, c0 + lane - 16)) : cf_saddr(a + CF_AT(row < CF_B ? row : 0, c0));
+      const unsigned row_a = (virt && lower) ? cf_saddr(x + CF_XAT(c0 >> 4, 0, lane - 16)) : cf_saddr(a + CF_AT(row < CF_B ? row : 0, c0));
       const unsigned row_s = (virt && lower) ? 8u : (unsigned)(CF_LD * 8);
       const unsigned lst_a = lb_a + 8 * lane;
       unsigned lq_a = lb_a + 64 * 8;
@@ -490,7 +563,8 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
 // chain): a right-side triangular solve is independent per row, so warp w owns rows 8w..8w+7 through all four 16-column steps
 //   S = U[:, b] - U[:, <b] Lkk[b, <b]^T      (U[:, <b] already holds the result)
 //   U[:, b] = S X_bb^T
-// with a private 8 x 16 scratch (S) and no CTA barrier at all.  No 64x64 inverse is ever formed.
+// with a private 8 x 16 scratch (S) and no CTA barrier at all.  No 64x64 inverse is ever formed.  X is the compact inverse image
+// (CF_XAT); S is a 64 x 16 scratch in tile layout (16 columns of CF_LD).
 __device__ __noinline__ void cf_bsolve64(double *U, const double *Lkk, const double *X, double *S) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -516,8 +590,8 @@ __device__ __noinline__ void cf_bsolve64(double *U, const double *Lkk, const dou
     for (int k4 = 0; k4 < 16; k4 += 4) {
       const double sv = S[CF_AT(r, k4 + t)];
       if (k4 < 8) // X_bb lower triangular: columns 0..7 only need k < 8
-        dmma_m8n8k4(c0[0], c0[1], sv, X[CF_AT(cb + g, cb + k4 + t)]);
-      dmma_m8n8k4(c1[0], c1[1], sv, X[CF_AT(cb + 8 + g, cb + k4 + t)]);
+        dmma_m8n8k4(c0[0], c0[1], sv, X[CF_XAT(b, g, k4 + t)]);
+      dmma_m8n8k4(c1[0], c1[1], sv, X[CF_XAT(b, 8 + g, k4 + t)]);
     }
     __syncwarp();
 #pragma unroll
@@ -530,35 +604,46 @@ __device__ __noinline__ void cf_bsolve64(double *U, const double *Lkk, const dou
 }
 
 __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(128) double sm[];
   // every shared array is carved from the one dynamic block: addresses of static __shared__ variables are re-derived from
-  // SR_CgaCtaId (S2R, ~100+ cycles) wherever the compiler rematerialises them - inside the pivot loop that tripled its latency
-  double *thr = sm + 5 * CF_B * CF_LD, *pivinv = thr + CF_B, *bcast = pivinv + CF_B; // bcast: 8 warps x 96, 16-byte aligned
+  // SR_CgaCtaId (S2R, ~100+ cycles) wherever the compiler rematerialises them - inside the pivot loop that tripled its latency.
+  // Layout (doubles): [0,16) two mbarriers (+ padding to 128 B) | tile buffers | role-specific (see the three branches)
+  double *tb = sm + 16; // tile buffers: 128-byte aligned bulk-copy targets
+  const unsigned mb0 = cf_saddr(sm);
   __shared__ int s_epoch;
   const int tid = threadIdx.x;
-  if (tid == 0)
+  if (tid == 0) {
     s_epoch = *(volatile int *)p.ctrl + 1;
+    cf_mbar_init(mb0, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   const int e = s_epoch;
   const int Tp = p.Tp, T = p.T;
   int *fdiag = p.flags, *fpan = p.flags + Tp; // D(k): L(k,k) and Linv(k) published; P(i,k): L(i,k) published
   int *fud = fpan + T * Tp, *fus = fud + T;   // U(j,j) / U(i,i-1): tile updated through all panels but the last, for the spine
+  double *slotL = p.xch, *slotUs = p.xch + (size_t)T * T * CF_SLOT, *slotUd = slotUs + (size_t)T * CF_SLOT;
+#define CF_SLOTL(i, k) (slotL + ((size_t)(k) * T + (i)) * CF_SLOT)
+  const int IO = 224; // lane 0 of warp 7: the thread that issues bulk copies and releases flags (warp 7 never runs a pivot chain)
 
   if (blockIdx.x == 0) {
     // ---- spine: every diagonal block, back to back (warm instruction cache, no global-memory hop on the critical path) ----
-    double *a = sm, *b1 = sm + CF_B * CF_LD, *b2 = sm + 2 * CF_B * CF_LD, *b3 = sm + 3 * CF_B * CF_LD, *b4 = sm + 4 * CF_B * CF_LD;
+    double *a = tb, *b3 = tb + CF_SLOT, *b4 = tb + 2 * CF_SLOT;
+    double *xc = tb + 3 * CF_SLOT, *sscr = xc + CF_XSZ, *thr = sscr + 16 * CF_LD, *pivinv = thr + CF_B, *bcast = pivinv + CF_B; // bcast: 8 x 96
+    unsigned par_pf = 0;
+    CfDeferred dfr; // column stores of the previous step's factor tiles into A, issued by warp 7 during the first pivot chain
+    dfr.n = 0;
     CF_TS(0)
     cf_load_tile(a, p.A, p.ld, min(CF_B, p.n), min(CF_B, p.n), true);
     __syncthreads();
     if (tid < CF_B)
       thr[tid] = p.tol * a[CF_AT(tid, tid)];
-    for (int idx = tid; idx < CF_B * CF_LD; idx += 256)
-      b1[idx] = 0.0; // the inverse tile: only its lower blocks are ever written
+    for (int idx = tid; idx < CF_XSZ; idx += 256)
+      xc[idx] = 0.0; // the inverse image: only the lower triangles of its blocks are ever written
     for (int k = 0; k < Tp; k++) {
-      const int bs = min(CF_B, p.npiv - CF_B * k), rv = min(CF_B, p.n - CF_B * k);
+      const int bs = min(CF_B, p.npiv - CF_B * k);
       double *gA = p.A + (size_t)(CF_B * k) * p.ld + CF_B * k;
       const bool has_panel = k + 1 < T, next_diag = k + 1 < Tp;
-      const int rv1 = has_panel ? min(CF_B, p.n - CF_B * (k + 1)) : 0;
       double *gP = p.A + (size_t)(CF_B * k) * p.ld + CF_B * (k + 1);
       if (k < 3)
         CF_TS(1 + 2 * k)
@@ -569,36 +654,50 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       pf.flag1 = next_diag ? fud + k + 1 : nullptr;
       pf.s0 = b3;
       pf.s1 = b4;
-      pf.g0 = gP;
-      pf.g1 = gP + (size_t)CF_B * p.ld;
-      pf.ld = p.ld;
-      pf.rv = rv1;
-      cf_potrf64(a, b1, bs, thr, p.tol == 0.0, pivinv, p.info, bcast, pf, e, dbgp);
+      pf.g0 = slotUs + (size_t)(k + 1) * CF_SLOT;
+      pf.g1 = slotUd + (size_t)(k + 1) * CF_SLOT;
+      pf.mbar = mb0;
+      cf_potrf64(a, xc, bs, thr, p.tol == 0.0, pivinv, p.info, bcast, pf, dfr, e, dbgp);
+      dfr.n = 0;
       if (k < 3)
         CF_TS(2 + 2 * k)
       PT(13)
-      cf_store_xdiag(b1, p.LinvD + (size_t)k * CF_B * CF_B); // the four 16x16 inverses
-      PT(19)
-      cf_store_tile(a, gA, p.ld, rv, bs, true);
+      // strictly-upper entries inside the diagonal 8x8 blocks were touched by the in-tile trailing updates: the factor is later read
+      // as a dense operand, so they leave as zeros (nothing in this kernel reads them)
+      for (int idx = tid; idx < CF_B * 8; idx += 256) {
+        const int c = idx >> 3, r = (c & ~7) + (idx & 7);
+        if (r < c)
+          a[CF_AT(r, c)] = 0.0;
+      }
+      cf_fence_async_smem();
+      __syncthreads();
+      if (tid == IO) { // L(k,k) and its block inverses -> exchange slots (2 bulk copies), the factor columns -> the matrix
+        cf_bulk_s2g(CF_SLOTL(k, k), cf_saddr(a), CF_SLOT_BYTES);
+        cf_bulk_s2g(p.LinvD + (size_t)k * CF_B * CF_B, cf_saddr(xc), CF_XBYTES);
+        cf_bulk_commit();
+      }
+      dfr.src[0] = a; // the factor columns go into the matrix A later, off the critical path (nobody in this launch reads A)
+      dfr.dst[0] = gA;
+      dfr.n = 1;
       PT(20)
-      cf_signal(fdiag + k, e);
-      PT(21)
       if (has_panel) {
-        // the two tiles of the next step (their flags were polled by the idle warp during the last pivot chain); issued after the
-        // release above: a fence with copies in flight waits for them
-        cf_cpasync_tile(b3, gP, p.ld, rv1, CF_B, false);
-        if (next_diag)
-          cf_cpasync_tile(b4, gP + (size_t)CF_B * p.ld, p.ld, rv1, rv1, true);
         if (next_diag && tid < CF_B)
           thr[tid] = p.tol * __ldcg(p.diag0 + CF_B * (k + 1) + tid);
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        PT(23)
-        __syncthreads();
+        cf_mbar_wait(mb0, par_pf); // the two tiles of the next step (bulk loads started during the last pivot chain)
+        par_pf ^= 1;
         PT(24)
-        cf_bsolve64(b3, a, b1, b2); // L(k+1,k) = U(k+1,k) L(k,k)^-T
+        cf_bsolve64(b3, a, xc, sscr); // L(k+1,k) = U(k+1,k) L(k,k)^-T
+        cf_fence_async_smem();
         __syncthreads();
         PT(25)
-        cf_store_tile(b3, gP, p.ld, rv1, bs, false);
+        if (tid == IO) {
+          cf_publish_end(fdiag + k, e); // (the bulk copies above have long landed)
+          cf_bulk_s2g(CF_SLOTL(k + 1, k), cf_saddr(b3), CF_SLOT_BYTES);
+          cf_bulk_commit();
+        }
+        dfr.src[1] = b3;
+        dfr.dst[1] = gP;
+        dfr.n = 2;
         PT(26)
         if (next_diag) {
           cf_mma_64<2>(b4, b3, b3, -1.0, true, false); // lower triangle of the next diagonal tile
@@ -607,13 +706,26 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
           a = b4;
           b4 = tmp;
         }
+        dfr.ld = p.ld;
+        dfr.ncol = bs;
         PT(27)
-        cf_signal(fpan + (k + 1) * Tp + k, e); // after the update: the panel stores have landed, the release costs nothing
+        if (tid == IO)
+          cf_publish_end(fpan + (k + 1) * Tp + k, e);
         PT(28)
+      } else if (tid == IO) {
+        cf_publish_end(fdiag + k, e);
       }
     }
+    dfr.ld = p.ld;
+    dfr.ncol = min(CF_B, p.npiv - CF_B * (Tp - 1));
+    {
+      const int w = tid >> 5; // the last step's tiles
+      if ((w == 4 || w == 5) && w - 4 < dfr.n)
+        cf_deferred_store(dfr, w - 4, tid & 31);
+    }
   } else if ((int)blockIdx.x < p.ntile) {
-    double *a = sm, *b1 = sm + CF_B * CF_LD, *b2 = sm + 2 * CF_B * CF_LD;
+    double *a = tb, *b1 = tb + CF_SLOT, *b2 = tb + 2 * CF_SLOT;
+    double *xc = tb + 3 * CF_SLOT, *sscr = xc + CF_XSZ;
     int j = 0, rem = blockIdx.x;
     while (rem >= T - j) {
       rem -= T - j;
@@ -623,6 +735,7 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
     const int rv = min(CF_B, p.n - CF_B * i), cv = min(CF_B, p.n - CF_B * j);
     const int bs = min(CF_B, p.npiv - CF_B * j);
     double *gA = p.A + (size_t)(CF_B * j) * p.ld + CF_B * i;
+    unsigned par = 0;
     CF_TS(0)
     cf_load_tile(a, gA, p.ld, rv, cv, i == j);
     __syncthreads();
@@ -631,51 +744,68 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       __stcg(p.diag0 + CF_B * j + tid, a[CF_AT(tid, tid)]); // original diagonal: reference of the zero-pivot rule
     const int kmax = (i == j) ? j - 1 : j; // the spine applies the last update of a diagonal tile itself
     for (int k = 0; k < kmax; k++) {
-      cf_wait(fpan + i * Tp + k, e);
-      if (i != j)
-        cf_wait(fpan + j * Tp + k, e);
-      cf_load_tile(b1, p.A + (size_t)(CF_B * k) * p.ld + CF_B * i, p.ld, rv, CF_B, false);
-      if (i != j)
-        cf_load_tile(b2, p.A + (size_t)(CF_B * k) * p.ld + CF_B * j, p.ld, cv, CF_B, false);
-      __syncthreads();
+      if (tid == 0) { // wait for the panel tile(s) of column block k, then one bulk load each
+        cf_acquire(fpan + i * Tp + k, e);
+        if (i != j)
+          cf_acquire(fpan + j * Tp + k, e);
+        cf_fence_async_all();
+        cf_mbar_expect_tx(mb0, (i != j) ? 2 * CF_SLOT_BYTES : CF_SLOT_BYTES);
+        cf_bulk_g2s(cf_saddr(b1), CF_SLOTL(i, k), CF_SLOT_BYTES, mb0);
+        if (i != j)
+          cf_bulk_g2s(cf_saddr(b2), CF_SLOTL(j, k), CF_SLOT_BYTES, mb0);
+      }
+      cf_mbar_wait(mb0, par);
+      par ^= 1;
       if (i != j)
         cf_mma_64<0>(a, b1, b2, -1.0, true, false);
       else
         cf_mma_64<2>(a, b1, b1, -1.0, true, false);
-      __syncthreads();
+      __syncthreads(); // b1 / b2 are overwritten by the next iteration's loads
     }
     CF_TS(3)
-    if (i == j) {
-      cf_store_tile(a, gA, p.ld, rv, cv, true);
-      cf_signal(fud + j, e);
-    } else if (i == j + 1) {
-      cf_store_tile(a, gA, p.ld, rv, cv, false);
-      cf_signal(fus + i, e);
-    } else {
-      cf_wait(fdiag + j, e);
-      CF_TS(4)
-      cf_load_tile(b1, p.A + (size_t)(CF_B * j) * p.ld + CF_B * j, p.ld, min(CF_B, p.n - CF_B * j), bs, true); // L(j,j)
-      cf_load_xdiag(b2, p.LinvD + (size_t)j * CF_B * CF_B);                                                   // its 16x16 inverses
+    if (i == j || i == j + 1) { // hand the tile (updated through all panels but the last) to the spine
+      cf_fence_async_smem();
       __syncthreads();
+      if (tid == 0) {
+        cf_publish_begin((i == j ? slotUd + (size_t)j * CF_SLOT : slotUs + (size_t)i * CF_SLOT), cf_saddr(a), CF_SLOT_BYTES);
+        cf_publish_end(i == j ? fud + j : fus + i, e);
+      }
+    } else {
+      if (tid == 0) {
+        cf_acquire(fdiag + j, e);
+        cf_fence_async_all();
+        cf_mbar_expect_tx(mb0, CF_SLOT_BYTES + CF_XBYTES);
+        cf_bulk_g2s(cf_saddr(b1), CF_SLOTL(j, j), CF_SLOT_BYTES, mb0);                              // L(j,j)
+        cf_bulk_g2s(cf_saddr(xc), p.LinvD + (size_t)j * CF_B * CF_B, CF_XBYTES, mb0);                // its 16x16 inverses
+      }
+      cf_mbar_wait(mb0, par);
+      par ^= 1;
       CF_TS(5)
-      cf_bsolve64(a, b1, b2, sm + 3 * CF_B * CF_LD);
+      cf_bsolve64(a, b1, xc, sscr);
+      cf_fence_async_smem();
       __syncthreads();
       CF_TS(6)
-      cf_store_tile(a, gA, p.ld, rv, bs, false);
-      cf_signal(fpan + i * Tp + j, e);
+      if (tid == 0) {
+        cf_publish_begin(CF_SLOTL(i, j), cf_saddr(a), CF_SLOT_BYTES);
+        cf_publish_end(fpan + i * Tp + j, e);
+      }
+      cf_store_tile(a, gA, p.ld, rv, bs, false); // the factor tile into the matrix (nobody in this launch reads it there)
       CF_TS(7)
     }
+    if (tid == 0)
+      cf_bulk_wait_all();
   } else {
     // ---- row block of the right-hand side: Y = M L^-T, right-looking ----
     const int rb = blockIdx.x - p.ntile;
     const int ms = p.mstride;
-    double *mrow = sm;                 // CF_RB x ms
-    double *Lt = sm + CF_RB * ms;      // 64 x CF_LD
-    double *yk = Lt + CF_B * CF_LD;    // CF_RB x CF_LD (row-major)
-    double *Xt = yk + CF_RB * CF_LD;   // 64 x CF_LD: the 16x16 inverses of L(k,k)'s diagonal blocks
-    double *sb = Xt + CF_B * CF_LD;    // 2 warps x 8 x 20 scratch
+    double *Lt = tb;                     // one tile buffer (bulk-load target, 128-byte aligned)
+    double *Xt = tb + CF_SLOT;           // compact inverse image of L(k,k)'s diagonal blocks
+    double *mrow = Xt + CF_XSZ;          // CF_RB x ms
+    double *yk = mrow + CF_RB * ms;      // CF_RB x CF_LD (row-major)
+    double *sb = yk + CF_RB * CF_LD;     // 2 warps x 8 x 20 scratch (320 doubles; chi2 reduction: 256)
     const int row0 = rb * CF_RB;
     const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    unsigned par = 0;
     double wsq = 0.0;
     for (int idx = tid; idx < CF_RB * Tp * CF_B; idx += 256) {
       const int r = idx & (CF_RB - 1), k = idx >> 4;
@@ -692,10 +822,15 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
     __syncthreads();
     for (int k = 0; k < Tp; k++) {
       const int bs = min(CF_B, p.npiv - CF_B * k);
-      cf_wait(fdiag + k, e);
-      cf_load_tile(Lt, p.A + (size_t)(CF_B * k) * p.ld + CF_B * k, p.ld, min(CF_B, p.n - CF_B * k), bs, true);
-      cf_load_xdiag(Xt, p.LinvD + (size_t)k * CF_B * CF_B);
-      __syncthreads();
+      if (tid == 0) {
+        cf_acquire(fdiag + k, e);
+        cf_fence_async_all();
+        cf_mbar_expect_tx(mb0, CF_SLOT_BYTES + CF_XBYTES);
+        cf_bulk_g2s(cf_saddr(Lt), CF_SLOTL(k, k), CF_SLOT_BYTES, mb0);
+        cf_bulk_g2s(cf_saddr(Xt), p.LinvD + (size_t)k * CF_B * CF_B, CF_XBYTES, mb0);
+      }
+      cf_mbar_wait(mb0, par);
+      par ^= 1;
       if (warp < 2) { // yk (16 x 64) = mrow[:, 64k ..] L(k,k)^-T: rows are independent, warp w owns rows 8w..8w+7 (cf_bsolve64 in row-major)
         const int r = 8 * warp + g;
         double *sw = sb + warp * 160;
@@ -719,8 +854,8 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
           for (int k4 = 0; k4 < 16; k4 += 4) {
             const double sv = sw[g * 20 + k4 + t];
             if (k4 < 8)
-              dmma_m8n8k4(c0[0], c0[1], sv, Xt[CF_AT(cb + g, cb + k4 + t)]);
-            dmma_m8n8k4(c1[0], c1[1], sv, Xt[CF_AT(cb + 8 + g, cb + k4 + t)]);
+              dmma_m8n8k4(c0[0], c0[1], sv, Xt[CF_XAT(b, g, k4 + t)]);
+            dmma_m8n8k4(c1[0], c1[1], sv, Xt[CF_XAT(b, 8 + g, k4 + t)]);
           }
           __syncwarp();
 #pragma unroll
@@ -746,9 +881,14 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
         }
       }
       for (int j = k + 1; j < Tp; j++) {
-        cf_wait(fpan + j * Tp + k, e);
-        cf_load_tile(Lt, p.A + (size_t)(CF_B * k) * p.ld + CF_B * j, p.ld, min(CF_B, p.n - CF_B * j), CF_B, false);
-        __syncthreads();
+        if (tid == 0) {
+          cf_acquire(fpan + j * Tp + k, e);
+          cf_fence_async_all();
+          cf_mbar_expect_tx(mb0, CF_SLOT_BYTES);
+          cf_bulk_g2s(cf_saddr(Lt), CF_SLOTL(j, k), CF_SLOT_BYTES, mb0);
+        }
+        cf_mbar_wait(mb0, par);
+        par ^= 1;
         double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
         const double *pa = yk + g * CF_LD + t;
         const double *pb = Lt + CF_AT(8 * warp + g, t);
@@ -763,7 +903,7 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
         pm[1] -= c01;
         pm[8 * ms] -= c10;
         pm[8 * ms + 1] -= c11;
-        __syncthreads();
+        __syncthreads(); // Lt is overwritten by the next bulk load
       }
     }
     if (p.z && p.mrows >= row0 && p.mrows < row0 + CF_RB && p.chi2) {
@@ -797,7 +937,6 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
   }
 }
 
-static bool g_cf_attr_set = false;
 
 // Factor the leading npiv columns of the n x n lower-stored matrix A in place (rows npiv..n-1 are solved along) and, when M is
 // given, solve Y = M L^-T (mrows x npiv) and w = L^-1 z in the same launch.
@@ -821,6 +960,7 @@ int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const dou
   for (int j = 0; j < p.Tp; j++)
     p.ntile += p.T - j;
   p.LinvD = c->cf_linv;
+  p.xch = c->cf_xch;
   p.diag0 = c->cf_diag0;
   p.flags = c->cf_flags;
   p.ctrl = c->cf_ctrl;
@@ -840,26 +980,25 @@ int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const dou
   const int vrows = M ? (mrows + (z ? 1 : 0)) : 0;
   p.nrb = (vrows + CF_RB - 1) / CF_RB;
   p.mstride = p.Tp * CF_B + 4;
-  size_t smem_tile = ((size_t)5 * CF_B * CF_LD + 2 * CF_B + 8 * 96) * sizeof(double);
-  size_t smem_rows = ((size_t)CF_RB * p.mstride + 2 * (size_t)CF_B * CF_LD + (size_t)CF_RB * CF_LD + 320) * sizeof(double);
+  size_t smem_tile = ((size_t)16 + 3 * CF_SLOT + CF_XSZ + 16 * CF_LD + 2 * CF_B + 8 * 96) * sizeof(double);
+  size_t smem_rows = ((size_t)16 + CF_SLOT + CF_XSZ + (size_t)CF_RB * p.mstride + (size_t)CF_RB * CF_LD + 320) * sizeof(double);
   size_t smem = std::max(smem_tile, p.nrb ? smem_rows : 0);
   if (smem > 220 * 1024)
     return fail(c, OVP_ERR_CAPACITY, "chol_fused: %d columns need %zu B of shared memory", npiv, smem);
-  if (!g_cf_attr_set) {
+  if (!c->cf_attr_set) {
     OVP_CUDA(cudaFuncSetAttribute(chol_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    g_cf_attr_set = true;
+    c->cf_attr_set = true;
   }
   const int grid = p.ntile + p.nrb;
   {
     // the grid must be co-resident (the spine and the tile CTAs wait on each other): one CTA per SM at this shared-memory size
-    static int max_coresident = 0;
-    if (!max_coresident) {
-      int per_sm = 0, sms = 0, dev = 0;
-      OVP_CUDA(cudaGetDevice(&dev));
-      OVP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (!c->cf_max_coresident) {
+      int per_sm = 0, sms = 0;
+      OVP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
       OVP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_fused_kernel, 256, 220 * 1024));
-      max_coresident = std::max(1, per_sm) * sms;
+      c->cf_max_coresident = std::max(1, per_sm) * sms;
     }
+    const int max_coresident = c->cf_max_coresident;
     if (grid > max_coresident)
       return fail(c, OVP_ERR_CAPACITY, "chol_fused: a %d-wide system with %d right-hand-side rows needs %d co-resident CTAs, the device holds %d", n,
                   vrows, grid, max_coresident);

@@ -3,6 +3,7 @@
 // marginalize (:276-344), get_marginal_covariance (:231-259), set_initial_covariance (:204-229),
 // initialize_invertible's covariance growth (:568-573) and ov_type::*::update (the manifold update of every variable).
 #include "ovp_internal.h"
+#include "host_math.h"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -155,23 +156,44 @@ __global__ void zero_band_kernel(double *P, int ld, int N, int s) {
   }
 }
 
+// Handles are slots of the variable table.  A marginalised variable's slot goes to a FIFO free list and is handed out again once
+// OVP_HANDLE_REUSE_LAG newer slots have been freed (a stale handle held by the caller keeps failing with NOT_IN_STATE for a while
+// instead of silently naming a new variable), so the table - and every O(table) pass: finish_update_kernel, upload_var_table,
+// sync_host_values, the plan signature - stays the size of the live state instead of growing by one clone per camera frame.
+#define OVP_HANDLE_REUSE_LAG 64
 int state_append_variable(Ctx *c, Var v, const double *value, const double *fej, int *handle) {
-  if ((int)c->vars.size() >= c->max_handles)
-    return fail(c, OVP_ERR_CAPACITY, "variable handle capacity %d exceeded", c->max_handles);
   int st = sync_host_values(c);
   if (st)
     return st;
-  int h = (int)c->vars.size();
-  c->vars.push_back(v);
-  c->h_val.resize((size_t)(h + 1) * OVP_VAL_STRIDE, 0.0);
-  c->h_fej.resize((size_t)(h + 1) * OVP_VAL_STRIDE, 0.0);
-  for (int i = 0; i < v.nvalue; i++) {
-    c->h_val[(size_t)h * OVP_VAL_STRIDE + i] = value ? value[i] : 0.0;
-    c->h_fej[(size_t)h * OVP_VAL_STRIDE + i] = fej ? fej[i] : (value ? value[i] : 0.0);
+  int h;
+  const bool table_full = (int)c->vars.size() >= c->max_handles;
+  if (!c->free_handles.empty() && (table_full || (int)c->free_handles.size() > OVP_HANDLE_REUSE_LAG)) {
+    h = c->free_handles.front();
+    c->free_handles.pop_front();
+    c->vars[h] = v;
+  } else {
+    if (table_full)
+      return fail(c, OVP_ERR_CAPACITY, "variable handle capacity %d exceeded", c->max_handles);
+    h = (int)c->vars.size();
+    c->vars.push_back(v);
+    c->h_val.resize((size_t)(h + 1) * OVP_VAL_STRIDE, 0.0);
+    c->h_fej.resize((size_t)(h + 1) * OVP_VAL_STRIDE, 0.0);
+  }
+  for (int i = 0; i < OVP_VAL_STRIDE; i++) {
+    c->h_val[(size_t)h * OVP_VAL_STRIDE + i] = (i < v.nvalue && value) ? value[i] : 0.0;
+    c->h_fej[(size_t)h * OVP_VAL_STRIDE + i] = (i < v.nvalue) ? (fej ? fej[i] : (value ? value[i] : 0.0)) : 0.0;
   }
   c->var_table_dirty = true;
   *handle = h;
   return push_host_values(c, h);
+}
+
+double chi2_q95(Ctx *c, int dof) {
+  if (dof < 1)
+    dof = 1;
+  if (dof < c->chi2_table_n)
+    return c->chi2_table[dof];
+  return hm::chi2_quantile95(dof);
 }
 
 int check_status_flags(Ctx *c) {

@@ -34,7 +34,8 @@ struct FeatArgs {
   int mode;               // 0: MSCKF point (nullspace + per-feature gate), 1: MSCKF plane (nullspace, H_cp carried, no gate),
                           // 2: SLAM (landmark and plane are state columns, no nullspace, gate with plane -> no-plane fallback)
   int plane_handle;       // mode 1: >= 0: plane is in the state (cp from val/fej tables); -1: use plane_cp
-  double plane_cp[3];
+  const double *plane_cp; // mode 1, plane not in the state: its 3 linearisation values in the batch staging buffer (read through
+                          // the pointer so that a replayed CUDA graph sees the values of THIS call, not of the capture call)
   double white_px, white_c;
   const double *P;
   int ldP;

@@ -9,6 +9,61 @@
 namespace ovp {
 namespace hm {
 
+// 0.95 quantile of the chi-squared distribution with `dof` degrees of freedom: what boost::math::quantile(chi_squared(dof), 0.95)
+// returns in the reference (UpdaterMSCKF.cpp:59-62, on the fly beyond its 500-entry table, :616-619).  Newton iteration on the
+// regularised lower incomplete gamma function P(dof/2, x/2) (series below a+1, Lentz continued fraction above), started from the
+// Wilson-Hilferty approximation; relative accuracy ~1e-13.
+inline double gamma_p(double a, double x) {
+  if (x <= 0.0)
+    return 0.0;
+  const double lg = std::lgamma(a);
+  if (x < a + 1.0) {
+    double ap = a, sum = 1.0 / a, del = sum;
+    for (int n = 0; n < 10000; n++) {
+      ap += 1.0;
+      del *= x / ap;
+      sum += del;
+      if (std::fabs(del) < std::fabs(sum) * 1e-17)
+        break;
+    }
+    return sum * std::exp(-x + a * std::log(x) - lg);
+  }
+  const double tiny = 1e-300;
+  double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+  for (int i = 1; i < 10000; i++) {
+    const double an = -i * (i - a);
+    b += 2.0;
+    d = an * d + b;
+    if (std::fabs(d) < tiny)
+      d = tiny;
+    c = b + an / c;
+    if (std::fabs(c) < tiny)
+      c = tiny;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (std::fabs(del - 1.0) < 1e-17)
+      break;
+  }
+  return 1.0 - std::exp(-x + a * std::log(x) - lg) * h;
+}
+inline double chi2_quantile95(int dof) {
+  const double k = dof, a = 0.5 * k, z = 1.6448536269514722;
+  const double t = 1.0 - 2.0 / (9.0 * k) + z * std::sqrt(2.0 / (9.0 * k));
+  double x = std::fmax(1e-3, k * t * t * t);
+  for (int it = 0; it < 100; it++) {
+    const double f = gamma_p(a, 0.5 * x) - 0.95;
+    const double pdf = 0.5 * std::exp(-0.5 * x + (a - 1.0) * std::log(0.5 * x) - std::lgamma(a));
+    const double dx = f / pdf;
+    x -= dx;
+    if (x <= 0.0)
+      x = 1e-6;
+    if (std::fabs(dx) < 1e-14 * x)
+      break;
+  }
+  return x;
+}
+
 struct M3 {
   double a[9];
   double &operator()(int i, int j) { return a[3 * i + j]; }

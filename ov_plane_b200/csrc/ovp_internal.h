@@ -3,6 +3,7 @@
 #include "../../include/ovp.h"
 #include "gemm.cuh"
 #include <cuda_runtime.h>
+#include <deque>
 #include <map>
 #include <string>
 #include <vector>
@@ -39,11 +40,13 @@ struct Ctx {
   std::string last_error;
   int64_t launches = 0;
   bool use_graphs = true;    // replay the static launch sequence of a prepared batch as a CUDA graph
+  double gram_tol = 1e-11;   // zero-pivot rule of the Gram Cholesky, relative to the column's original diagonal (ovp_set_rank_tolerance)
 
   // --- State mirror -------------------------------------------------------------------------------------------
   int Nmax = 0, ldP = 0, N = 0;
   double *dP = nullptr;
   std::vector<Var> vars;          // indexed by handle
+  std::deque<int> free_handles;   // slots of marginalised variables, reused FIFO (ekf.cu state_append_variable)
   std::vector<int> order;         // State::_variables (handles)
   std::vector<double> h_val, h_fej; // host mirror, OVP_VAL_STRIDE per handle
   bool host_values_stale = false;   // device values are newer than the host mirror
@@ -71,9 +74,12 @@ struct Ctx {
   int *dflags = nullptr;       // device flags / status words (256 ints)
   double *dscal = nullptr;     // device scalars (256 doubles)
   // fused Cholesky (cholfused.cu): diagonal-block inverses, inter-CTA flags, epoch word
-  double *cf_linv = nullptr, *cf_diag0 = nullptr;
+  double *cf_linv = nullptr, *cf_diag0 = nullptr, *cf_xch = nullptr;
   int *cf_flags = nullptr, *cf_ctrl = nullptr;
   int cf_maxT = 0;
+  bool cf_attr_set = false;   // per context (= per device): >48 KB dynamic shared memory opt-in of chol_fused_kernel / feature kernels
+  int cf_max_coresident = 0;  // co-resident CTA capacity of this device for chol_fused_kernel
+  bool feat_smem_set = false;
   int max_meas_rows = 0;
   double *dHs = nullptr;       // stacked [H_x | H_cp | res], max_meas_rows x (Rcap) col-major
   size_t Hs_elems = 0;
@@ -159,6 +165,8 @@ int sync_host_values(Ctx *c);
 int push_host_values(Ctx *c, int handle);
 int state_append_variable(Ctx *c, Var v, const double *value, const double *fej, int *handle);
 int check_status_flags(Ctx *c);
+// chi-squared 0.95 quantile: the injected table (ovp_set_chi2_table) below its length, computed exactly beyond it - never clamped
+double chi2_q95(Ctx *c, int dof);
 
 // ---- features.cu -------------------------------------------------------------------------------------------------
 // extra: forced_cols != nullptr => point features only, x columns fixed to this list of state indices (multi-GPU shard
@@ -178,3 +186,13 @@ int msckf_update_impl(Ctx *c, const ovp_feature_batch *batch, const ovp_updater_
 struct ovp_ctx {
   ovp::Ctx c;
 };
+namespace ovp {
+// every ABI entry point that touches the device starts here: allocations, attribute settings and launches must land on the
+// context's own device when one process drives several GPUs (one ctx per device)
+static inline Ctx *enter(ovp_ctx *h) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != h->c.device)
+    cudaSetDevice(h->c.device);
+  return &h->c;
+}
+} // namespace ovp

@@ -53,9 +53,59 @@ def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+def load_variant(path):
+    """A differently compiled build of the same oracle sources (tools/oracle_sensitivity.py: FMA-contracted build)."""
+    L = C.CDLL(path)
+    L.orc_create.restype = C.c_void_p
+    L.orc_last_error.restype = C.c_char_p
+    L.orc_get_timestamp.restype = C.c_double
+    return L
+
+
+_PROBE_T = C.CFUNCTYPE(C.c_double, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+
+class GaugeProbe(object):
+    """Context manager around the oracle's GaugeProbe instrumentation (oracle.hpp): splits every gated plane chi2 into its
+    well-defined part and the squared projection of the compressed residual onto the left null space of the compressed Jacobian
+    (rows the reference keeps although their Jacobian part is round-off).  `gate_without=True` makes the oracle gate on the
+    well-defined part (what the CUDA path computes); `records` holds (rows, cols, rank, junk, gap) per gated system."""
+
+    def __init__(self, gate_without, variant=None, rank_tol=1e-7):
+        self.lib = variant if variant is not None else lib()
+        self.gate_without = gate_without
+        self.rank_tol = rank_tol
+        self.records = []
+        self._cb = _PROBE_T(self._probe)
+
+    def _probe(self, rows, cols, Hp, zp):
+        H = np.ctypeslib.as_array(Hp, (cols, rows)).T
+        z = np.ctypeslib.as_array(zp, (rows,))
+        if rows == 0 or cols == 0:
+            return 0.0
+        U, sv, _ = np.linalg.svd(H, full_matrices=True)
+        rank = int((sv > self.rank_tol * sv[0]).sum())
+        zn = U[:, rank:].T @ z
+        junk = float(zn @ zn)
+        gap = (sv[rank - 1] / sv[0], (sv[rank] / sv[0]) if rank < len(sv) else 0.0)
+        self.records.append((rows, cols, rank, junk, gap))
+        return junk
+
+    def __enter__(self):
+        self.lib.orc_set_gauge_probe(self._cb, int(self.gate_without))
+        return self
+
+    def __exit__(self, *a):
+        self.lib.orc_set_gauge_probe(_PROBE_T(), 0)
+        return False
+
+    def junk(self):
+        return np.array([r[3] for r in self.records])
+
+
 class OracleContext(object):
-    def __init__(self, o, **_unused):
-        self.lib = lib()
+    def __init__(self, o, variant=None, **_unused):
+        self.lib = variant if variant is not None else lib()
         self.h = C.c_void_p(self.lib.orc_create(int(o["do_fej"]), int(o["use_rk4_integration"]), int(o["imu_avg"]),
                                                 int(o["do_calib_camera_pose"]), int(o["do_calib_camera_intrinsics"]),
                                                 int(o["do_calib_camera_timeoffset"]), int(o["max_clone_size"]),

@@ -28,6 +28,22 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
 
 
+def test_product_library_exports_only_the_declared_abi():
+    """libovp.so exports exactly the symbols of include/ovp.h: no test / tuning hooks (those live in libovp_debug.so and are
+    declared in include/ovp_debug.h)."""
+    import subprocess
+    from ov_plane_b200 import api
+    out = subprocess.check_output(["nm", "-D", "--defined-only", api.LIB_PATH]).decode()
+    exported = sorted(set(re.findall(r"\b T (ovp_[a-z0-9_]+)$", out, flags=re.M)))
+    assert exported == declared_symbols(), sorted(set(exported) ^ set(declared_symbols()))
+    txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ovp_debug.h")).read(), flags=re.S)
+    hooks = sorted(set(re.findall(r"\b(ovp_debug_[a-z0-9_]+)\s*\(", txt)))
+    assert len(hooks) >= 5
+    dbg = ctypes.CDLL(api.DEBUG_LIB_PATH)
+    assert not [h for h in hooks if not hasattr(dbg, h)]
+    assert not [s for s in declared_symbols() if not hasattr(dbg, s)]
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the product path must fail loudly, not fall back."""
     try:

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def ctx():
     S = synth.make_scenario("tiny_points")
-    c = api.Context(S.options, device=0, max_state=640, max_meas_rows=4096)
+    c = api.Context(S.options, device=0, max_state=640, max_meas_rows=4096, debug=True)  # libovp_debug.so: ovp_debug_chol_solve (include/ovp_debug.h)
     yield c
     c.close()
 

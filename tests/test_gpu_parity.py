@@ -150,23 +150,57 @@ def test_nullspace_and_compress_invariants(chi2_table):
     assert np.array_equal(gR, Hx) and np.array_equal(gz, res)
 
 
+def oracle_msckf_update(orc, batch, sigma_pix=1.0, mult=1.0):
+    """The oracle's UpdaterMSCKF::update with the plane chi2 of every gated plane split into its well-defined part and the
+    remainder carried by the rank-deficient rows the reference keeps (oracle.hpp GaugeProbe): the oracle gates on the
+    well-defined part, which is the quantity the CUDA path computes.  `plane_status_ref` / `plane_chi2_ref`: what the
+    unmodified reference gate says for the same systems (chi2 including the round-off defined rows)."""
+    import oracle_backend
+    with oracle_backend.GaugeProbe(gate_without=True) as gp:
+        o = orc.msckf_update(batch, sigma_pix, mult)
+    ids = np.asarray(batch["plane_ids"]).astype(np.int64)
+    order = [i for i in np.argsort(ids, kind="stable") if o["plane_status"][i] != -1]  # planes are visited in ascending id
+    junk = gp.junk()
+    assert len(junk) == len(order), (len(junk), len(order))
+    o["plane_chi2_ref"] = o["plane_chi2"].copy()
+    o["plane_chi2"] = o["plane_chi2"].copy()
+    o["plane_junk"] = np.zeros(len(ids))
+    for i, j in zip(order, junk):
+        o["plane_chi2"][i] -= j
+        o["plane_junk"][i] = j
+    o["probe_records"] = gp.records
+    for rows, cols, rank, _, gap in gp.records:
+        assert gap[0] > 1e-7 and gap[1] < 1e-12, "no clean rank gap in the compressed Jacobian: %s" % str(gap)
+    return o
+
+
 def _run_msckf(name, seed, chi2_table, mult=1.0, **kw):
     S = synth.make_scenario(name, seed=seed)
     ctx, orc, chg, cho = make_pair(S, chi2_table, **kw)
     g = ctx.msckf_update(synth.feature_batch(S, chg), 1.0, mult)
-    o = orc.msckf_update(synth.feature_batch(S, cho), 1.0, mult)
+    o = oracle_msckf_update(orc, synth.feature_batch(S, cho), 1.0, mult)
     return S, ctx, orc, chg, cho, g, o
 
 
-def _check_msckf(S, ctx, orc, chg, cho, g, o, tol=REL, chi_tol=1e-7):
+def _check_msckf(S, ctx, orc, chg, cho, g, o, tol=REL, chi_tol=1e-7, plane_chi_tol=1e-6):
     assert np.array_equal(g["feat_status"], o["feat_status"]), "accept/reject flags differ: %s" % str(
         np.nonzero(g["feat_status"] != o["feat_status"]))
-    assert np.array_equal(g["plane_status"], o["plane_status"])
-    m = o["feat_status"] != 2
+    assert np.array_equal(g["plane_status"], o["plane_status"]), (g["plane_status"], o["plane_status"])
+    m = (o["feat_status"] == 0) | (o["feat_status"] == 1)
     assert np.allclose(g["feat_chi2"][m], o["feat_chi2"][m], rtol=chi_tol, atol=0), np.abs(g["feat_chi2"][m] / o["feat_chi2"][m] - 1).max()
+    pm = o["plane_status"] != -1
+    if pm.any():
+        assert np.allclose(g["plane_chi2"][pm], o["plane_chi2"][pm], rtol=plane_chi_tol, atol=0), (g["plane_chi2"], o["plane_chi2"])
     # Hx_order (variable order of the final stacked system): indices must be identical
     assert [chg.index(h) if h in chg else -h - 1 for h in g["hx_order"]] == [cho.index(h) if h in cho else -h - 1 for h in o["hx_order"]]
     return compare_states(ctx, orc, S, chg, cho, tol)
+
+
+def _plane_report(tag, g, o, e):
+    pm = o["plane_status"] != -1
+    print(tag, "cov rel err %.3e" % e, "| plane chi2 gpu", np.round(g["plane_chi2"][pm], 3), "oracle well-defined", np.round(o["plane_chi2"][pm], 3),
+          "max rel diff %.2e" % (np.abs(g["plane_chi2"][pm] / o["plane_chi2"][pm] - 1).max() if pm.any() else 0.0),
+          "| reference chi2 incl. round-off rows", np.round(o["plane_chi2_ref"][pm], 2), "| status", g["plane_status"][pm])
 
 
 @pytest.mark.parametrize("name,seed", [("tiny_points", 0), ("tiny_points", 4), ("cfg1_euroc_n96", 0), ("cfg2_n256_f200", 0)])
@@ -176,28 +210,26 @@ def test_msckf_update_points(name, seed, chi2_table):
     print(name, seed, "cov rel err %.2e" % e, "accepted", int((g["feat_status"] == 1).sum()), "of", S.F)
 
 
-@pytest.mark.parametrize("name,seed", [("tiny_planes", 0), ("tiny_planes", 3), ("small_planes", 0), ("small_planes", 1)])
+@pytest.mark.parametrize("name,seed", [("tiny_planes", 0), ("tiny_planes", 3), ("small_planes", 0), ("small_planes", 1), ("small_planes", 2)])
 def test_msckf_update_planes(name, seed, chi2_table):
-    """In-state planes.  UpdaterPlane::measurement_compress_inplace drops rows whose H_x part is zero although their H_cp / res
-    parts are not (UpdaterPlane.cpp:545-551); with the exactly rank-deficient H_x of this path the 3 surviving 'arbitrary'
-    combinations are round-off defined in the reference itself — the CUDA path keeps none of them.  The gates and
-    the point-path quantities are still compared exactly; state / covariance within a band measured in DESIGN.md."""
+    """In-state planes: gates, plane chi2 (well-defined part, see oracle_msckf_update), per-feature chi2, Hx_order, state and
+    covariance at the north-star tolerance."""
     S, ctx, orc, chg, cho, g, o = _run_msckf(name, seed, chi2_table)
-    assert np.array_equal(g["plane_status"], o["plane_status"])
-    assert np.array_equal(g["feat_status"], o["feat_status"])
-    Pg, Po = ctx.cov(), orc.cov()
-    e = relerr(Pg, Po)
-    print(name, seed, "plane chi2 gpu", np.round(g["plane_chi2"], 2), "oracle", np.round(o["plane_chi2"], 2), "cov rel err %.3e" % e)
-    assert e < 5e-3
+    e = _check_msckf(S, ctx, orc, chg, cho, g, o)
+    _plane_report("%s %d" % (name, seed), g, o, e)
 
 
 def test_msckf_update_cfg3_full(chi2_table):
+    """The benchmarked workload (BASELINE config 3: N = 512, 600 features, 8 in-state planes): 8 sequential plane updates +
+    the point update, everything at the north-star tolerance."""
     S, ctx, orc, chg, cho, g, o = _run_msckf("cfg3_n512_f600_p8", 0, chi2_table)
-    assert np.array_equal(g["plane_status"], o["plane_status"])
-    assert np.array_equal(g["feat_status"], o["feat_status"])
-    e = relerr(ctx.cov(), orc.cov())
-    print("cfg3 cov rel err %.3e" % e, "launches", ctx.launch_count())
-    assert e < 5e-3
+    # the point features are gated against the posterior of the 8 plane updates (itself equal to the oracle's to ~3e-8), so their
+    # chi2 is compared at the north-star 1e-6 here instead of the 1e-7 of the single-update cases
+    e = _check_msckf(S, ctx, orc, chg, cho, g, o, chi_tol=1e-6)
+    m = (o["feat_status"] == 0) | (o["feat_status"] == 1)
+    print("cfg3 per-feature chi2 max rel diff %.2e" % np.abs(g["feat_chi2"][m] / o["feat_chi2"][m] - 1).max())
+    _plane_report("cfg3_n512_f600_p8 0", g, o, e)
+    print("cfg3 launches", ctx.launch_count(), "accepted point features", int((g["feat_status"] == 1).sum()))
 
 
 def test_msckf_update_cfg3_points_only(chi2_table):

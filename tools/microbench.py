@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from ov_plane_b200 import api, synth
 S = synth.make_scenario("tiny_points")
-ctx = api.Context(S.options, device=0, max_state=576, max_meas_rows=4096)
+ctx = api.Context(S.options, device=0, max_state=576, max_meas_rows=4096, debug=True)
 for n in (512, 1024, 2048, 4096):
     print("own DMMA gemm n=%d: %.2f TFLOP/s" % (n, ctx.selftest_dgemm_tflops(n, 5)))
 lat = np.zeros(16)

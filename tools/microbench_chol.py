@@ -7,7 +7,7 @@ from ov_plane_b200 import api, synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 474
 mrows = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 S = synth.make_scenario("tiny_points")
-ctx = api.Context(S.options, device=0, max_state=576, max_meas_rows=4096)
+ctx = api.Context(S.options, device=0, max_state=576, max_meas_rows=4096, debug=True)
 for (nn, mm) in ((n, 0), (n, mrows), (128, 0), (64, 0)):
     T = (nn + 63) // 64
     cap = 3 + 16 * (T * (T + 1) // 2 + 40) + 64

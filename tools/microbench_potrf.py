@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from ov_plane_b200 import api, synth
 S = synth.make_scenario("tiny_points")
-ctx = api.Context(S.options, device=0, max_state=128, max_meas_rows=4096)
+ctx = api.Context(S.options, device=0, max_state=128, max_meas_rows=4096, debug=True)
 names = ["0 smem broadcast (production)", "1 = 0 without panel/pivinv stores", "2 chain only via smem", "3 shuffle pivot + smem updates",
          "4 shuffle pivot chain only", "5 = 3 with double2 reads", "6 shuffle pivot + eager next entry", "7 = 6 software-pipelined", "8 pre-shuffled operands, fused shift (production)"]
 for v, nm in enumerate(names):

@@ -90,25 +90,51 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU algorithm (oracle restatement), all host cores = independent single-thread filters
 # ------------------------------------------------------------------------------------------------------------------------
-def _oracle_one_update(seed):
+def _oracle_filter(job):
+    """One single-thread reference filter pinned to one core: `warm` untimed + `steps` timed full updates of WORKLOAD (each from the
+    same prior).  Returns per-step wall times, the reference's own per-stage timers and the gate counts."""
+    seed, core, warm, steps = job
+    if core is not None:
+        try:
+            os.sched_setaffinity(0, {core})
+        except Exception:
+            pass
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_backend  # bench.py may execute oracle/ only in the cpu_baseline and --impl reference legs
     from ov_plane_b200 import synth
     S = synth.make_scenario(WORKLOAD, seed=seed)
-    o = oracle_backend.OracleContext(S.options)
-    o.set_chi2_table(synth.chi2_table())
-    ch = synth.load_scenario_into(o, S)
-    b = synth.feature_batch(S, ch)
-    t4 = np.zeros(4)
-    t0 = time.perf_counter()
-    r = o.msckf_update(b, 1.0, 1.0, timers=t4)
-    dt = time.perf_counter() - t0
-    o.close()
-    return dt, t4.tolist(), int((r["feat_status"] == 1).sum())
+    chi2 = synth.chi2_table()
+    times, stages, acc, planes = [], [], 0, 0
+    for it in range(warm + steps):
+        o = oracle_backend.OracleContext(S.options)
+        o.set_chi2_table(chi2)
+        ch = synth.load_scenario_into(o, S)
+        b = synth.feature_batch(S, ch)
+        t4 = np.zeros(4)
+        t0 = time.perf_counter()
+        r = o.msckf_update(b, 1.0, 1.0, timers=t4)
+        dt = time.perf_counter() - t0
+        o.close()
+        if it >= warm:
+            times.append(dt)
+            stages.append(t4.tolist())
+        acc, planes = int((r["feat_status"] == 1).sum()), int((r["plane_status"] == 1).sum())
+    return times, stages, acc, planes, S.N, S.F
+
+
+def workload_config(state_N, features, accepted, planes_passed):
+    """The SAME object on the GPU line and on the reference line (the driver compares the two)."""
+    return {"workload": WORKLOAD, "state_N": state_N, "features": features, "obs_per_feature": 20, "planes_in_state": 8,
+            "accepted_point_features": accepted, "planes_passed": planes_passed,
+            "parallelism": "replicas only (the per-plane update chain is sequential): one independent filter per GPU on the GPU arm, one "
+                           "single-thread filter per pinned host core on the reference arm, N of them for --gpus N",
+            "l2": "GPU arm: flushed between timed steps (256 MB write); reference arm: host caches, every step starts from a fresh state",
+            "step": "restore(P, x) + 8 plane updates + 1 point update"}
 
 
 def cpu_baseline_single():
-    dt, t4, acc = _oracle_one_update(0)
+    times, stages, acc, planes, N, F = _oracle_filter((0, None, 0, 1))
+    dt, t4 = times[0], stages[0]
     return {"value": 1.0 / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": "1 full %s update, single thread, oracle restatement of the reference's Givens/Eigen-order algorithm "
                       "(reference flags -O3, no Eigen available): %.2f s = plane updates %.2f + feature system %.2f + compression %.2f + "
@@ -116,51 +142,48 @@ def cpu_baseline_single():
 
 
 def run_reference(args):
-    """The reference's update path is single-threaded, so "all the host threads it can use" = independent
-    filters side by side.  Its Givens sweeps stream a ~150 MB matrix per filter, so concurrency is memory-bound: time 1 filter and
-    W concurrent filters and report whichever configuration gives the higher aggregate throughput."""
+    """The reference's update path is single-threaded.  Like the GPU arm (one filter replica per GPU, weak scaling),
+    `--gpus N` runs exactly N concurrent single-thread filters, each pinned to its own core, each doing `warmup` untimed and `steps`
+    timed full updates; value = sum over filters of 1 / median(step time).  If `steps` would not fit the time budget it is reduced
+    and the line says so (`steps` is the number actually timed)."""
     rank = env_int("RANK", 0)
     if rank != 0:
         return
     import multiprocessing as mp
     try:
-        avail = len(os.sched_getaffinity(0))
+        avail = sorted(os.sched_getaffinity(0))
     except Exception:
-        avail = os.cpu_count() or 1
-    budget = 150.0
-    t_begin = time.perf_counter()
-    single = []
-    n_total = max(1, args.steps)
-    while len(single) < n_total and (time.perf_counter() - t_begin) < budget * 0.5:
-        dt, _, _ = _oracle_one_update(0)
-        single.append(dt)
-        if len(single) >= 3:
-            break
-    t1 = float(np.mean(single))
-    best = {"cores": 1, "ms": 1e3 * t1, "value": 1.0 / t1, "steps": len(single)}
-    W = max(1, min(avail, 8))
-    if W > 1 and (time.perf_counter() - t_begin) + 4 * t1 < budget:
-        ctx = mp.get_context("spawn")
-        pool = ctx.Pool(W)
-        pool.map(_oracle_one_update, list(range(W)))  # spawn + import warm-up round
-        t0 = time.perf_counter()
-        pool.map(_oracle_one_update, list(range(W)))
-        tW = time.perf_counter() - t0
-        pool.close()
-        if W / tW > best["value"]:
-            best = {"cores": W, "ms": 1e3 * tW, "value": W / tW, "steps": 1}
-        multi_note = "; %d concurrent filters took %.1f s (%.3f updates/s)" % (W, tW, W / tW)
-    else:
-        multi_note = ""
-    line = {"impl": "reference", "metric": METRIC, "value": best["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": best["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "each step = %d concurrent single-thread filter(s), each running one full update" %
-                                                    best["cores"]},
-            "cpu_baseline": {"value": best["value"], "unit": UNIT, "cores": best["cores"], "kind": "port",
-                             "sample": "%d timed step(s) of the full %s update, bounded to ~%.0f s; 1 filter alone: %.2f s per update%s; "
-                                       "host threads available: %d" % (best["steps"], WORKLOAD, budget, t1, multi_note, avail)},
-            "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        avail = list(range(os.cpu_count() or 1))
+    nf = max(1, min(args.gpus, len(avail)))
+    cores = [avail[(i * len(avail)) // nf] for i in range(nf)]
+    budget = 240.0
+    # one untimed probe update on the first core sizes the run
+    t_probe = _oracle_filter((0, cores[0], 0, 1))[0][0]
+    warm = max(0, min(args.warmup, 1 if t_probe * (args.warmup + args.steps) > budget else args.warmup))
+    steps = max(3, min(args.steps, int((budget - t_probe) / t_probe) - warm))
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(nf) as pool:
+        res = pool.map(_oracle_filter, [(i, cores[i], warm, steps) for i in range(nf)])
+    wall = time.perf_counter() - t0
+    med = [float(np.median(r[0])) for r in res]
+    allt = np.concatenate([np.asarray(r[0]) for r in res])
+    value = float(sum(1.0 / m for m in med))
+    st = np.median(np.concatenate([np.asarray(r[1]) for r in res]), axis=0)
+    acc, planes, N, F = res[0][2], res[0][3], res[0][4], res[0][5]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": 1e3 * nf / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(N, F, acc, planes),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nf, "kind": "port",
+                             "sample": "%d filter(s) x (%d warm-up + %d timed) full %s updates, oracle restatement of the reference's "
+                                       "Givens/Eigen-order algorithm built with the reference's flags (no Eigen in this image); requested steps %d"
+                                       % (nf, warm, steps, WORKLOAD, args.steps)},
+            "step_seconds": {"median": float(np.median(allt)), "p95": float(np.percentile(allt, 95)), "min": float(allt.min()),
+                             "max": float(allt.max()), "per_filter_median": med},
+            "stage_seconds_median": {"plane_updates": float(st[0]), "feature_system": float(st[1]), "compression": float(st[2]),
+                                     "ekf_update": float(st[3])},
+            "host": {"cores_available": len(avail), "cores_used": cores, "wall_s": wall},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
 
@@ -200,6 +223,14 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def gather_over_ranks(x):
+        if dist is None:
+            return [x]
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
 
     def sum_over_ranks(x):
         if dist is None:
@@ -250,6 +281,7 @@ def main():
     clocks = sampler.stop()
     ctx.msckf_finish()
     step_ms = [a.elapsed_time(b) for a, b in ev]
+    per_rank_ms = gather_over_ranks(float(np.mean(step_ms)))
     ms_per_step = max_over_ranks(float(np.mean(step_ms)))
     value = world / (ms_per_step * 1e-3)
 
@@ -331,11 +363,8 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "state_N": S.N, "features": S.F, "obs_per_feature": 20, "planes_in_state": len(S.planes),
-                       "accepted_point_features": accepted, "planes_passed": planes_passed,
-                       "parallelism": "1 filter replica per GPU (replicas only; the per-plane update chain is sequential)",
-                       "l2": "flushed between timed steps (256 MB write)", "step": "restore(P, x) + 8 plane updates + 1 point update"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof}
+            "config": workload_config(S.N, S.F, accepted, planes_passed),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "per_rank_ms_per_step": per_rank_ms}
 
     # ---- throughput mode: C independent filters on ONE GPU, one stream + one CUDA graph each (the update chain of a single filter
     #      is latency-bound and occupies a few SMs at a time; independent filters fill the rest of the chip) ----
@@ -410,19 +439,24 @@ def main():
     except Exception as e:
         line["propagation"] = {"error": repr(e)}
 
-    # ---- sharded large update (cfg5: 4000 features sharded over the ranks, one NCCL all-gather of [R z]) ----
-    if world > 1 and not args.no_sharded:
+    # ---- sharded large update (cfg5: 4000 features sharded over the ranks; the library owns the NCCL communicator and runs ONE
+    #      all-gather of the packed rank-local Gram matrices inside ovp_msckf_update_sharded) - reported at N = 1 as well ----
+    if not args.no_sharded:
         try:
             S5 = synth.make_scenario("cfg5_n512_f4000", seed=0)
             c5 = api.Context(S5.options, device=local, max_state=576, max_meas_rows=160000)
             c5.set_chi2_table(chi2)
             ch5 = synth.load_scenario_into(c5, S5)
             c5.snapshot()
+            # rank 0 creates the communicator id; torch.distributed only carries the 128 bytes to the peers (plumbing)
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(c5.nccl_unique_id()), dtype=torch.uint8))
+            if dist is not None:
+                dist.broadcast(idt, 0)
+            c5.nccl_init(bytes(idt.cpu().numpy().tobytes()), world, rank)
             mine = [i for i in range(S5.F) if i % world == rank]
             b5 = synth.feature_batch(S5, ch5, mine)
-            n = c5.msckf_shard_columns(ch5)
-            blk = torch.zeros((n + 1) * (n + 1), dtype=torch.float64, device="cuda")
-            allb = torch.zeros(world * (n + 1) * (n + 1), dtype=torch.float64, device="cuda")
             s5 = torch.cuda.ExternalStream(c5.stream(), device=torch.device("cuda", local))
             ts = []
             for it in range(3 + min(args.steps, 10)):
@@ -431,18 +465,20 @@ def main():
                 t0 = torch.cuda.Event(enable_timing=True)
                 t1 = torch.cuda.Event(enable_timing=True)
                 t0.record(s5)
-                c5.msckf_shard_compress(b5, ch5, blk.data_ptr(), 1.0, 1.0)
-                with torch.cuda.stream(s5):
-                    dist.all_gather_into_tensor(allb, blk)
-                c5.msckf_update_gathered(allb.data_ptr(), world, ch5)
+                c5.msckf_update_sharded(b5, ch5, 1.0, 1.0)
                 t1.record(s5)
                 barrier()
                 if it >= 3:
                     ts.append(t0.elapsed_time(t1))
             sms = max_over_ranks(float(np.mean(ts)))
-            line["sharded_cfg5"] = {"workload": "cfg5_n512_f4000 (4000 features / %d ranks, all-gather of %d [R z] blocks of %d doubles)" %
-                                    (world, world, (n + 1) * (n + 1)), "ms_per_update": sms, "updates_per_s": 1e3 / sms,
-                                    "collective": "ncclAllGather via torch.distributed"}
+            n5 = c5.msckf_shard_columns(ch5)
+            line["sharded_cfg5"] = {"workload": "cfg5_n512_f4000 (4000 features / %d ranks)" % world, "ms_per_update": sms, "updates_per_s": 1e3 / sms,
+                                    "collective": "ncclAllGather of %d packed lower triangles of %d doubles, issued by the library on the ctx's own "
+                                                  "communicator (ovp_msckf_update_sharded); summed in rank order, update replicated" %
+                                                  (world, (n5 + 1) * (n5 + 2) // 2),
+                                    "timing": "CUDA events on the library stream around the whole call (host plan + H2D + kernels + collective), "
+                                              "max over ranks"}
+            c5.nccl_finalize()
             c5.close()
         except Exception as e:  # the replica line above stays valid
             line["sharded_cfg5"] = {"error": repr(e)}

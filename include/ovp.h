@@ -216,6 +216,19 @@ int ovp_msckf_shard_compress(ovp_ctx *ctx, const ovp_feature_batch *batch, const
                              const int *all_clone_handles, int n_clones, double *d_out, int *feat_status, double *feat_chi2);
 int ovp_msckf_update_gathered(ovp_ctx *ctx, const double *d_blocks, int G, const int *all_clone_handles, int n_clones);
 
+/* The same update with the collective INSIDE the library (what a C++ host such as VioManager calls): the context owns an NCCL
+ * communicator (libnccl.so.2 is dlopen'ed on first use).  Rank 0 obtains a 128-byte id with ovp_nccl_unique_id and hands it to its
+ * peers by any means (MPI, a file, a socket); every rank then calls ovp_nccl_init(id, nranks, rank).  ovp_msckf_update_sharded is
+ * collective: every rank passes ITS features (F may be 0) and the same all_clone_handles; rank-local Jacobians, gates and Gram
+ * matrix, ONE ncclAllGather of the packed lower triangles ((n+1)(n+2)/2 doubles per rank) over NVLink, the sum in rank order
+ * (bit-identical on every rank), one compression + EKF update replicated on every rank.  feat_status / feat_chi2: this rank's
+ * features. */
+int ovp_nccl_unique_id(ovp_ctx *ctx, char id128[128]);
+int ovp_nccl_init(ovp_ctx *ctx, const char id128[128], int nranks, int rank);
+int ovp_nccl_finalize(ovp_ctx *ctx);
+int ovp_msckf_update_sharded(ovp_ctx *ctx, const ovp_feature_batch *local_batch, const ovp_updater_options *opt, const int *all_clone_handles,
+                             int n_clones, int *feat_status, double *feat_chi2);
+
 /* ---- Propagator (state/Propagator.cpp) ------------------------------------------------------------------------------- */
 int ovp_propagator_set_noise(ovp_ctx *ctx, double sigma_w, double sigma_wb, double sigma_a, double sigma_ab,
                              double gravity_mag);                       /* NoiseManager.h:41-63, Propagator.h:57-64 */
@@ -227,6 +240,35 @@ int ovp_propagate_and_clone(ovp_ctx *ctx, double timestamp, double *Phi15, doubl
  * state_plus13 = [q_GtoI(4) p_IinG(3) v_IinI(3) w_IinI(3)], cov144 = 12 x 12 column-major over [theta p v_local w];
  * *ok = 0 when fewer than two IMU samples cover [state time, timestamp] (the reference returns false). */
 int ovp_fast_state_propagate(ovp_ctx *ctx, double timestamp, double *state_plus13, double *cov144, int *ok);
+
+/* ---- Triangulation on the device: the step right before the path (UpdaterMSCKF.cpp:142-194, UpdaterSLAM.cpp:118-160) ---- */
+/* ov_core FeatureInitializerOptions (defaults of OpenVINS @74a63cf when opt == NULL) */
+typedef struct ovp_triangulation_options {
+  int max_runs;
+  double init_lamda, max_lamda, min_dx, min_dcost, lam_mult, min_dist, max_dist, max_baseline, max_cond_number;
+} ovp_triangulation_options;
+/* FeatureInitializer::single_triangulation + single_gaussnewton for F features at once, against the clone and extrinsics values
+ * that live in the context: meas_offset / meas_clone as in ovp_feature_batch (measurements in time order: the anchor is the last
+ * one), uv_norm = Feature::uvs_norm (undistorted normalised coordinates, 2 floats per measurement).  status[f] = 1: p_FinG[3f..]
+ * is the refined position; 0: the reference would drop the feature (condition number, depth range, baseline ratio, NaN). */
+int ovp_triangulate_features(ovp_ctx *ctx, int F, const int *meas_offset, const int *meas_clone, const float *uv_norm,
+                             const ovp_triangulation_options *opt, double *p_FinG, int *status);
+
+/* ---- UpdaterZeroVelocity (update/UpdaterZeroVelocity.cpp:68-318) ------------------------------------------------------- */
+typedef struct ovp_zupt_options {
+  double gravity_mag;           /* VioManagerOptions.h:206 */
+  double zupt_max_velocity;     /* reject when |v_IinG| is above (unless the disparity check passes) */
+  double zupt_noise_multiplier; /* R *= multiplier (:176-178) */
+  double zupt_max_disparity;    /* average pixel disparity below which the platform counts as stationary (:219) */
+  double chi2_multipler;        /* UpdaterOptions::chi2_multipler */
+} ovp_zupt_options;
+/* UpdaterZeroVelocity::feed_imu: the ZUPT updater keeps its own IMU buffer (noises: ovp_propagator_set_noise) */
+int ovp_zupt_feed_imu(ovp_ctx *ctx, double timestamp, const double wm[3], const double am[3]);
+/* try_update: average_disparity / num_features are the outputs of FeatureHelper::compute_disparity between the state time and
+ * `timestamp` (front end, upstream).  *accepted = 1: the zero-velocity update was applied (bias propagation + EKFUpdate with the
+ * diagonal R) and the state time moved to `timestamp`; 0: nothing was touched, do the normal propagate + clone. */
+int ovp_zupt_try_update(ovp_ctx *ctx, const ovp_zupt_options *opt, double timestamp, double average_disparity, int num_features,
+                        int *accepted, double *chi2);
 
 /* Split form of ovp_msckf_update for callers that keep one feature batch resident on the device: prepare = validation,
  * planning and the single host->device copy; launch = kernels only (asynchronous, repeatable: the state changes, the plan

@@ -2187,4 +2187,266 @@ struct Propagator {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// UpdaterZeroVelocity::try_update (update/UpdaterZeroVelocity.cpp:68-318) with the flags the reference hard-codes
+// (:113-116: integrated_accel_constraint = false, model_time_varying_bias = true, override_with_disparity_check = true,
+// explicitly_enforce_zero_motion = false).  FeatureHelper::compute_disparity (ov_core, front end) is upstream: its outputs
+// arrive as inputs.  H_order is {q, bg, ba} of the IMU (:119-121); the oracle's Var has no sub-variables, so H is laid out
+// over the whole IMU variable (15 columns, zeros for p and v) - the zero columns add exact zeros to every product of
+// EKFUpdate.  The bias propagation EKFPropagation({bg, ba}, {bg, ba}, I, Q_bias) (:253-259) with Phi = I changes exactly
+// the six diagonal entries P_ii += Q_ii (StateHelper.cpp:85-105: C = P[:, new] I, D = Q + I C[new rows]).
+// ---------------------------------------------------------------------------------------------------------------
+struct UpdaterZeroVelocity {
+  NoiseManager _noises;
+  Mat _gravity = vec3(0, 0, 9.81);
+  double _zupt_max_velocity = 1.0, _zupt_noise_multiplier = 1.0, _zupt_max_disparity = 1.0, chi2_multipler = 1.0;
+  std::vector<ImuData> imu_data;
+  double last_prop_time_offset = 0.0;
+  bool have_last_prop_time_offset = false;
+  double last_zupt_state_timestamp = 0.0;
+  double last_chi2 = 0.0;
+
+  bool try_update(StateP state, double timestamp, double average_disparity, int num_features, const Chi2Table &chi2tab) {
+    if (imu_data.empty()) {
+      last_zupt_state_timestamp = 0.0;
+      return false;
+    }
+    if (state->_timestamp == timestamp) {
+      last_zupt_state_timestamp = 0.0;
+      return false;
+    }
+    const double dtv = state->_calib_dt_CAMtoIMU->value[0];
+    if (!have_last_prop_time_offset) {
+      last_prop_time_offset = dtv;
+      have_last_prop_time_offset = true;
+    }
+    double t_off_new = dtv;
+    double time0 = state->_timestamp + last_prop_time_offset;
+    double time1 = timestamp + t_off_new;
+    std::vector<ImuData> imu_recent = Propagator::select_imu_readings(imu_data, time0, time1);
+    last_prop_time_offset = t_off_new;
+    if (imu_recent.size() < 2) {
+      last_zupt_state_timestamp = 0.0;
+      return false;
+    }
+    VarP imu = state->_imu;
+    int h_size = 15;
+    int m_size = 6 * ((int)imu_recent.size() - 1);
+    Mat H(m_size, h_size), res(m_size, 1);
+    Mat R = Mat::Identity(m_size);
+    double dt_summed = 0;
+    for (size_t i = 0; i + 1 < imu_recent.size(); i++) {
+      double dt = imu_recent.at(i + 1).timestamp - imu_recent.at(i).timestamp;
+      Mat a_hat = imu_recent.at(i).am - imu->bias_a();
+      Mat r_w = -1.0 * (imu_recent.at(i).wm - imu->bias_g());
+      Mat r_a = -1.0 * (a_hat - imu->Rot() * _gravity);
+      for (int j = 0; j < 3; j++) {
+        res((int)(6 * i) + j, 0) = r_w(j, 0);
+        res((int)(6 * i) + 3 + j, 0) = r_a(j, 0);
+      }
+      Mat R_GtoI_jacob = state->_options.do_fej ? imu->Rot_fej() : imu->Rot();
+      Mat sk = -1.0 * skew_x(R_GtoI_jacob * _gravity);
+      for (int j = 0; j < 3; j++) {
+        H((int)(6 * i) + j, 9 + j) = -1.0; // d w / d bg   (:164; bg = IMU columns 9..11)
+        for (int l = 0; l < 3; l++)
+          H((int)(6 * i) + 3 + j, l) = sk(j, l); // d a / d theta (:166)
+        H((int)(6 * i) + 3 + j, 12 + j) = -1.0;  // d a / d ba    (:167; ba = IMU columns 12..14)
+      }
+      for (int j = 0; j < 3; j++) {
+        R((int)(6 * i) + j, (int)(6 * i) + j) *= _noises.sigma_w * _noises.sigma_w / dt;
+        R((int)(6 * i) + 3 + j, (int)(6 * i) + 3 + j) *= _noises.sigma_a * _noises.sigma_a / dt;
+      }
+      dt_summed += dt;
+    }
+    R = _zupt_noise_multiplier * R;
+    double Qb[6];
+    for (int j = 0; j < 3; j++) {
+      Qb[j] = dt_summed * _noises.sigma_wb; // the reference multiplies by sigma_wb / sigma_ab here, NOT by their squares (:186-187):
+      Qb[3 + j] = dt_summed * _noises.sigma_ab; // a property of the reference that parity has to reproduce
+    }
+    std::vector<VarP> Hx_order = {imu};
+    Mat P_marg = StateHelper::get_marginal_covariance(state, Hx_order);
+    for (int j = 0; j < 6; j++)
+      P_marg(9 + j, 9 + j) += Qb[j];
+    Mat S = H * P_marg * H.T() + R;
+    Mat L;
+    if (!chol_lower(S, L))
+      ref_exit("UpdaterZeroVelocity: S not positive definite");
+    Mat y = res;
+    chol_solve_inplace(L, y);
+    double chi2 = dot(res, y);
+    last_chi2 = chi2;
+    double chi2_check = chi2tab.at(res.rows());
+    bool disparity_passed = (average_disparity < _zupt_max_disparity && num_features > 20); // :219
+    if (!disparity_passed && (chi2 > chi2_multipler * chi2_check || imu->vel().norm() > _zupt_max_velocity)) {
+      last_zupt_state_timestamp = 0.0;
+      return false;
+    }
+    // accepted: propagate the biases (Phi = I, see the header comment), then update with the IMU measurements
+    const int ib = imu->id + 9;
+    for (int j = 0; j < 6; j++) {
+      state->_Cov(ib + j, ib + j) += Qb[j];
+      if (state->_Cov(ib + j, ib + j) < 0.0)
+        ref_exit("EKFPropagation: negative diagonal");
+    }
+    StateHelper::EKFUpdate(state, Hx_order, H, res, R);
+    state->_timestamp = timestamp;
+    last_zupt_state_timestamp = timestamp;
+    return true;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// ov_core::FeatureInitializer::single_triangulation + single_gaussnewton (OpenVINS @74a63cf, NOT under /root/reference:
+// restated from the published algorithm; call sites UpdaterMSCKF.cpp:142-194, UpdaterSLAM.cpp:118-160).  Dense Mat arithmetic,
+// inverse by cofactors, extreme singular values by cyclic Jacobi - deliberately different numerics from the CUDA path's
+// closed forms (parity unpinned by the reference: this checks the restatement against itself in two formulations).
+// ---------------------------------------------------------------------------------------------------------------
+struct FeatureInitializerOptions {
+  int max_runs = 5;
+  double init_lamda = 1e-3, max_lamda = 1e10, min_dx = 1e-6, min_dcost = 1e-6, lam_mult = 10, min_dist = 0.10, max_dist = 60, max_baseline = 40,
+         max_cond_number = 10000;
+};
+struct FeatureInitializer {
+  FeatureInitializerOptions _options;
+  struct ClonePose {
+    Mat R, p;
+  };
+  static void sym_eig_minmax(Mat A, double &emin, double &emax) { // cyclic Jacobi on a symmetric 3x3
+    for (int sweep = 0; sweep < 30; sweep++)
+      for (int p = 0; p < 3; p++)
+        for (int q = p + 1; q < 3; q++) {
+          if (std::abs(A(p, q)) < 1e-300)
+            continue;
+          double th = 0.5 * std::atan2(2 * A(p, q), A(q, q) - A(p, p));
+          double c = std::cos(th), s = std::sin(th);
+          Mat J = Mat::Identity(3);
+          J(p, p) = c;
+          J(q, q) = c;
+          J(p, q) = s;
+          J(q, p) = -s;
+          A = J.T() * A * J;
+        }
+    emin = std::min(A(0, 0), std::min(A(1, 1), A(2, 2)));
+    emax = std::max(A(0, 0), std::max(A(1, 1), A(2, 2)));
+  }
+  double compute_error(const std::vector<ClonePose> &cams, const std::vector<float> &uvn, double alpha, double beta, double rho) const {
+    double err = 0;
+    const Mat &R_GtoA = cams.back().R;
+    const Mat &p_AinG = cams.back().p;
+    for (size_t m = 0; m < cams.size(); m++) {
+      Mat R_AtoCi = cams[m].R * R_GtoA.T();
+      Mat p_CiinA = R_GtoA * (cams[m].p - p_AinG);
+      Mat p_AinCi = -1.0 * (R_AtoCi * p_CiinA);
+      double hi1 = R_AtoCi(0, 0) * alpha + R_AtoCi(0, 1) * beta + R_AtoCi(0, 2) + rho * p_AinCi(0, 0);
+      double hi2 = R_AtoCi(1, 0) * alpha + R_AtoCi(1, 1) * beta + R_AtoCi(1, 2) + rho * p_AinCi(1, 0);
+      double hi3 = R_AtoCi(2, 0) * alpha + R_AtoCi(2, 1) * beta + R_AtoCi(2, 2) + rho * p_AinCi(2, 0);
+      float z0 = (float)(hi1 / hi3), z1 = (float)(hi2 / hi3);
+      float r0 = uvn[2 * m] - z0, r1 = uvn[2 * m + 1] - z1;
+      float n = std::sqrt(r0 * r0 + r1 * r1);
+      err += std::pow(n, 2);
+    }
+    return err;
+  }
+  bool triangulate_and_refine(const std::vector<ClonePose> &cams, const std::vector<float> &uvn, Mat &p_FinG) const {
+    const Mat &R_GtoA = cams.back().R;
+    const Mat &p_AinG = cams.back().p;
+    Mat A(3, 3), b(3, 1);
+    for (size_t m = 0; m < cams.size(); m++) {
+      Mat R_AtoCi = cams[m].R * R_GtoA.T();
+      Mat p_CiinA = R_GtoA * (cams[m].p - p_AinG);
+      Mat b_i = R_AtoCi.T() * vec3(uvn[2 * m], uvn[2 * m + 1], 1.0);
+      b_i = (1.0 / b_i.norm()) * b_i;
+      Mat Bperp = skew_x(b_i);
+      Mat Ai = Bperp.T() * Bperp;
+      A = A + Ai;
+      b = b + Ai * p_CiinA;
+    }
+    Mat p_f = inverse_small(A) * b;
+    double emin, emax;
+    sym_eig_minmax(A, emin, emax);
+    double condA = emax / emin;
+    if (std::abs(condA) > _options.max_cond_number || p_f(2, 0) < _options.min_dist || p_f(2, 0) > _options.max_dist || std::isnan(p_f.norm()))
+      return false;
+    double rho = 1 / p_f(2, 0), alpha = p_f(0, 0) / p_f(2, 0), beta = p_f(1, 0) / p_f(2, 0);
+    double lam = _options.init_lamda, eps = 10000;
+    int runs = 0;
+    bool recompute = true;
+    double cost_old = compute_error(cams, uvn, alpha, beta, rho);
+    Mat Hess(3, 3), grad(3, 1);
+    while (runs < _options.max_runs && lam < _options.max_lamda && eps > _options.min_dx) {
+      if (recompute) {
+        Hess = Mat(3, 3);
+        grad = Mat(3, 1);
+        for (size_t m = 0; m < cams.size(); m++) {
+          Mat R_AtoCi = cams[m].R * R_GtoA.T();
+          Mat p_CiinA = R_GtoA * (cams[m].p - p_AinG);
+          Mat p_AinCi = -1.0 * (R_AtoCi * p_CiinA);
+          double hi1 = R_AtoCi(0, 0) * alpha + R_AtoCi(0, 1) * beta + R_AtoCi(0, 2) + rho * p_AinCi(0, 0);
+          double hi2 = R_AtoCi(1, 0) * alpha + R_AtoCi(1, 1) * beta + R_AtoCi(1, 2) + rho * p_AinCi(1, 0);
+          double hi3 = R_AtoCi(2, 0) * alpha + R_AtoCi(2, 1) * beta + R_AtoCi(2, 2) + rho * p_AinCi(2, 0);
+          Mat H(2, 3);
+          H(0, 0) = (R_AtoCi(0, 0) * hi3 - hi1 * R_AtoCi(2, 0)) / (std::pow(hi3, 2));
+          H(0, 1) = (R_AtoCi(0, 1) * hi3 - hi1 * R_AtoCi(2, 1)) / (std::pow(hi3, 2));
+          H(0, 2) = (p_AinCi(0, 0) * hi3 - hi1 * p_AinCi(2, 0)) / (std::pow(hi3, 2));
+          H(1, 0) = (R_AtoCi(1, 0) * hi3 - hi2 * R_AtoCi(2, 0)) / (std::pow(hi3, 2));
+          H(1, 1) = (R_AtoCi(1, 1) * hi3 - hi2 * R_AtoCi(2, 1)) / (std::pow(hi3, 2));
+          H(1, 2) = (p_AinCi(1, 0) * hi3 - hi2 * p_AinCi(2, 0)) / (std::pow(hi3, 2));
+          float z0 = (float)(hi1 / hi3), z1 = (float)(hi2 / hi3);
+          Mat res(2, 1);
+          res(0, 0) = (double)(uvn[2 * m] - z0);
+          res(1, 0) = (double)(uvn[2 * m + 1] - z1);
+          grad = grad + H.T() * res;
+          Hess = Hess + H.T() * H;
+        }
+      }
+      Mat Hess_l = Hess;
+      for (int r = 0; r < 3; r++)
+        Hess_l(r, r) *= (1.0 + lam);
+      Mat dx = inverse_small(Hess_l) * grad;
+      double cost = compute_error(cams, uvn, alpha + dx(0, 0), beta + dx(1, 0), rho + dx(2, 0));
+      if (cost <= cost_old && (cost_old - cost) / cost_old < _options.min_dcost) {
+        alpha += dx(0, 0);
+        beta += dx(1, 0);
+        rho += dx(2, 0);
+        eps = 0;
+        break;
+      }
+      if (cost <= cost_old) {
+        recompute = true;
+        cost_old = cost;
+        alpha += dx(0, 0);
+        beta += dx(1, 0);
+        rho += dx(2, 0);
+        runs++;
+        lam = lam / _options.lam_mult;
+        eps = dx.norm();
+      } else {
+        recompute = false;
+        lam = lam * _options.lam_mult;
+        continue;
+      }
+    }
+    Mat p_FinA = vec3(alpha / rho, beta / rho, 1 / rho);
+    // tangent plane of the bearing: the two directions orthogonal to p_FinA (ov_core takes them from a Householder QR of p_FinA)
+    Mat n = (1.0 / p_FinA.norm()) * p_FinA;
+    Mat t1 = (std::abs(n(0, 0)) < 0.9) ? vec3(1, 0, 0) : vec3(0, 1, 0);
+    t1 = t1 - dot(t1, n) * n;
+    t1 = (1.0 / t1.norm()) * t1;
+    Mat t2 = skew_x(n) * t1;
+    double base_line_max = 0.0;
+    for (size_t m = 0; m < cams.size(); m++) {
+      Mat p_CiinA = R_GtoA * (cams[m].p - p_AinG);
+      double base_line = std::sqrt(std::pow(dot(t1, p_CiinA), 2) + std::pow(dot(t2, p_CiinA), 2));
+      if (base_line > base_line_max)
+        base_line_max = base_line;
+    }
+    if (p_FinA(2, 0) < _options.min_dist || p_FinA(2, 0) > _options.max_dist || (p_FinA.norm() / base_line_max) > _options.max_baseline ||
+        std::isnan(p_FinA.norm()))
+      return false;
+    p_FinG = R_GtoA.T() * p_FinA + p_AinG;
+    return true;
+  }
+};
+
 } // namespace orc

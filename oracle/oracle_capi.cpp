@@ -12,6 +12,7 @@ struct Ctx {
   Chi2Table chi2;
   std::string last_error;
   Propagator prop;
+  UpdaterZeroVelocity zupt;
   MsckfResult last_msckf;
 };
 inline Mat from_colmajor(const double *p, int r, int c) {
@@ -667,5 +668,61 @@ void orc_var_update(int kind, double *value, const double *dx) {
   v.value.assign(value, value + nv);
   v.update(dx);
   std::copy(v.value.begin(), v.value.end(), value);
+}
+
+// ---- UpdaterZeroVelocity ----
+void orc_zupt_set(void *p, double sigma_w, double sigma_wb, double sigma_a, double sigma_ab, double gravity_mag, double max_velocity,
+                  double noise_multiplier, double max_disparity, double chi2_mult) {
+  Ctx *c = (Ctx *)p;
+  c->zupt._noises.sigma_w = sigma_w;
+  c->zupt._noises.sigma_wb = sigma_wb;
+  c->zupt._noises.sigma_a = sigma_a;
+  c->zupt._noises.sigma_ab = sigma_ab;
+  c->zupt._gravity = vec3(0, 0, gravity_mag);
+  c->zupt._zupt_max_velocity = max_velocity;
+  c->zupt._zupt_noise_multiplier = noise_multiplier;
+  c->zupt._zupt_max_disparity = max_disparity;
+  c->zupt.chi2_multipler = chi2_mult;
+}
+void orc_zupt_feed_imu(void *p, double t, const double *wm, const double *am) {
+  Ctx *c = (Ctx *)p;
+  ImuData d;
+  d.timestamp = t;
+  d.wm = vec3(wm[0], wm[1], wm[2]);
+  d.am = vec3(am[0], am[1], am[2]);
+  c->zupt.imu_data.push_back(d);
+}
+int orc_zupt_try_update(void *p, double timestamp, double average_disparity, int num_features, int *accepted, double *chi2) {
+  Ctx *c = (Ctx *)p;
+  return guarded(c, [&] {
+    *accepted = c->zupt.try_update(c->state, timestamp, average_disparity, num_features, c->chi2) ? 1 : 0;
+    *chi2 = c->zupt.last_chi2;
+  });
+}
+
+// ---- FeatureInitializer (ov_core, restated) ----
+int orc_triangulate_features(void *p, int F, const int *meas_offset, const int *meas_clone, const float *uv_norm, double *p_FinG, int *status) {
+  Ctx *c = (Ctx *)p;
+  return guarded(c, [&] {
+    FeatureInitializer fi;
+    VarP calib = c->state->_calib_IMUtoCAM;
+    for (int f = 0; f < F; f++) {
+      std::vector<FeatureInitializer::ClonePose> cams;
+      std::vector<float> uvn;
+      for (int k = meas_offset[f]; k < meas_offset[f + 1]; k++) {
+        VarP cl = c->state->by_handle.at(meas_clone[k]);
+        FeatureInitializer::ClonePose cp;
+        cp.R = calib->Rot() * cl->Rot(); // UpdaterMSCKF.cpp:131-132
+        cp.p = cl->pos() - cp.R.T() * calib->pos();
+        cams.push_back(cp);
+        uvn.push_back(uv_norm[2 * k]);
+        uvn.push_back(uv_norm[2 * k + 1]);
+      }
+      Mat pf(3, 1);
+      status[f] = (cams.size() >= 2 && fi.triangulate_and_refine(cams, uvn, pf)) ? 1 : 0;
+      for (int i = 0; i < 3; i++)
+        p_FinG[3 * f + i] = status[f] ? pf(i, 0) : 0.0;
+    }
+  });
 }
 } // extern "C"

@@ -389,6 +389,28 @@ class Context(object):
         self._ck(self.lib.ovp_msckf_shard_compress(self.h, C.byref(fb), C.byref(uo), _p(ch), len(ch), C.c_void_p(d_out_ptr), _p(fs), _p(fc)))
         return dict(feat_status=fs[:fb.F], feat_chi2=fc[:fb.F])
 
+    # ---- collective inside the library (ovp_nccl_*): the ctx owns the communicator ----
+    def nccl_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self._ck(self.lib.ovp_nccl_unique_id(self.h, buf))
+        return buf.raw
+
+    def nccl_init(self, id128, nranks, rank):
+        self._ck(self.lib.ovp_nccl_init(self.h, C.c_char_p(bytes(id128)), int(nranks), int(rank)))
+
+    def nccl_finalize(self):
+        self._ck(self.lib.ovp_nccl_finalize(self.h))
+
+    def msckf_update_sharded(self, batch, all_clone_handles, sigma_pix=1.0, chi2_mult=1.0):
+        """This rank's features of ONE large point update; collective over the ctx's communicator (see include/ovp.h)."""
+        hs = _i32(all_clone_handles)
+        uo = UpdaterOptions(sigma_pix, chi2_mult)
+        F = int(batch["F"])
+        fs, fc = np.zeros(max(1, F), dtype=np.int32), np.zeros(max(1, F))
+        fb, keep = self._batch_struct(batch)
+        self._ck(self.lib.ovp_msckf_update_sharded(self.h, C.byref(fb), C.byref(uo), _p(hs), len(hs), _p(fs), _p(fc)))
+        return dict(feat_status=fs[:F], feat_chi2=fc[:F])
+
     def msckf_update_gathered(self, d_blocks_ptr, G, all_clone_handles):
         ch = _i32(all_clone_handles)
         self._ck(self.lib.ovp_msckf_update_gathered(self.h, C.c_void_p(d_blocks_ptr), int(G), _p(ch), len(ch)))
@@ -401,6 +423,27 @@ class Context(object):
     def feed_imu(self, t, wm, am):
         w, a = _f64(wm), _f64(am)
         self._ck(self.lib.ovp_propagator_feed_imu(self.h, C.c_double(t), _p(w), _p(a)))
+
+    # ---- FeatureInitializer (triangulation, the step before the update path) ----
+    def triangulate_features(self, meas_offset, meas_clone, uv_norm):
+        mo, mc = _i32(meas_offset), _i32(meas_clone)
+        uvn = np.ascontiguousarray(uv_norm, dtype=np.float32)
+        F = len(mo) - 1
+        pf, st = np.zeros((max(1, F), 3)), np.zeros(max(1, F), dtype=np.int32)
+        self._ck(self.lib.ovp_triangulate_features(self.h, F, _p(mo), _p(mc), _p(uvn), None, _p(pf), _p(st)))
+        return pf[:F], st[:F]
+
+    # ---- UpdaterZeroVelocity ----
+    def zupt_feed_imu(self, t, wm, am):
+        w, a = _f64(wm), _f64(am)
+        self._ck(self.lib.ovp_zupt_feed_imu(self.h, C.c_double(t), _p(w), _p(a)))
+
+    def zupt_try_update(self, t, average_disparity, num_features, gravity_mag=9.81, max_velocity=1.0, noise_multiplier=1.0, max_disparity=1.0,
+                        chi2_mult=1.0):
+        zo = (C.c_double * 5)(gravity_mag, max_velocity, noise_multiplier, max_disparity, chi2_mult)
+        acc, chi = C.c_int(0), C.c_double(0.0)
+        self._ck(self.lib.ovp_zupt_try_update(self.h, zo, C.c_double(t), C.c_double(average_disparity), int(num_features), C.byref(acc), C.byref(chi)))
+        return bool(acc.value), chi.value
 
     def fast_state_propagate(self, t):
         sp, cv, ok = np.zeros(13), np.zeros((12, 12), order="F"), C.c_int(0)

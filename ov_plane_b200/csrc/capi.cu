@@ -307,6 +307,9 @@ int ovp_create(const ovp_state_options *opt, int device, int max_state, int max_
   *out = h;
   OVP_CUDA(cudaSetDevice(device));
   OVP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  OVP_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  OVP_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  OVP_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   for (int i = 0; i < 8; i++)
     OVP_CUDA(cudaEventCreate(&c->ev[i]));
   c->Nmax = (max_state + 63) / 64 * 64;
@@ -465,7 +468,11 @@ void ovp_destroy(ovp_ctx *h) {
   cudaFree(c->dcols);
   cudaFree(c->dflags);
   cudaFree(c->dscal);
+  if (c->nccl_comm)
+    ovp_nccl_finalize(h);
+  cudaFree(c->d_gather);
   cudaFree(c->dHs);
+  cudaFree(c->d_mw);
   cudaFree(c->dPart);
   cudaFree(c->d_chi2_table);
   cudaFree(c->d_batch);
@@ -483,6 +490,12 @@ void ovp_destroy(ovp_ctx *h) {
     cudaFreeHost(c->h_pinned);
   for (int i = 0; i < 8; i++)
     cudaEventDestroy(c->ev[i]);
+  if (c->stream2)
+    cudaStreamDestroy(c->stream2);
+  if (c->ev_fork)
+    cudaEventDestroy(c->ev_fork);
+  if (c->ev_join)
+    cudaEventDestroy(c->ev_join);
   if (c->stream)
     cudaStreamDestroy(c->stream);
   delete h;

@@ -3,6 +3,7 @@
 // (compiled as part of the unity build ovp_unity.cu, after capi.cu)
 #include <climits>
 #include "host_math.h"
+#include "triangulate_core.h"
 
 using namespace ovp;
 
@@ -861,6 +862,10 @@ int ovp_msckf_update_gathered(ovp_ctx *h, const double *d_blocks, int G, const i
   return check_status_flags(c);
 }
 
+} // extern "C"
+#include "capi_nccl.inc"
+extern "C" {
+
 // ---- Propagator ----------------------------------------------------------------------------------------------------------
 int ovp_propagator_set_noise(ovp_ctx *h, double sigma_w, double sigma_wb, double sigma_a, double sigma_ab, double gravity_mag) {
   Ctx *c = ovp::enter(h);
@@ -1448,6 +1453,245 @@ int ovp_transfer_bytes(ovp_ctx *h, int64_t *h2d, int64_t *d2h) {
 }
 
 } // extern "C"
+
+// ---- FeatureInitializer::single_triangulation + single_gaussnewton on the device (triangulate_core.h) --------------------------------
+namespace ovp {
+// camera pose of every clone handle: R_GtoCi = R_ItoC R_GtoIi, p_CiinG = p_IiinG - R_GtoCi^T p_IinC (UpdaterMSCKF.cpp:122-140)
+__global__ void cam_pose_kernel(int nh, const int *var_kind, const int *var_id, const double *val, int h_calib, double *Rc, double *pc) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= nh || var_kind[h] != OVP_KIND_POSE || var_id[h] < 0 || h == h_calib)
+    return;
+  const double *v = val + (size_t)h * OVP_VAL_STRIDE, *cal = val + (size_t)h_calib * OVP_VAL_STRIDE;
+  double Ri[9], RC[9], R[9];
+  quat_to_rot(v, Ri);
+  quat_to_rot(cal, RC);
+  mat3_mul(RC, Ri, R);
+  for (int i = 0; i < 9; i++)
+    Rc[9 * (size_t)h + i] = R[i];
+  for (int i = 0; i < 3; i++)
+    pc[3 * (size_t)h + i] = v[4 + i] - (R[i] * cal[4] + R[3 + i] * cal[5] + R[6 + i] * cal[6]);
+}
+__global__ void triangulate_kernel(int F, const int *meas_offset, const int *meas_clone, const float *uvn, const double *Rc, const double *pc,
+                                   TriOptions o, double *p_FinG, int *status) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F)
+    return;
+  const int m0 = meas_offset[f], m = meas_offset[f + 1] - m0;
+  double pf[3] = {0.0, 0.0, 0.0};
+  const int ok = (m >= 2) ? triangulate_feature(m, meas_clone + m0, Rc, pc, uvn + 2 * (size_t)m0, o, pf) : 0;
+  status[f] = ok;
+  for (int i = 0; i < 3; i++)
+    p_FinG[3 * (size_t)f + i] = pf[i];
+}
+} // namespace ovp
+extern "C" int ovp_triangulate_features(ovp_ctx *h, int F, const int *meas_offset, const int *meas_clone, const float *uv_norm,
+                                        const ovp_triangulation_options *opt, double *p_FinG, int *status) {
+  Ctx *c = ovp::enter(h);
+  if (F <= 0)
+    return OVP_OK;
+  if (!meas_offset || !meas_clone || !uv_norm || !p_FinG || !status)
+    return fail(c, OVP_ERR_BAD_ARGS, "triangulate_features: null argument");
+  const int M = meas_offset[F];
+  for (int k = 0; k < M; k++) {
+    const int hh = meas_clone[k];
+    if (hh < 0 || hh >= (int)c->vars.size() || !c->vars[hh].alive || c->vars[hh].kind != OVP_KIND_POSE || c->vars[hh].id < 0)
+      return fail(c, OVP_ERR_BAD_ARGS, "triangulate_features: measurement %d: handle %d is not a clone in the state", k, hh);
+  }
+  if (c->var_table_dirty) {
+    int st = upload_var_table(c);
+    if (st)
+      return st;
+  }
+  TriOptions o = {5, 1e-3, 1e10, 1e-6, 1e-6, 10.0, 0.10, 60.0, 40.0, 10000.0}; // FeatureInitializerOptions defaults (ov_core)
+  if (opt) {
+    o.max_runs = opt->max_runs;
+    o.init_lamda = opt->init_lamda;
+    o.max_lamda = opt->max_lamda;
+    o.min_dx = opt->min_dx;
+    o.min_dcost = opt->min_dcost;
+    o.lam_mult = opt->lam_mult;
+    o.min_dist = opt->min_dist;
+    o.max_dist = opt->max_dist;
+    o.max_baseline = opt->max_baseline;
+    o.max_cond_number = opt->max_cond_number;
+  }
+  const int nh = (int)c->vars.size();
+  // staging: [offsets | clones | uvn] in, [p_FinG | status] out, camera pose table
+  const size_t b_off = 0, b_cl = b_off + (size_t)(F + 1) * 4, b_uv = (b_cl + (size_t)M * 4 + 7) & ~(size_t)7, b_pf = (b_uv + (size_t)M * 8 + 7) & ~(size_t)7;
+  const size_t b_st = b_pf + (size_t)F * 24, b_R = (b_st + (size_t)F * 4 + 7) & ~(size_t)7, b_p = b_R + (size_t)nh * 72, b_end = b_p + (size_t)nh * 24;
+  int st = ensure_stage(c, b_end / 8 + 8);
+  if (st)
+    return st;
+  char *d = (char *)c->d_stage;
+  OVP_CUDA(cudaMemcpyAsync(d + b_off, meas_offset, (size_t)(F + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(d + b_cl, meas_clone, (size_t)M * 4, cudaMemcpyHostToDevice, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(d + b_uv, uv_norm, (size_t)M * 8, cudaMemcpyHostToDevice, c->stream));
+  c->h2d_bytes += (int64_t)((F + 1) * 4 + M * 12);
+  cam_pose_kernel<<<(nh + 127) / 128, 128, 0, c->stream>>>(nh, c->d_var_kind, c->d_var_id, c->d_val, c->h_calib, (double *)(d + b_R), (double *)(d + b_p));
+  triangulate_kernel<<<(F + 63) / 64, 64, 0, c->stream>>>(F, (const int *)(d + b_off), (const int *)(d + b_cl), (const float *)(d + b_uv),
+                                                          (const double *)(d + b_R), (const double *)(d + b_p), o, (double *)(d + b_pf), (int *)(d + b_st));
+  c->launches += 2;
+  OVP_CUDA(cudaMemcpyAsync(p_FinG, d + b_pf, (size_t)F * 24, cudaMemcpyDeviceToHost, c->stream));
+  OVP_CUDA(cudaMemcpyAsync(status, d + b_st, (size_t)F * 4, cudaMemcpyDeviceToHost, c->stream));
+  OVP_CUDA(cudaStreamSynchronize(c->stream));
+  c->d2h_bytes += (int64_t)F * 28;
+  return OVP_OK;
+}
+
+// ---- UpdaterZeroVelocity::try_update (update/UpdaterZeroVelocity.cpp:68-318) -------------------------------------------------------------
+// With the flags the reference hard-codes (:113-116): measurements w_true = 0, a_true = 0 for every IMU interval between the state time and
+// `timestamp`; chi2 against the IMU marginal inflated by the bias random walk; accepted when the disparity check passes, or when chi2 and
+// the velocity pass; then the bias propagation (Phi = I, so EKFPropagation changes exactly the six diagonal entries P_ii += Q_ii) and ONE
+// StateHelper::EKFUpdate with the diagonal R.  FeatureHelper::compute_disparity (front end) is upstream: its outputs are arguments.
+// H is laid out over the whole IMU variable (15 columns, zeros for p and v): the reference's {q, bg, ba} sub-variable order gives the same
+// products.  The small host-side linear algebra (chi2 of a <= few-hundred-row system against a 15 x 15 marginal) needs no GPU.
+namespace ovp {
+__global__ void add_diag6_kernel(double *P, int ld, int id0, const double *q6) {
+  const int j = threadIdx.x;
+  if (j < 6)
+    P[(size_t)(id0 + j) * ld + id0 + j] += q6[j];
+}
+} // namespace ovp
+extern "C" {
+int ovp_zupt_feed_imu(ovp_ctx *h, double timestamp, const double wm[3], const double am[3]) {
+  ImuSample s;
+  s.t = timestamp;
+  for (int i = 0; i < 3; i++) {
+    s.wm[i] = wm[i];
+    s.am[i] = am[i];
+  }
+  h->c.zupt_imu.push_back(s);
+  return OVP_OK;
+}
+int ovp_zupt_try_update(ovp_ctx *h, const ovp_zupt_options *zo, double timestamp, double average_disparity, int num_features, int *accepted,
+                        double *chi2_out) {
+  using namespace ovp::hm;
+  Ctx *c = ovp::enter(h);
+  if (!zo || !accepted)
+    return fail(c, OVP_ERR_BAD_ARGS, "zupt_try_update: null argument");
+  *accepted = 0;
+  if (chi2_out)
+    *chi2_out = 0.0;
+  if (c->zupt_imu.empty() || c->timestamp == timestamp) { // :71-80
+    c->zupt_last_state_timestamp = 0.0;
+    return OVP_OK;
+  }
+  int st = sync_host_values(c);
+  if (st)
+    return st;
+  const double *iv = &c->h_val[(size_t)c->h_imu * OVP_VAL_STRIDE];
+  const double *ifej = &c->h_fej[(size_t)c->h_imu * OVP_VAL_STRIDE];
+  const double t_off_new = c->h_val[(size_t)c->h_dt * OVP_VAL_STRIDE];
+  if (!c->zupt_have_offset) {
+    c->zupt_last_offset = t_off_new;
+    c->zupt_have_offset = true;
+  }
+  const double time0 = c->timestamp + c->zupt_last_offset, time1 = timestamp + t_off_new;
+  std::vector<ImuSample> rec = select_imu_readings(c->zupt_imu, time0, time1);
+  c->zupt_last_offset = t_off_new;
+  if (rec.size() < 2) {
+    c->zupt_last_state_timestamp = 0.0;
+    return OVP_OK;
+  }
+  const int m = 6 * ((int)rec.size() - 1);
+  if (m > c->Rcap)
+    return fail(c, OVP_ERR_CAPACITY, "zupt: %d measurement rows exceed capacity %d", m, c->Rcap);
+  std::vector<double> H((size_t)m * 15, 0.0), res(m, 0.0), Rd(m, 0.0);
+  double Rv[9], Rj[9];
+  quat_to_rot(iv, Rv);
+  quat_to_rot(c->opt.do_fej ? ifej : iv, Rj);
+  const double g[3] = {0.0, 0.0, zo->gravity_mag};
+  double Rg[3], Rjg[3];
+  mat3_vec(Rv, g, Rg);
+  mat3_vec(Rj, g, Rjg);
+  double sk[9];
+  skew3(Rjg, sk);
+  double dt_summed = 0.0;
+  for (size_t i = 0; i + 1 < rec.size(); i++) {
+    const double dt = rec[i + 1].t - rec[i].t;
+    for (int j = 0; j < 3; j++) {
+      const double a_hat = rec[i].am[j] - iv[13 + j];
+      res[6 * i + j] = -(rec[i].wm[j] - iv[10 + j]);
+      res[6 * i + 3 + j] = -(a_hat - Rg[j]);
+      H[(size_t)(9 + j) * m + 6 * i + j] = -1.0;
+      for (int l = 0; l < 3; l++)
+        H[(size_t)l * m + 6 * i + 3 + j] = -sk[3 * j + l];
+      H[(size_t)(12 + j) * m + 6 * i + 3 + j] = -1.0;
+      Rd[6 * i + j] = zo->zupt_noise_multiplier * (c->sigma_w * c->sigma_w / dt);
+      Rd[6 * i + 3 + j] = zo->zupt_noise_multiplier * (c->sigma_a * c->sigma_a / dt);
+    }
+    dt_summed += dt;
+  }
+  double Qb[6];
+  for (int j = 0; j < 3; j++) {
+    Qb[j] = dt_summed * c->sigma_wb; // sigma, not sigma^2: exactly what the reference does (:186-187)
+    Qb[3 + j] = dt_summed * c->sigma_ab;
+  }
+  // chi2 = res^T (H P_marg H^T + R)^-1 res with the inflated IMU marginal (:189-193), on the host
+  double Pm[225];
+  st = ovp_get_marginal_covariance(h, &c->h_imu, 1, Pm);
+  if (st)
+    return st;
+  for (int j = 0; j < 6; j++)
+    Pm[(9 + j) * 15 + 9 + j] += Qb[j];
+  std::vector<double> T((size_t)m * 15), S((size_t)m * m);
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < 15; j++) {
+      double a = 0.0;
+      for (int k = 0; k < 15; k++)
+        a += H[(size_t)k * m + i] * Pm[j * 15 + k];
+      T[(size_t)j * m + i] = a;
+    }
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j <= i; j++) {
+      double a = (i == j) ? Rd[i] : 0.0;
+      for (int k = 0; k < 15; k++)
+        a += T[(size_t)k * m + i] * H[(size_t)k * m + j];
+      S[(size_t)j * m + i] = a;
+    }
+  std::vector<double> y(res);
+  for (int j = 0; j < m; j++) { // Cholesky (lower, in place) and forward substitution in one sweep
+    double d = S[(size_t)j * m + j];
+    if (!(d > 0.0))
+      return fail(c, OVP_ERR_NOT_POSITIVE_DEFINITE, "zupt: innovation covariance not positive definite");
+    d = std::sqrt(d);
+    S[(size_t)j * m + j] = d;
+    y[j] /= d;
+    for (int i = j + 1; i < m; i++) {
+      S[(size_t)j * m + i] /= d;
+      y[i] -= S[(size_t)j * m + i] * y[j];
+    }
+    for (int k = j + 1; k < m; k++) {
+      const double lkj = S[(size_t)j * m + k];
+      for (int i = k; i < m; i++)
+        S[(size_t)k * m + i] -= S[(size_t)j * m + i] * lkj;
+    }
+  }
+  double chi2 = 0.0;
+  for (int i = 0; i < m; i++)
+    chi2 += y[i] * y[i];
+  if (chi2_out)
+    *chi2_out = chi2;
+  const double chi2_check = chi2_q95(c, m);
+  const bool disparity_passed = average_disparity < zo->zupt_max_disparity && num_features > 20; // :219
+  const double vnorm = std::sqrt(iv[7] * iv[7] + iv[8] * iv[8] + iv[9] * iv[9]);
+  if (!disparity_passed && (chi2 > zo->chi2_multipler * chi2_check || vnorm > zo->zupt_max_velocity)) {
+    c->zupt_last_state_timestamp = 0.0;
+    return OVP_OK;
+  }
+  // accepted (:253-264): bias propagation, then the update, then move the state time forward
+  OVP_CUDA(cudaMemcpyAsync(c->dscal + 32, Qb, 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  add_diag6_kernel<<<1, 32, 0, c->stream>>>(c->dP, c->ldP, c->vars[c->h_imu].id + 9, c->dscal + 32);
+  c->launches++;
+  st = ovp_ekf_update(h, &c->h_imu, 1, H.data(), m, res.data(), Rd.data());
+  if (st)
+    return st;
+  c->timestamp = timestamp;
+  c->zupt_last_state_timestamp = timestamp;
+  *accepted = 1;
+  return OVP_OK;
+}
+}
 
 // ---- UpdaterSLAM entry points (slam_host.inc) ----------------------------------------------------------------------------
 namespace ovp {

@@ -53,6 +53,7 @@ struct CholFusedArgs {
   int *gate_flag;
   int nrb, mstride;
   long long *dbg; // optional: 16 globaltimer stamps per CTA (tools/microbench.py)
+  int no_lookahead; // 1: the spine applies L(k,k) to the next step's tiles only after the whole 64-column factorisation (A/B switch)
 };
 
 __device__ __forceinline__ long long cf_gtime() {
@@ -434,8 +435,90 @@ __device__ __forceinline__ void cf_deferred_store(const CfDeferred &d, int q, in
   for (int c = 0; c < d.ncol; c++)
     __stcg(reinterpret_cast<double2 *>(g + (size_t)c * d.ld), *reinterpret_cast<const double2 *>(s + c * CF_LD));
 }
+// Lookahead inside the spine: while the pivot chain of 16-column panel p runs on warps 0..vw, the warps that carry no chain apply the
+// FINISHED panels b < p of L(k,k) to the two tiles the next step needs -
+//   BS(b): L(k+1,k)[:, b] = (U[:, b] - U[:, <b] L(k,k)[b, <b]^T) X_bb^T      (right-side solve, independent per 8-row group)
+//   UP(b): D(k+1) -= L(k+1,k)[:, b] L(k+1,k)[:, b]^T                         (lower 8x8 blocks)
+// - so that after the last chain only panel 3 is left.  The two tiles arrive by bulk copy some time into the factorisation (their
+// producers wait for this CTA's previous panel): the I/O warp polls their flags / the mbarrier WITHOUT blocking (it gives up when the
+// chain of the current panel signals completion) and records the state in shared memory; the helpers look at that state once per panel,
+// after the CTA barrier, so every warp takes the same decision.
+struct CfOverlap {
+  bool on, diag;           // lookahead enabled for this step; a next diagonal tile exists
+  double *U, *D, *scr;     // shared-memory tiles U(k+1,k) -> L(k+1,k), D(k+1), and the 64 x 16 solve scratch
+  const int *flagU, *flagD;
+  const double *slotU, *slotD;
+  unsigned mbar, parity;
+  volatile int *sync;      // shared memory: [0] number of finished pivot chains of this step, [1] tile state: 0 flags pending, 1 loading, 2 landed
+  int done;                // panels [0, done) have been applied
+};
+// one 8-row group rg of panel b of the right-side solve (the body of cf_bsolve64 for one row group and one block)
+__device__ __forceinline__ void cf_bs_unit(double *U, const double *Lkk, const double *X, double *S, int rg, int b, int lane) {
+  const int g = lane >> 2, t = lane & 3, r = 8 * rg + g, cb = 16 * b;
+  double a0[2] = {0.0, 0.0}, a1[2] = {0.0, 0.0};
+#pragma unroll 4
+  for (int k4 = 0; k4 < cb; k4 += 4) {
+    const double av = U[CF_AT(r, k4 + t)];
+    dmma_m8n8k4(a0[0], a0[1], av, Lkk[CF_AT(cb + g, k4 + t)]);
+    dmma_m8n8k4(a1[0], a1[1], av, Lkk[CF_AT(cb + 8 + g, k4 + t)]);
+  }
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    S[CF_AT(r, 2 * t + h)] = U[CF_AT(r, cb + 2 * t + h)] - a0[h];
+    S[CF_AT(r, 8 + 2 * t + h)] = U[CF_AT(r, cb + 8 + 2 * t + h)] - a1[h];
+  }
+  __syncwarp();
+  double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+#pragma unroll
+  for (int k4 = 0; k4 < 16; k4 += 4) {
+    const double sv = S[CF_AT(r, k4 + t)];
+    if (k4 < 8)
+      dmma_m8n8k4(c0[0], c0[1], sv, X[CF_XAT(b, g, k4 + t)]);
+    dmma_m8n8k4(c1[0], c1[1], sv, X[CF_XAT(b, 8 + g, k4 + t)]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    U[CF_AT(r, cb + 2 * t + h)] = c0[h];
+    U[CF_AT(r, cb + 8 + 2 * t + h)] = c1[h];
+  }
+  __syncwarp();
+}
+// lower 8x8 block q (0..35, row-major over the lower triangle of 8x8 blocks) of D -= L[:, b] L[:, b]^T
+__device__ __forceinline__ void cf_up_unit(double *D, const double *L, int q, int b, int lane) {
+  const int g = lane >> 2, t = lane & 3, cb = 16 * b;
+  int bi = 0;
+  while (q >= bi + 1) {
+    q -= bi + 1;
+    bi++;
+  }
+  const int bj = q;
+  double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+  for (int k4 = 0; k4 < 16; k4 += 4)
+    dmma_m8n8k4(c0, c1, L[CF_AT(8 * bi + g, cb + k4 + t)], L[CF_AT(8 * bj + g, cb + k4 + t)]);
+  double *pc = D + CF_AT(8 * bi + g, 8 * bj + 2 * t);
+  pc[0] -= c0;
+  pc[CF_LD] -= c1;
+}
+// panels [b0, b1) by `nh` warps (this warp is number `hi` of them); `bar` = named barrier id shared by exactly these warps (0: __syncthreads)
+__device__ __forceinline__ void cf_apply_panels(const CfOverlap &ov, const double *Lkk, const double *X, int b0, int b1, int hi, int nh, int bar,
+                                                int lane) {
+  for (int b = b0; b < b1; b++) {
+    for (int rg = hi; rg < 8; rg += nh)
+      cf_bs_unit(ov.U, Lkk, X, ov.scr, rg, b, lane);
+    if (!ov.diag)
+      continue;
+    if (bar)
+      asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nh * 32) : "memory");
+    else
+      __syncthreads();
+    for (int q = hi; q < 36; q += nh)
+      cf_up_unit(ov.D, ov.U, q, b, lane);
+  }
+}
 __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool strict, double *pivinv, int *info, double *bcast,
-                           const CfPrefetch &pf, const CfDeferred &dfr, int epoch, long long *dbgp = nullptr) {
+                           const CfPrefetch &pf, const CfDeferred &dfr, CfOverlap &ov, int epoch, long long *dbgp = nullptr) {
 #define PT(slot)                                                                                                             \
   if (dbgp && threadIdx.x == 0)                                                                                              \
     dbgp[slot] = clock64();
@@ -450,10 +533,35 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
   for (int c0 = 0; c0 < bs; c0 += 16) {
     const int nbp = min(16, bs - c0);
     const int vw = (CF_B - c0 - 16) / 16; // warps 0..vw-1 carry the rows below the block, warp vw carries the identity (below)
+    const int pnl = c0 >> 4;
+    const int st0 = ov.on ? ov.sync[1] : 0; // tile state at the start of this panel: the same value in every warp (written before the barrier)
     if ((warp_u == 4 || warp_u == 5) && c0 == 0) { // (never chain warps: vw <= 3) the previous step's factor tiles -> A
       if (warp_u - 4 < dfr.n)
         cf_deferred_store(dfr, warp_u - 4, lane);
-    } else if (warp_u == 7) { // the I/O warp
+      if (ov.on)
+        asm volatile("bar.sync 2, 96;" ::: "memory"); // ... before the I/O warp lets the bulk loads overwrite those buffers
+    } else if (warp_u == 7 && ov.on) { // the I/O warp, lookahead mode: non-blocking progress on the next step's two tiles
+      if (c0 == 0)
+        asm volatile("bar.sync 2, 96;" ::: "memory");
+      if (lane == 0) {
+        int st = ov.sync[1];
+        while (st < 2 && ov.sync[0] <= pnl) {
+          if (st == 0) {
+            if (cf_ld_acquire(ov.flagU) == epoch && (!ov.diag || cf_ld_acquire(ov.flagD) == epoch)) {
+              cf_fence_async_all();
+              cf_mbar_expect_tx(ov.mbar, ov.diag ? 2 * CF_SLOT_BYTES : CF_SLOT_BYTES);
+              cf_bulk_g2s(cf_saddr(ov.U), ov.slotU, CF_SLOT_BYTES, ov.mbar);
+              if (ov.diag)
+                cf_bulk_g2s(cf_saddr(ov.D), ov.slotD, CF_SLOT_BYTES, ov.mbar);
+              st = 1;
+            }
+          } else if (cf_mbar_try(ov.mbar, ov.parity)) {
+            st = 2;
+          }
+        }
+        ov.sync[1] = st;
+      }
+    } else if (warp_u == 7) { // the I/O warp, blocking prefetch during the last panel (no lookahead for this step)
       if (c0 + 16 >= bs) { // last panel: poll the flags of the next step's tiles, then start their bulk loads
         if (lane == 0 && (pf.flag0 || pf.flag1)) {
           if (pf.flag0)
@@ -548,8 +656,15 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
       }
       if (strict && bad && tid == 0)
         atomicExch(info, 1);
+      if (ov.on && tid == 0)
+        ov.sync[0] = pnl + 1; // this panel's chain is finished (the I/O warp stops polling)
       PT(1 + 3 * (c0 >> 4))
+    } else if (ov.on && st0 == 2 && pnl > ov.done) {
+      // idle warps vw+1 .. 6: apply the finished panels [done, pnl) to the next step's tiles
+      cf_apply_panels(ov, a, x, ov.done, pnl, warp_u - (vw + 1), 6 - vw, 3, lane);
     }
+    if (ov.on && st0 == 2)
+      ov.done = pnl;
     __syncthreads();
     PT(2 + 3 * (c0 >> 4))
     if (CF_B - c0 - 16 > 0 && nbp == 16) // (a partial block is the last pivot block: everything to its right is never read)
@@ -610,6 +725,7 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
   // Layout (doubles): [0,16) two mbarriers (+ padding to 128 B) | tile buffers | role-specific (see the three branches)
   double *tb = sm + 16; // tile buffers: 128-byte aligned bulk-copy targets
   const unsigned mb0 = cf_saddr(sm);
+  volatile int *csync = reinterpret_cast<volatile int *>(sm + 2); // spine: [0] finished pivot chains of the step, [1] state of the lookahead tiles
   __shared__ int s_epoch;
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -649,15 +765,33 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
         CF_TS(1 + 2 * k)
       long long *dbgp = (p.dbg && k == 1) ? p.dbg + (size_t)gridDim.x * 16 : nullptr;
       PT(0)
+      CfOverlap ov; // lookahead: the idle warps apply finished panels to the next step's tiles while the pivot chains run
+      ov.on = has_panel && bs == CF_B && !p.no_lookahead;
+      ov.diag = next_diag;
+      ov.U = b3;
+      ov.D = b4;
+      ov.scr = sscr;
+      ov.flagU = fus + k + 1;
+      ov.flagD = fud + k + 1;
+      ov.slotU = slotUs + (size_t)(k + 1) * CF_SLOT;
+      ov.slotD = slotUd + (size_t)(k + 1) * CF_SLOT;
+      ov.mbar = mb0;
+      ov.parity = par_pf;
+      ov.sync = csync;
+      ov.done = 0;
+      if (tid == 0) {
+        csync[0] = 0;
+        csync[1] = 0;
+      }
       CfPrefetch pf;
-      pf.flag0 = has_panel ? fus + k + 1 : nullptr;
-      pf.flag1 = next_diag ? fud + k + 1 : nullptr;
+      pf.flag0 = (has_panel && !ov.on) ? fus + k + 1 : nullptr;
+      pf.flag1 = (next_diag && !ov.on) ? fud + k + 1 : nullptr;
       pf.s0 = b3;
       pf.s1 = b4;
-      pf.g0 = slotUs + (size_t)(k + 1) * CF_SLOT;
-      pf.g1 = slotUd + (size_t)(k + 1) * CF_SLOT;
+      pf.g0 = ov.slotU;
+      pf.g1 = ov.slotD;
       pf.mbar = mb0;
-      cf_potrf64(a, xc, bs, thr, p.tol == 0.0, pivinv, p.info, bcast, pf, dfr, e, dbgp);
+      cf_potrf64(a, xc, bs, thr, p.tol == 0.0, pivinv, p.info, bcast, pf, dfr, ov, e, dbgp);
       dfr.n = 0;
       if (k < 3)
         CF_TS(2 + 2 * k)
@@ -683,10 +817,27 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       if (has_panel) {
         if (next_diag && tid < CF_B)
           thr[tid] = p.tol * __ldcg(p.diag0 + CF_B * (k + 1) + tid);
-        cf_mbar_wait(mb0, par_pf); // the two tiles of the next step (bulk loads started during the last pivot chain)
-        par_pf ^= 1;
-        PT(24)
-        cf_bsolve64(b3, a, xc, sscr); // L(k+1,k) = U(k+1,k) L(k,k)^-T
+        if (ov.on) {
+          if (tid == IO && csync[1] == 0) { // the tiles' flags had not shown up while the chains ran: now wait for them
+            cf_acquire(ov.flagU, e);
+            if (next_diag)
+              cf_acquire(ov.flagD, e);
+            cf_fence_async_all();
+            cf_mbar_expect_tx(mb0, next_diag ? 2 * CF_SLOT_BYTES : CF_SLOT_BYTES);
+            cf_bulk_g2s(cf_saddr(b3), ov.slotU, CF_SLOT_BYTES, mb0);
+            if (next_diag)
+              cf_bulk_g2s(cf_saddr(b4), ov.slotD, CF_SLOT_BYTES, mb0);
+          }
+          cf_mbar_wait(mb0, par_pf);
+          par_pf ^= 1;
+          PT(24)
+          cf_apply_panels(ov, a, xc, ov.done, 4, tid >> 5, 8, 0, tid & 31); // what the lookahead has not reached (panel 3 at least)
+        } else {
+          cf_mbar_wait(mb0, par_pf); // the two tiles of the next step (bulk loads started during the last pivot chain)
+          par_pf ^= 1;
+          PT(24)
+          cf_bsolve64(b3, a, xc, sscr); // L(k+1,k) = U(k+1,k) L(k,k)^-T
+        }
         cf_fence_async_smem();
         __syncthreads();
         PT(25)
@@ -700,8 +851,10 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
         dfr.n = 2;
         PT(26)
         if (next_diag) {
-          cf_mma_64<2>(b4, b3, b3, -1.0, true, false); // lower triangle of the next diagonal tile
-          __syncthreads();
+          if (!ov.on) {
+            cf_mma_64<2>(b4, b3, b3, -1.0, true, false); // lower triangle of the next diagonal tile
+            __syncthreads();
+          }
           double *tmp = a;
           a = b4;
           b4 = tmp;
@@ -977,6 +1130,13 @@ int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const dou
   p.ldy = ldy;
   p.w = w;
   p.dbg = dbg;
+  {
+    // the in-spine lookahead is OFF by default: measured on B200 the two tiles it needs arrive ~22 K cycles after this CTA's previous
+    // panel is published (their producers' acquire -> bulk load -> 64^3 update -> bulk store -> release round trip), i.e. after the last
+    // pivot chain, so the helpers never get to run and the unit-wise tail is slower than cf_bsolve64 + cf_mma_64 (170 vs 143 us at n = 474)
+    static const char *nl = getenv("OVP_CHOL_LOOKAHEAD");
+    p.no_lookahead = (nl && nl[0] == '1') ? 0 : 1;
+  }
   const int vrows = M ? (mrows + (z ? 1 : 0)) : 0;
   p.nrb = (vrows + CF_RB - 1) / CF_RB;
   p.mstride = p.Tp * CF_B + 4;

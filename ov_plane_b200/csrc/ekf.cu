@@ -55,29 +55,32 @@ __global__ void __launch_bounds__(128) finish_update_kernel(int nh, const int *v
   if (id < 0)
     return;
   const int s = var_size[h];
-  // lane -> (row i = lane & 15 of the variable, half kh = lane >> 4 of the compressed rows): the s rows of one column of Y are
-  // contiguous, so a half warp reads one 8 s-byte run per column; four accumulators per lane break the FMA dependency chain
-  const int i = lane & 15, kh = lane >> 4;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  if (i < s) {
-    const double *y = Y + id + i;
-    int k = kh;
-    for (; k + 6 < rr; k += 8) {
-      a0 = fma(y[(size_t)k * ldy], w[k], a0);
-      a1 = fma(y[(size_t)(k + 2) * ldy], w[k + 2], a1);
-      a2 = fma(y[(size_t)(k + 4) * ldy], w[k + 4], a2);
-      a3 = fma(y[(size_t)(k + 6) * ldy], w[k + 6], a3);
-    }
-    for (; k < rr; k += 2)
-      a0 = fma(y[(size_t)k * ldy], w[k], a0);
-  }
-  double d = (a0 + a1) + (a2 + a3);
-  d += __shfl_xor_sync(0xffffffffu, d, 16);
+  // lanes stride over the compressed rows k (all loads of a lane are independent: 15 accumulators, one per row of the variable; the s
+  // rows of one column of Y are contiguous), then a fixed-order shuffle tree per row
   double acc[15];
 #pragma unroll
   for (int j = 0; j < 15; j++)
-    acc[j] = __shfl_sync(0xffffffffu, d, j); // dx of row j (rows >= s: zero)
-  if (lane < s && P[(size_t)(id + lane) * ldP + id + lane] < 0.0)
+    acc[j] = 0.0;
+  {
+    const double *y = Y + id;
+#pragma unroll 2
+    for (int k = lane; k < rr; k += 32) {
+      const double wk = w[k];
+      const double *yk = y + (size_t)k * ldy;
+#pragma unroll
+      for (int j = 0; j < 15; j++)
+        if (j < s)
+          acc[j] = fma(yk[j], wk, acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 15; j++)
+    if (j < s) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o); // dx of row j on every lane
+    }
+  if (P && lane < s && P[(size_t)(id + lane) * ldP + id + lane] < 0.0)
     atomicExch(neg_flag, 1);
   if (lane != 0)
     return;
@@ -165,6 +168,13 @@ int state_append_variable(Ctx *c, Var v, const double *value, const double *fej,
   int st = sync_host_values(c);
   if (st)
     return st;
+  // `value` / `fej` may point INTO the host mirror (StateHelper::clone passes the cloned variable's own values): copy them out
+  // before the mirror can be reallocated below
+  double vbuf[OVP_VAL_STRIDE], fbuf[OVP_VAL_STRIDE];
+  for (int i = 0; i < OVP_VAL_STRIDE; i++) {
+    vbuf[i] = (i < v.nvalue && value) ? value[i] : 0.0;
+    fbuf[i] = (i < v.nvalue) ? (fej ? fej[i] : (value ? value[i] : 0.0)) : 0.0;
+  }
   int h;
   const bool table_full = (int)c->vars.size() >= c->max_handles;
   if (!c->free_handles.empty() && (table_full || (int)c->free_handles.size() > OVP_HANDLE_REUSE_LAG)) {
@@ -180,8 +190,8 @@ int state_append_variable(Ctx *c, Var v, const double *value, const double *fej,
     c->h_fej.resize((size_t)(h + 1) * OVP_VAL_STRIDE, 0.0);
   }
   for (int i = 0; i < OVP_VAL_STRIDE; i++) {
-    c->h_val[(size_t)h * OVP_VAL_STRIDE + i] = (i < v.nvalue && value) ? value[i] : 0.0;
-    c->h_fej[(size_t)h * OVP_VAL_STRIDE + i] = (i < v.nvalue) ? (fej ? fej[i] : (value ? value[i] : 0.0)) : 0.0;
+    c->h_val[(size_t)h * OVP_VAL_STRIDE + i] = vbuf[i];
+    c->h_fej[(size_t)h * OVP_VAL_STRIDE + i] = fbuf[i];
   }
   c->var_table_dirty = true;
   *handle = h;
@@ -213,10 +223,23 @@ int check_status_flags(Ctx *c) {
 // EKF update core (see ovp_internal.h).  K M^T = M S^-1 M^T is applied as (M L^-T)(M L^-T)^T and dx = (M L^-T)(L^-1 z):
 // algebraically the reference's K = M S^-1, P -= K M^T, dx = K res (StateHelper.cpp:165-171,190).
 // -------------------------------------------------------------------------------------------------------------------
+int join_side_stream(Ctx *c) {
+  if (c->join_pending) {
+    OVP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    c->join_pending = false;
+  }
+  return OVP_OK;
+}
+
 int ekf_update_core(Ctx *c, const int *d_cols, int nc, MatView HT, int rr, const double *d_z, const double *d_Rdiag, double gate_thresh,
-                    int *d_gate_flag, double *d_chi2, bool apply, int zstride) {
+                    int *d_gate_flag, double *d_chi2, bool apply, int zstride, bool defer_join) {
   if (rr <= 0 || nc <= 0)
     return OVP_OK;
+  {
+    int stj = join_side_stream(c); // this update reads P
+    if (stj)
+      return stj;
+  }
   if (rr > c->wsS.cap || nc > c->Rcap)
     return fail(c, OVP_ERR_CAPACITY, "ekf_update: system %d x %d exceeds capacity %d", rr, nc, c->Rcap);
   if (c->var_table_dirty) {
@@ -251,18 +274,36 @@ int ekf_update_core(Ctx *c, const int *d_cols, int nc, MatView HT, int rr, const
   }
   if (!apply)
     return OVP_OK;
-  // 6. P -= Y Y^T (lower tiles, mirrored)  [skipped on the device when the gate failed]
+  // 6. P -= Y Y^T (lower tiles, mirrored) and the negative-diagonal check (StateHelper.cpp:176-187)  [skipped on the device when the gate
+  //    failed].  Nothing downstream needs the new P before the next update's M = P[:, ids] H^T (or a point-feature gate), so this branch
+  //    runs on the side stream, in parallel with step 7 and with whatever the caller enqueues next on the main stream.
+  const bool side = c->stream2 != nullptr && !c->profiling;
+  cudaStream_t main_stream = c->stream;
+  if (side) {
+    OVP_CUDA(cudaEventRecord(c->ev_fork, main_stream));
+    OVP_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    c->stream = c->stream2; // the launch helpers below enqueue on c->stream
+  }
   {
     GemmProblem p = make_problem(N, N, rr, mv(c->dY, c->Nmax), mv(c->dY, c->Nmax, 1), c->dP, c->ldP, -1.0, 1.0);
     p.tri = TRI_LOWER_MIRROR;
     launch_gemm1(c, p, flag);
   }
-  // 7. dx = Y w, update of every variable, negative-diagonal check: one launch
+  diag_check_kernel<<<(N + 255) / 256, 256, 0, c->stream>>>(c->dP, c->ldP, N, c->dflags, flag);
+  c->launches++;
+  if (side) {
+    c->stream = main_stream;
+    OVP_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+    c->join_pending = true;
+  }
+  // 7. dx = Y w and the manifold update of every variable: one launch
   int nh = (int)c->vars.size();
   finish_update_kernel<<<(nh * 32 + 127) / 128, 128, 0, c->stream>>>(nh, c->d_var_id, c->d_var_size, c->d_var_kind, c->d_val, c->dY, c->Nmax, d_w, rr,
-                                                                      c->dP, c->ldP, c->dflags, flag);
+                                                                      nullptr, c->ldP, c->dflags, flag);
   c->launches++;
   c->host_values_stale = true;
+  if (!defer_join)
+    return join_side_stream(c);
   return OVP_OK;
 }
 

@@ -10,7 +10,9 @@
 #include "ovp_internal.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <set>
 
 namespace ovp {
@@ -461,8 +463,16 @@ __global__ void gram_reduce_kernel(const double *part, int ldp, int nsplit, int 
   G[(size_t)j * ldg + i] = s;
 }
 
-// Gram + reduce of the stacked system Hs (rows x nc) into ws.S (lower)
-static int gram_of_stacked(Ctx *c, int rows, int nc, int ldHs) {
+#include "msckf_warp.inc"
+
+// D part of the block-sparse Gram matrix (msckf_warp.inc), combined with the SYRK partials in gram_reduce_sparse_kernel
+struct SparseD {
+  int ncal, nslots, nd, nchunk;
+  const double *Dcc, *Ddc, *Dddp;
+};
+// Gram + reduce of the stacked system Hs (rows x nc) into ws.S (lower).  With sp: Hs holds the 4-rows-per-feature SYRK operand Y and
+// the result is G = D - Y^T Y; work = algorithmic flops reported for the launch.
+static int gram_of_stacked(Ctx *c, int rows, int nc, int ldHs, const SparseD *sp = nullptr, double work = -1.0) {
   int tiles = (nc + OVP_GT - 1) / OVP_GT;
   int ldp = tiles * OVP_GT;
   int ntile_lower = tiles * (tiles + 1) / 2;
@@ -476,11 +486,15 @@ static int gram_of_stacked(Ctx *c, int rows, int nc, int ldHs) {
   int kchunk = ((rows + nsplit - 1) / nsplit + OVP_GK - 1) / OVP_GK * OVP_GK;
   nsplit = (rows + kchunk - 1) / kchunk;
   dim3 grid(tiles, tiles, nsplit);
-  prof_begin(c, PROF_GRAM, (double)nc * nc * rows); // algorithmic flops of the symmetric product: 2 * n^2 * r / 2
+  prof_begin(c, PROF_GRAM, work >= 0.0 ? work : (double)nc * nc * rows); // algorithmic flops of the symmetric product: 2 * n^2 * r / 2
   gram_kernel<<<grid, 128, 0, c->stream>>>(c->dHs, ldHs, rows, nc, kchunk, c->dPart, ldp);
   c->launches++;
   prof_end(c);
-  gram_reduce_kernel<<<(nc * nc + 255) / 256, 256, 0, c->stream>>>(c->dPart, ldp, nsplit, nc, c->wsG.S, c->wsG.cap);
+  if (sp)
+    gram_reduce_sparse_kernel<<<(nc * nc + 255) / 256, 256, 0, c->stream>>>(c->dPart, ldp, nsplit, nc, sp->ncal, sp->nslots, sp->nd, sp->Dcc, sp->Ddc,
+                                                                              sp->Dddp, sp->nchunk, c->wsG.S, c->wsG.cap);
+  else
+    gram_reduce_kernel<<<(nc * nc + 255) / 256, 256, 0, c->stream>>>(c->dPart, ldp, nsplit, nc, c->wsG.S, c->wsG.cap);
   c->launches++;
   return OVP_OK;
 }

@@ -36,6 +36,12 @@ struct DenseWs {
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // side stream of the update chain: the covariance downdate P -= Y Y^T (and its negative-diagonal check) of update k runs here while the
+  // main stream already applies dx and builds the next update's Jacobians / Gram matrix (which do not read P); joined before the next
+  // reader of P.  Fork / join through events, so the pattern is captured into the CUDA graph as parallel branches.
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool join_pending = false;
   ovp_state_options opt;
   std::string last_error;
   int64_t launches = 0;
@@ -85,6 +91,13 @@ struct Ctx {
   size_t Hs_elems = 0;
   double *dPart = nullptr;     // split-K partials for the Gram kernel
   size_t part_elems = 0;
+  // NCCL communicator owned by the context (capi_nccl.inc; libnccl is dlopen'ed on first use, no link-time dependency)
+  void *nccl_comm = nullptr;
+  int nccl_rank = 0, nccl_nranks = 1;
+  double *d_gather = nullptr;  // nranks packed lower triangles
+  size_t d_gather_elems = 0;
+  double *d_mw = nullptr;      // warp-per-feature path: measurement blocks, per-feature dense blocks, D part (msckf_warp.inc)
+  size_t d_mw_elems = 0;
   // feature batch staging
   void *d_batch = nullptr;
   size_t d_batch_bytes = 0;
@@ -98,6 +111,10 @@ struct Ctx {
   double sigma_w = 1.6968e-04, sigma_wb = 1.9393e-05, sigma_a = 2.0000e-3, sigma_ab = 3.0000e-03;
   double gravity[3] = {0, 0, 9.81};
   std::vector<ImuSample> imu_data;
+  // UpdaterZeroVelocity keeps its own IMU buffer and time-offset memory (UpdaterZeroVelocity.h)
+  std::vector<ImuSample> zupt_imu;
+  double zupt_last_offset = 0.0, zupt_last_state_timestamp = 0.0;
+  bool zupt_have_offset = false;
   double last_prop_time_offset = 0.0;
   bool have_last_prop_time_offset = false;
 
@@ -159,7 +176,8 @@ void launch_fill(Ctx *c, double *p, size_t n, double v);
 // nc state indices).  z: rr.  Rdiag: rr or nullptr (identity).  If gate_thresh >= 0, chi2 = z^T S^-1 z is compared with
 // it on the device and the update is skipped when larger (flag written to d_gate_flag, chi2 to d_chi2).
 int ekf_update_core(Ctx *c, const int *d_cols, int nc, MatView HT, int rr, const double *d_z, const double *d_Rdiag, double gate_thresh,
-                    int *d_gate_flag, double *d_chi2, bool apply = true, int zstride = 1);
+                    int *d_gate_flag, double *d_chi2, bool apply = true, int zstride = 1, bool defer_join = false);
+int join_side_stream(Ctx *c); // make the main stream wait for the side stream's covariance downdate (no-op when nothing is pending)
 int upload_var_table(Ctx *c);
 int sync_host_values(Ctx *c);
 int push_host_values(Ctx *c, int handle);
@@ -174,10 +192,13 @@ double chi2_q95(Ctx *c, int dof);
 struct MsckfExtra {
   const std::vector<int> *forced_cols = nullptr;
   double *d_export = nullptr;
+  bool allgather_gram = false; // sharded update: all-gather the rank-local packed Gram matrices over the ctx's NCCL communicator, sum them
+                               // in rank order on every rank, then the ordinary compression + EKF update (replicated)
   int64_t only_plane_id = 0;   // init_vio_plane: build the W system of this (out-of-state) plane only and stop
   double sigma_c_scale = 0.0;  // > 0: multiply sigma_constraint (const_init_multi)
 };
 int msckf_last_W(Ctx *c, int *rowsW, int *ncx, int *rows_ref, const int **d_cols);
+int allgather_gram(Ctx *c, int nc1); // capi_nccl.inc: wsG.S (rank-local Gram, lower) -> sum over the ranks of the ctx's communicator
 int msckf_update_impl(Ctx *c, const ovp_feature_batch *batch, const ovp_updater_options *opt, int *feat_status, double *feat_chi2,
                       int *plane_status, double *plane_chi2, int *hx_order, int *hx_order_n, const MsckfExtra *extra = nullptr);
 

@@ -350,6 +350,27 @@ class OracleContext(object):
         w, a = _f64(wm), _f64(am)
         self.lib.orc_prop_feed_imu(self.h, C.c_double(t), _p(w), _p(a))
 
+    def triangulate_features(self, meas_offset, meas_clone, uv_norm):
+        mo, mc = _i32(meas_offset), _i32(meas_clone)
+        uvn = np.ascontiguousarray(uv_norm, dtype=np.float32)
+        F = len(mo) - 1
+        pf, st = np.zeros((max(1, F), 3)), np.zeros(max(1, F), dtype=np.int32)
+        self._ck(self.lib.orc_triangulate_features(self.h, F, _p(mo), _p(mc), _p(uvn), _p(pf), _p(st)))
+        return pf[:F], st[:F]
+
+    # ---- UpdaterZeroVelocity ----
+    def zupt_feed_imu(self, t, wm, am):
+        w, a = _f64(wm), _f64(am)
+        self.lib.orc_zupt_feed_imu(self.h, C.c_double(t), _p(w), _p(a))
+
+    def zupt_try_update(self, t, average_disparity, num_features, gravity_mag=9.81, max_velocity=1.0, noise_multiplier=1.0, max_disparity=1.0,
+                        chi2_mult=1.0, noises=(1.6968e-04, 1.9393e-05, 2.0e-3, 3.0e-3)):
+        self.lib.orc_zupt_set(self.h, *[C.c_double(x) for x in noises], C.c_double(gravity_mag), C.c_double(max_velocity),
+                              C.c_double(noise_multiplier), C.c_double(max_disparity), C.c_double(chi2_mult))
+        acc, chi = C.c_int(0), C.c_double(0.0)
+        self._ck(self.lib.orc_zupt_try_update(self.h, C.c_double(t), C.c_double(average_disparity), int(num_features), C.byref(acc), C.byref(chi)))
+        return bool(acc.value), chi.value
+
     def fast_state_propagate(self, t):
         sp, cv, ok = np.zeros(13), np.zeros((12, 12), order="F"), C.c_int(0)
         self._ck(self.lib.orc_prop_fast_state_propagate(self.h, C.c_double(t), _p(sp), _p(cv), C.byref(ok)))

@@ -21,7 +21,7 @@ def test_rank_tolerance_sweep(name, chi2_table):
         ctx.set_rank_tolerance(tol)
         g = ctx.msckf_update(synth.feature_batch(S, chg), 1.0, 1.0)
         o = oracle_msckf_update(orc, synth.feature_batch(S, cho), 1.0, 1.0)
-        errs.append(_check_msckf(S, ctx, orc, chg, cho, g, o))
+        errs.append(_check_msckf(S, ctx, orc, chg, cho, g, o, chi_tol=1e-6))
         ctx.close()
     print(name, "cov rel err over tol 1e-9..1e-13:", ["%.1e" % e for e in errs])
 
@@ -35,7 +35,7 @@ def test_compression_stress_scenarios(sigma_px, name, over, chi2_table):
     ctx, orc, chg, cho = make_pair(S, chi2_table)
     g = ctx.msckf_update(synth.feature_batch(S, chg), sigma_px, 1.0)
     o = oracle_msckf_update(orc, synth.feature_batch(S, cho), sigma_px, 1.0)
-    e = _check_msckf(S, ctx, orc, chg, cho, g, o)
+    e = _check_msckf(S, ctx, orc, chg, cho, g, o, chi_tol=1e-6)
     print(name, "sigma_px", sigma_px, "cov rel err %.2e" % e, "accepted", int((g["feat_status"] == 1).sum()), "of", S.F)
 
 
@@ -165,3 +165,30 @@ def test_handle_table_stays_bounded_over_a_long_run(chi2_table):
     assert ctx.cov_rows() == orc.cov_rows()
     assert max(seen) < len(chg) + 80 + 8, "handle table grew to %d slots for %d live clones" % (max(seen) + 1, len(chg))
     compare_states(ctx, orc, S, chg, cho, 1e-9)
+
+
+@pytest.mark.parametrize("name", ["cfg1_euroc_n96", "small_planes", "cfg3_n512_f600_p8"])
+def test_block_sparse_gram_equals_dense_stacked_path(name, chi2_table):
+    """The warp-per-feature path (G = D - Y^T Y, never materialising the stacked Jacobian, msckf_warp.inc) against the dense stacked
+    path (feature_kernel + SYRK over all projected rows; OVP_DENSE_STACK=1): same gates, chi2 and posterior."""
+    import os
+    S = synth.make_scenario(name, seed=0)
+    out = {}
+    for mode in ("0", "1"):
+        os.environ["OVP_DENSE_STACK"] = mode
+        try:
+            ctx = api.Context(S.options, device=0, max_state=max(128, S.N + 64), max_meas_rows=60000)
+            ctx.set_chi2_table(chi2_table)
+            ch = synth.load_scenario_into(ctx, S)
+            r = ctx.msckf_update(synth.feature_batch(S, ch), 1.0, 1.0)
+            out[mode] = (r, ctx.cov(), ctx.launch_count())
+            ctx.close()
+        finally:
+            os.environ.pop("OVP_DENSE_STACK", None)
+    (r0, P0, l0), (r1, P1, l1) = out["0"], out["1"]
+    assert np.array_equal(r0["feat_status"], r1["feat_status"]) and np.array_equal(r0["plane_status"], r1["plane_status"])
+    m = (r0["feat_status"] == 0) | (r0["feat_status"] == 1)
+    e_chi = np.abs(r0["feat_chi2"][m] / r1["feat_chi2"][m] - 1).max() if m.any() else 0.0
+    e = relerr(P0, P1)
+    print(name, "block-sparse vs dense: cov rel diff %.2e, per-feature chi2 max rel diff %.2e, launches %d vs %d" % (e, e_chi, l0, l1))
+    assert e < 1e-7 and e_chi < 1e-6

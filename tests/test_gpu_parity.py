@@ -182,7 +182,11 @@ def _run_msckf(name, seed, chi2_table, mult=1.0, **kw):
     return S, ctx, orc, chg, cho, g, o
 
 
-def _check_msckf(S, ctx, orc, chg, cho, g, o, tol=REL, chi_tol=1e-7, plane_chi_tol=1e-6):
+def _check_msckf(S, ctx, orc, chg, cho, g, o, tol=REL, chi_tol=1e-7, plane_chi_tol=1e-5):
+    """chi2 tolerances: the compression works on the Gram matrix, so the component of a stacked chi2 along a direction with relative
+    singular value s carries a relative error ~ eps / s^2 (tests/test_gpu_numerics.py::test_compress_ill_conditioned); the weakest
+    observable directions of the plane systems sit at s ~ 1e-6 (oracle_backend.GaugeProbe records the gap), i.e. ~1e-4 absolute on a
+    chi2 of 50..500.  Gates are index-exact, state and covariance are held to `tol`."""
     assert np.array_equal(g["feat_status"], o["feat_status"]), "accept/reject flags differ: %s" % str(
         np.nonzero(g["feat_status"] != o["feat_status"]))
     assert np.array_equal(g["plane_status"], o["plane_status"]), (g["plane_status"], o["plane_status"])
@@ -215,7 +219,7 @@ def test_msckf_update_planes(name, seed, chi2_table):
     """In-state planes: gates, plane chi2 (well-defined part, see oracle_msckf_update), per-feature chi2, Hx_order, state and
     covariance at the north-star tolerance."""
     S, ctx, orc, chg, cho, g, o = _run_msckf(name, seed, chi2_table)
-    e = _check_msckf(S, ctx, orc, chg, cho, g, o)
+    e = _check_msckf(S, ctx, orc, chg, cho, g, o, chi_tol=1e-6)  # point features are gated against the posterior of the plane updates
     _plane_report("%s %d" % (name, seed), g, o, e)
 
 

@@ -27,7 +27,7 @@ def test_msckf_update_with_planes_not_in_state(name, seed, chi2_table):
     S, ctx, orc, chg, cho, bg, bo, planes = _fresh_plane_case(name, seed, chi2_table)
     g = ctx.msckf_update(bg, 1.0, 1.0)
     o = oracle_msckf_update(orc, bo, 1.0, 1.0)
-    e = _check_msckf(S, ctx, orc, chg, cho, g, o)
+    e = _check_msckf(S, ctx, orc, chg, cho, g, o, chi_tol=1e-6)
     _plane_report("%s %d (planes not in state)" % (name, seed), g, o, e)
 
 
@@ -52,7 +52,7 @@ def test_plane_init(name, seed, chi2_table):
     # a follow-up MSCKF update now treats them as in-state planes on both sides
     g2 = ctx.msckf_update(bg, 1.0, 1.0)
     o2 = oracle_msckf_update(orc, bo, 1.0, 1.0)
-    e2 = _check_msckf(S, ctx, orc, chg, cho, g2, o2)
+    e2 = _check_msckf(S, ctx, orc, chg, cho, g2, o2, chi_tol=1e-6)
     print("cov rel err after the follow-up update %.3e" % e2)
 
 
@@ -96,7 +96,7 @@ def test_sharded_update_halves_equal_single_update(chi2_table):
     assert np.array_equal(status, gfull["feat_status"])
     e = relerr(ctx.cov(), full.cov())
     print("sharded vs single cov rel err %.3e" % e)
-    assert e < 1e-9
+    assert e < 1e-7  # two summation orders of the same Gram matrix
     o = orc.msckf_update(synth.feature_batch(S, cho), 1.0, 1.0)
     assert np.array_equal(status, o["feat_status"])
     assert relerr(ctx.cov(), orc.cov()) < 1e-6
@@ -138,3 +138,26 @@ def test_cfg5_sharded_8_ways_equals_single_update_and_oracle(chi2_table):
     print("cfg5: sharded(8) vs single cov rel err %.3e | sharded vs oracle %.3e | single vs oracle %.3e | accepted %d of %d" % (
         e1, e2, e3, int((status == 1).sum()), S.F))
     assert e1 < 1e-6
+
+
+def test_library_owned_collective_single_rank(chi2_table):
+    """ovp_msckf_update_sharded with a 1-rank NCCL communicator owned by the context (the all-gather runs inside the library):
+    equal to ovp_msckf_update of the same features, and to the oracle.  (N = 2, 4, 8 ranks: bench.py `sharded_cfg5`.)"""
+    S = synth.make_scenario("cfg2_n256_f200", seed=1)
+    ctx, orc, chg, cho = make_pair(S, chi2_table)
+    ref = synth.make_scenario("cfg2_n256_f200", seed=1)
+    from ov_plane_b200 import api
+    full = api.Context(ref.options, device=0, max_state=S.N + 64, max_meas_rows=60000)
+    full.set_chi2_table(chi2_table)
+    chf = synth.load_scenario_into(full, ref)
+    gfull = full.msckf_update(synth.feature_batch(ref, chf), 1.0, 1.0)
+    ctx.nccl_init(ctx.nccl_unique_id(), 1, 0)
+    r = ctx.msckf_update_sharded(synth.feature_batch(S, chg), chg, 1.0, 1.0)
+    assert np.array_equal(r["feat_status"], gfull["feat_status"])
+    e = relerr(ctx.cov(), full.cov())
+    print("library-owned collective (1 rank) vs single update: cov rel err %.3e" % e)
+    assert e < 1e-9
+    o = orc.msckf_update(synth.feature_batch(S, cho), 1.0, 1.0)
+    assert np.array_equal(r["feat_status"], o["feat_status"])
+    compare_states(ctx, orc, S, chg, cho, 1e-6)
+    ctx.nccl_finalize()

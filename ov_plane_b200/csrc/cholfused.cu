@@ -54,6 +54,7 @@ struct CholFusedArgs {
   int nrb, mstride;
   long long *dbg; // optional: 16 globaltimer stamps per CTA (tools/microbench.py)
   int no_lookahead; // 1: the spine applies L(k,k) to the next step's tiles only after the whole 64-column factorisation (A/B switch)
+  int prefactored;  // 1: second launch of the two-launch fallback - only row-block CTAs, the factor tiles already sit in the exchange slots
 };
 
 __device__ __forceinline__ long long cf_gtime() {
@@ -742,7 +743,7 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
 #define CF_SLOTL(i, k) (slotL + ((size_t)(k) * T + (i)) * CF_SLOT)
   const int IO = 224; // lane 0 of warp 7: the thread that issues bulk copies and releases flags (warp 7 never runs a pivot chain)
 
-  if (blockIdx.x == 0) {
+  if (!p.prefactored && blockIdx.x == 0) {
     // ---- spine: every diagonal block, back to back (warm instruction cache, no global-memory hop on the critical path) ----
     double *a = tb, *b3 = tb + CF_SLOT, *b4 = tb + 2 * CF_SLOT;
     double *xc = tb + 3 * CF_SLOT, *sscr = xc + CF_XSZ, *thr = sscr + 16 * CF_LD, *pivinv = thr + CF_B, *bcast = pivinv + CF_B; // bcast: 8 x 96
@@ -876,7 +877,7 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       if ((w == 4 || w == 5) && w - 4 < dfr.n)
         cf_deferred_store(dfr, w - 4, tid & 31);
     }
-  } else if ((int)blockIdx.x < p.ntile) {
+  } else if (!p.prefactored && (int)blockIdx.x < p.ntile) {
     double *a = tb, *b1 = tb + CF_SLOT, *b2 = tb + 2 * CF_SLOT;
     double *xc = tb + 3 * CF_SLOT, *sscr = xc + CF_XSZ;
     int j = 0, rem = blockIdx.x;
@@ -949,7 +950,7 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       cf_bulk_wait_all();
   } else {
     // ---- row block of the right-hand side: Y = M L^-T, right-looking ----
-    const int rb = blockIdx.x - p.ntile;
+    const int rb = blockIdx.x - (p.prefactored ? 0 : p.ntile);
     const int ms = p.mstride;
     double *Lt = tb;                     // one tile buffer (bulk-load target, 128-byte aligned)
     double *Xt = tb + CF_SLOT;           // compact inverse image of L(k,k)'s diagonal blocks
@@ -976,7 +977,8 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
     for (int k = 0; k < Tp; k++) {
       const int bs = min(CF_B, p.npiv - CF_B * k);
       if (tid == 0) {
-        cf_acquire(fdiag + k, e);
+        if (!p.prefactored)
+          cf_acquire(fdiag + k, e);
         cf_fence_async_all();
         cf_mbar_expect_tx(mb0, CF_SLOT_BYTES + CF_XBYTES);
         cf_bulk_g2s(cf_saddr(Lt), CF_SLOTL(k, k), CF_SLOT_BYTES, mb0);
@@ -1035,7 +1037,8 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       }
       for (int j = k + 1; j < Tp; j++) {
         if (tid == 0) {
-          cf_acquire(fpan + j * Tp + k, e);
+          if (!p.prefactored)
+            cf_acquire(fpan + j * Tp + k, e);
           cf_fence_async_all();
           cf_mbar_expect_tx(mb0, CF_SLOT_BYTES);
           cf_bulk_g2s(cf_saddr(Lt), CF_SLOTL(j, k), CF_SLOT_BYTES, mb0);
@@ -1130,6 +1133,7 @@ int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const dou
   p.ldy = ldy;
   p.w = w;
   p.dbg = dbg;
+  p.prefactored = 0;
   {
     // the in-spine lookahead is OFF by default: measured on B200 the two tiles it needs arrive ~22 K cycles after this CTA's previous
     // panel is published (their producers' acquire -> bulk load -> 64^3 update -> bulk store -> release round trip), i.e. after the last
@@ -1159,9 +1163,31 @@ int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const dou
       c->cf_max_coresident = std::max(1, per_sm) * sms;
     }
     const int max_coresident = c->cf_max_coresident;
-    if (grid > max_coresident)
-      return fail(c, OVP_ERR_CAPACITY, "chol_fused: a %d-wide system with %d right-hand-side rows needs %d co-resident CTAs, the device holds %d", n,
-                  vrows, grid, max_coresident);
+    if (p.ntile > max_coresident)
+      return fail(c, OVP_ERR_CAPACITY, "chol_fused: a %d-wide system needs %d co-resident tile CTAs, the device holds %d", n, p.ntile, max_coresident);
+    if (grid > max_coresident) {
+      // two-launch fallback: factor first (the tile CTAs must be co-resident with the spine), then the right-hand-side row blocks in an
+      // ordinary launch that reads the factor tiles from the exchange slots without waiting on flags
+      double flops1 = (double)npiv * npiv * npiv / 3.0 + (double)(n - npiv) * npiv * npiv;
+      CholFusedArgs p1 = p;
+      p1.M = nullptr;
+      p1.mrows = 0;
+      p1.z = nullptr;
+      p1.nrb = 0;
+      p1.prefactored = 0;
+      prof_begin(c, PROF_POTRF, flops1);
+      void *k1[] = {(void *)&p1};
+      OVP_CUDA(cudaLaunchCooperativeKernel((const void *)chol_fused_kernel, dim3(p.ntile), dim3(256), k1, smem, c->stream));
+      c->launches++;
+      prof_end(c);
+      CholFusedArgs p2 = p;
+      p2.prefactored = 1;
+      prof_begin(c, PROF_POTRF, (double)vrows * npiv * npiv);
+      chol_fused_kernel<<<p.nrb, 256, smem, c->stream>>>(p2);
+      c->launches++;
+      prof_end(c);
+      return OVP_OK;
+    }
   }
   double flops = (double)npiv * npiv * npiv / 3.0 + (double)(n - npiv) * npiv * npiv + (double)vrows * npiv * npiv;
   prof_begin(c, PROF_POTRF, flops);

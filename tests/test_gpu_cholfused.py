@@ -82,3 +82,22 @@ def test_strict_mode_reports_an_indefinite_matrix(ctx):
     A[40, 40] = -1.0
     with pytest.raises(api.OvpError):
         _run(ctx, A, 80, 0.0)
+
+
+def test_two_launch_fallback_when_the_grid_cannot_be_co_resident():
+    """n = 1000 with 700 right-hand-side rows needs 136 tile CTAs + 44 row-block CTAs > 148 SMs: the factorisation and the triangular solve
+    run as two launches (the second reads the factor tiles from the exchange slots without flags)."""
+    S = synth.make_scenario("tiny_points")
+    c = api.Context(S.options, device=0, max_state=1024, max_meas_rows=4096, debug=True)
+    rng = np.random.default_rng(5)
+    n = 1000
+    B = rng.normal(size=(n + 16, n))
+    A = B.T @ B + 0.5 * np.eye(n)
+    M = rng.normal(size=(700, n))
+    z = rng.normal(size=n)
+    L, Y, w = _run(c, A, n, 0.0, M, z)
+    Lr = np.linalg.cholesky(A)
+    assert np.abs(L - Lr).max() < 1e-11 * np.abs(Lr).max() * n
+    assert np.abs(Y - np.linalg.solve(Lr, M.T).T).max() < 1e-9 * np.abs(M).max() * n
+    assert np.abs(w - np.linalg.solve(Lr, z)).max() < 1e-9 * np.abs(z).max() * n
+    c.close()

@@ -29,5 +29,6 @@ def test_triangulation_matches_the_oracle(name, chi2_table):
     print(name, "triangulated %d of %d, max |gpu - oracle| %.2e m, median / max distance to the simulated truth %.3f / %.3f m" % (
         ok.sum(), S.F, d, np.median(err_truth), err_truth.max()))
     assert ok.sum() > 0.8 * S.F and sg[0] == 0
-    assert d < 1e-7          # both run LM on single-precision residuals: agreement is limited by those roundings, not by the algebra
+    assert d < 5e-5          # both run LM on SINGLE-precision residuals (ov_core: uvs_norm and the predicted z are floats): one float ulp of the
+                             # reprojection (6e-8) moves a point at 3-5 m depth seen over a 0.4 m baseline by ~1e-6 .. 1e-5 m
     assert np.median(err_truth) < 0.5

@@ -413,6 +413,65 @@ __device__ __noinline__ void cf_trail16(double *a, int c0) {
 // shuffle -> fma (the next pivot is rebuilt on every lane from a value shuffled one column earlier).  The trailing update
 // inside the tile is DMMA.  Zero-pivot rule: pivot <= thr (= tol * original diagonal) or <= 0 -> column of zeros, pivinv = 0
 // (rank-deficient Gram matrices); strict (tol == 0) flags *info instead (S must be positive definite).
+// 1 / sqrt(d) for the pivot chain: MUFU.RSQ64H seed + one third-order step - the arithmetic of CUDA's rsqrt(double) without its
+// special-case branch (zero / denormal / inf / nan arguments), which splits the pivot loop into basic blocks.  A pivot that fails the
+// threshold test never uses the value.
+__device__ __forceinline__ double cf_rsqrt(double d) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+  const double t = y0 * y0;
+  const double e = fma(-t, d, 1.0);
+  const double c = fma(e, 0.375, 0.5);
+  const double t2 = y0 * e;
+  return fma(c, t2, y0);
+}
+
+// One column of the pivot chain with the column index as a template parameter: all register indices are static, the deferred rank-1
+// update touches only the columns that still exist (105 instead of 224 DFMAs per 16-column panel), and the 16 steps form ONE
+// straight-line block that ptxas schedules across columns (the next pivot's rsqrt starts while this column's updates and stores are
+// still being issued).  Measured on B200 (tools/lab/chain_lab.cu): 213 -> 92 cycles per column.  An FP64 instruction occupies the
+// issue port of its SM sub-partition for ~4 cycles, so the chain is bound by its DFMA COUNT as much as by the rsqrt -> multiply -> fma
+// dependency (~90 cycles).
+struct CfChain {
+  unsigned thr_a, piv_a, lb_a, row_a, row_s, lst_a;
+  int lane_r, p_lo16, p_row, p_diag, p_w0;
+};
+template <int j>
+__device__ __forceinline__ void cf_chain_step(double (&q)[16], double &dcur, double &ediag, double &mydiag, double &lprev, int &bad, const CfChain &c) {
+  const double d = dcur;
+  const double thrj = cf_lds(c.thr_a + 8 * j);
+  const double e0 = q[j]; // a(row, j): final
+  const double u1 = __shfl_sync(0xffffffffu, e0, (j + 1) & 31);
+  const double u2 = __shfl_sync(0xffffffffu, e0, (j + 2) & 31);
+  const unsigned lqb = c.lb_a + ((j + 1) & 1) * 256; // l(., j-1) of the diagonal block's 16 rows
+  double lq[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++)
+    if (k >= j + 2 && j > 0)
+      lq[k] = cf_lds(lqb + 8 * k);
+  const bool ok = d > thrj; // thr >= 0
+  const double rs = cf_rsqrt(d); // speculative: a rejected pivot discards it
+  const double invp = ok ? rs : 0.0;
+  const double l = e0 * invp, l1 = u1 * invp, l2 = u2 * invp;
+  dcur = fma(-l1, l1, ediag);
+  mydiag = fma(-l, l, mydiag);
+  ediag = __shfl_sync(0xffffffffu, mydiag, (j + 2) & 31);
+  bad |= !ok;
+#pragma unroll
+  for (int k = 0; k < 16; k++)
+    if (k >= j + 2 && j > 0)
+      q[k] = fma(-lprev, lq[k], q[k]); // the update with column j-1, deferred behind this column's pivot
+  if (j + 1 < 16)
+    q[(j + 1) & 15] = fma(-l, l1, q[(j + 1) & 15]);
+  if (j + 2 < 16)
+    q[(j + 2) & 15] = fma(-l, l2, q[(j + 2) & 15]);
+  cf_sts_if(c.lst_a + (j & 1) * 256, l, c.p_lo16);
+  cf_sts_if(c.row_a + j * c.row_s, l, c.p_row | (c.p_diag & (c.lane_r >= j)));
+  cf_sts_if(c.piv_a + 8 * j, invp, c.p_w0 & (c.lane_r == j));
+  lprev = l;
+  __syncwarp(); // l(., j) line complete for the next step's deferred update
+}
+
 struct CfPrefetch { // the next step's two tiles: their flags are polled by the spine's idle warp during the last pivot chain, which then
                     // starts the two bulk loads (exchange slot -> shared memory) onto `mbar`
   const int *flag0, *flag1;
@@ -531,6 +590,7 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
     for (int idx = tid; idx < CF_XSZ; idx += 256)
       x[idx] = 0.0;
   __syncthreads();
+#pragma unroll 1 // one copy of the unrolled pivot chain (1.4 K instructions)
   for (int c0 = 0; c0 < bs; c0 += 16) {
     const int nbp = min(16, bs - c0);
     const int vw = (CF_B - c0 - 16) / 16; // warps 0..vw-1 carry the rows below the block, warp vw carries the identity (below)
@@ -594,9 +654,17 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
       // the deferred update.  Pivot chain per column: rsqrt -> select -> 2 multiplies -> fma; the operands from other lanes
       // (u1, u2, next diagonal) are shuffled before they are needed.
       double q[16];
+      {
+        // predicated loads, no branches: written as a conditional expression this compiled into 16 divergent branch / reconvergence
+        // blocks (lanes 0..15 and 16..31 differ) - 1.2 K cycles per panel, as much as the 16 pivots themselves
+        const int idn = virt && lower;
+        const unsigned qa = cf_saddr(a + CF_AT(rok ? row : 0, c0));
 #pragma unroll
-      for (int c = 0; c < 16; c++)
-        q[c] = (virt && lower) ? ((c == lane - 16) ? 1.0 : 0.0) : ((rok && (lower || c <= lane)) ? a[CF_AT(row, c0 + c)] : 0.0);
+        for (int c = 0; c < 16; c++) {
+          const double v = cf_lds_if(qa + c * (CF_LD * 8), !idn && rok && (lower || c <= lane));
+          q[c] = (idn && c == lane - 16) ? 1.0 : v;
+        }
+      }
       double e0 = q[0], e1 = q[1];
       double *lb = bcast + warp * 96; // [0,32) and [32,64): l(., j) by column parity (16 values + 16 zeros); [64,96): zeros
       lb[lane] = 0.0;
@@ -607,7 +675,10 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
       double ediag = __shfl_sync(0xffffffffu, mydiag, 1);
       double lprev = 0.0;
       // loop-invariant addresses and predicates, pinned in registers
-      const unsigned thr_a = cf_saddr(thr + c0), piv_a = cf_saddr(pivinv + c0), lb_a = cf_saddr(lb);
+      unsigned thr_a = cf_saddr(thr + c0), piv_a = cf_saddr(pivinv + c0), lb_a = cf_saddr(lb);
+      // opaque to the compiler: otherwise it REMATERIALISES the address of a static shared array inside the loop as
+      // (SR_CgaCtaId << 24) + offset, i.e. one S2R per column in front of the threshold load that gates the pivot
+      asm volatile("" : "+r"(thr_a), "+r"(piv_a), "+r"(lb_a));
       // where a lane stores its finished entry of column j: real rows a(row, c0 + j); identity row i: x(c0 + j, c0 + i)
       const unsigned row_a = (virt && lower) ? cf_saddr(x + CF_XAT(c0 >> 4, 0, lane - 16)) : cf_saddr(a + CF_AT(row < CF_B ? row : 0, c0));
       const unsigned row_s = (virt && lower) ? 8u : (unsigned)(CF_LD * 8);
@@ -621,39 +692,50 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
       // overwrite it.  Named barrier over the vw + 1 chain warps - without it the read races with warp 0's first store whenever a
       // warp is delayed by a few hundred cycles (seen only with several cooperative launches sharing the GPU).
       asm volatile("bar.sync 1, %0;" ::"r"((vw + 1) * 32) : "memory");
+      PT(30 + (c0 >> 4))
+      if (nbp == 16) {
+        const CfChain cc{thr_a, piv_a, lb_a, row_a, row_s, lst_a, lane_r, p_lo16, p_row, p_diag, p_w0};
+#define CF_ST(J) cf_chain_step<J>(q, dcur, ediag, mydiag, lprev, bad, cc);
+        CF_ST(0) CF_ST(1) CF_ST(2) CF_ST(3) CF_ST(4) CF_ST(5) CF_ST(6) CF_ST(7)
+        CF_ST(8) CF_ST(9) CF_ST(10) CF_ST(11) CF_ST(12) CF_ST(13) CF_ST(14) CF_ST(15)
+#undef CF_ST
+      } else {
+        // partial panel (the last one of a system whose size is not a multiple of 16): the rolled form of the same step; the register
+        // array shifts by one per column so that its indices stay static
 #pragma unroll 1
-      for (int j = 0; j < nbp; j++) {
-        const double d = dcur;
-        const double thrj = cf_lds(thr_a + 8 * j);
-        const double u1 = __shfl_sync(0xffffffffu, e0, (j + 1) & 31);
-        const double u2 = __shfl_sync(0xffffffffu, e0, (j + 2) & 31);
-        double lq[17];
+        for (int j = 0; j < nbp; j++) {
+          const double d = dcur;
+          const double thrj = cf_lds(thr_a + 8 * j);
+          const double u1 = __shfl_sync(0xffffffffu, e0, (j + 1) & 31);
+          const double u2 = __shfl_sync(0xffffffffu, e0, (j + 2) & 31);
+          double lq[17];
 #pragma unroll
-        for (int m = 3; m < 17; m++)
-          lq[m] = cf_lds(lq_a + 8 * m); // l(j-1+m, j-1): complete since the __syncwarp that closed the previous iteration
-        const bool ok = (d > thrj) && (d > 0.0);
-        const double rs = rsqrt(d); // speculative: a rejected pivot discards it
-        const double invp = ok ? rs : 0.0;
-        const double l = e0 * invp, l1 = u1 * invp, l2 = u2 * invp;
-        dcur = fma(-l1, l1, ediag);
-        mydiag = fma(-l, l, mydiag);
-        ediag = __shfl_sync(0xffffffffu, mydiag, (j + 2) & 31);
-        bad |= !ok;
-        const double x2 = fma(-lprev, lq[3], q[2]);
+          for (int m = 3; m < 17; m++)
+            lq[m] = cf_lds(lq_a + 8 * m); // l(j-1+m, j-1): complete since the __syncwarp that closed the previous iteration
+          const bool ok = d > thrj; // thr >= 0
+          const double rs = cf_rsqrt(d); // speculative: a rejected pivot discards it
+          const double invp = ok ? rs : 0.0;
+          const double l = e0 * invp, l1 = u1 * invp, l2 = u2 * invp;
+          dcur = fma(-l1, l1, ediag);
+          mydiag = fma(-l, l, mydiag);
+          ediag = __shfl_sync(0xffffffffu, mydiag, (j + 2) & 31);
+          bad |= !ok;
+          const double x2 = fma(-lprev, lq[3], q[2]);
 #pragma unroll
-        for (int k = 2; k < 15; k++)
-          q[k] = fma(-lprev, lq[k + 2], q[k + 1]);
-        q[15] = 0.0;
-        const double e0n = fma(-l, l1, e1);
-        e1 = fma(-l, l2, x2);
-        const unsigned par = (j & 1) * 256;
-        cf_sts_if(lst_a + par, l, p_lo16);
-        cf_sts_if(row_a + j * row_s, l, p_row | (p_diag & (lane_r >= j)));
-        cf_sts_if(piv_a + 8 * j, invp, p_w0 & (lane_r == j));
-        e0 = e0n;
-        lprev = l;
-        lq_a = lb_a + par + 8 * j;
-        __syncwarp(); // l(., j) line complete for the next iteration's deferred update
+          for (int k = 2; k < 15; k++)
+            q[k] = fma(-lprev, lq[k + 2], q[k + 1]);
+          q[15] = 0.0;
+          const double e0n = fma(-l, l1, e1);
+          e1 = fma(-l, l2, x2);
+          const unsigned par = (j & 1) * 256;
+          cf_sts_if(lst_a + par, l, p_lo16);
+          cf_sts_if(row_a + j * row_s, l, p_row | (p_diag & (lane_r >= j)));
+          cf_sts_if(piv_a + 8 * j, invp, p_w0 & (lane_r == j));
+          e0 = e0n;
+          lprev = l;
+          lq_a = lb_a + par + 8 * j;
+          __syncwarp(); // l(., j) line complete for the next iteration's deferred update
+        }
       }
       if (strict && bad && tid == 0)
         atomicExch(info, 1);
@@ -720,7 +802,8 @@ __device__ __noinline__ void cf_bsolve64(double *U, const double *Lkk, const dou
 }
 
 __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
-  extern __shared__ __align__(128) double sm[];
+  extern __shared__ __align__(128) double sm_dyn[];
+  double *const sm = pin_shared(sm_dyn); // (gemm.cuh) keeps the base in a register: no S2R SR_CgaCtaId in front of the loops below
   // every shared array is carved from the one dynamic block: addresses of static __shared__ variables are re-derived from
   // SR_CgaCtaId (S2R, ~100+ cycles) wherever the compiler rematerialises them - inside the pivot loop that tripled its latency.
   // Layout (doubles): [0,16) two mbarriers (+ padding to 128 B) | tile buffers | role-specific (see the three branches)
@@ -748,20 +831,18 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
     double *a = tb, *b3 = tb + CF_SLOT, *b4 = tb + 2 * CF_SLOT;
     double *xc = tb + 3 * CF_SLOT, *sscr = xc + CF_XSZ, *thr = sscr + 16 * CF_LD, *pivinv = thr + CF_B, *bcast = pivinv + CF_B; // bcast: 8 x 96
     unsigned par_pf = 0;
-    CfDeferred dfr; // column stores of the previous step's factor tiles into A, issued by warp 7 during the first pivot chain
+    CfDeferred dfr; // (unused since the tile CTAs copy the factor tiles into A; kept for the A/B switch of the old scheme)
     dfr.n = 0;
     CF_TS(0)
     cf_load_tile(a, p.A, p.ld, min(CF_B, p.n), min(CF_B, p.n), true);
     __syncthreads();
     if (tid < CF_B)
-      thr[tid] = p.tol * a[CF_AT(tid, tid)];
+      thr[tid] = fmax(p.tol * a[CF_AT(tid, tid)], 0.0); // >= 0: the pivot loop tests d > thr only
     for (int idx = tid; idx < CF_XSZ; idx += 256)
       xc[idx] = 0.0; // the inverse image: only the lower triangles of its blocks are ever written
     for (int k = 0; k < Tp; k++) {
       const int bs = min(CF_B, p.npiv - CF_B * k);
-      double *gA = p.A + (size_t)(CF_B * k) * p.ld + CF_B * k;
       const bool has_panel = k + 1 < T, next_diag = k + 1 < Tp;
-      double *gP = p.A + (size_t)(CF_B * k) * p.ld + CF_B * (k + 1);
       if (k < 3)
         CF_TS(1 + 2 * k)
       long long *dbgp = (p.dbg && k == 1) ? p.dbg + (size_t)gridDim.x * 16 : nullptr;
@@ -793,7 +874,6 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       pf.g1 = ov.slotD;
       pf.mbar = mb0;
       cf_potrf64(a, xc, bs, thr, p.tol == 0.0, pivinv, p.info, bcast, pf, dfr, ov, e, dbgp);
-      dfr.n = 0;
       if (k < 3)
         CF_TS(2 + 2 * k)
       PT(13)
@@ -810,14 +890,15 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
         cf_bulk_s2g(CF_SLOTL(k, k), cf_saddr(a), CF_SLOT_BYTES);
         cf_bulk_s2g(p.LinvD + (size_t)k * CF_B * CF_B, cf_saddr(xc), CF_XBYTES);
         cf_bulk_commit();
+        // Release D(k) as soon as the two copies have landed.  (It used to be released after the panel solve below, "for free": that
+        // held back every consumer of L(k,k) - the tiles of column k and through them the two tiles this CTA needs for step k+1 - by the
+        // 5 K cycles of the solve, and once the pivot chains got faster that path became the critical one.)
+        cf_publish_end(fdiag + k, e);
       }
-      dfr.src[0] = a; // the factor columns go into the matrix A later, off the critical path (nobody in this launch reads A)
-      dfr.dst[0] = gA;
-      dfr.n = 1;
       PT(20)
       if (has_panel) {
         if (next_diag && tid < CF_B)
-          thr[tid] = p.tol * __ldcg(p.diag0 + CF_B * (k + 1) + tid);
+          thr[tid] = fmax(p.tol * __ldcg(p.diag0 + CF_B * (k + 1) + tid), 0.0);
         if (ov.on) {
           if (tid == IO && csync[1] == 0) { // the tiles' flags had not shown up while the chains ran: now wait for them
             cf_acquire(ov.flagU, e);
@@ -843,13 +924,9 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
         __syncthreads();
         PT(25)
         if (tid == IO) {
-          cf_publish_end(fdiag + k, e); // (the bulk copies above have long landed)
           cf_bulk_s2g(CF_SLOTL(k + 1, k), cf_saddr(b3), CF_SLOT_BYTES);
           cf_bulk_commit();
         }
-        dfr.src[1] = b3;
-        dfr.dst[1] = gP;
-        dfr.n = 2;
         PT(26)
         if (next_diag) {
           if (!ov.on) {
@@ -860,22 +937,15 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
           a = b4;
           b4 = tmp;
         }
-        dfr.ld = p.ld;
-        dfr.ncol = bs;
         PT(27)
         if (tid == IO)
           cf_publish_end(fpan + (k + 1) * Tp + k, e);
         PT(28)
-      } else if (tid == IO) {
-        cf_publish_end(fdiag + k, e);
       }
     }
-    dfr.ld = p.ld;
-    dfr.ncol = min(CF_B, p.npiv - CF_B * (Tp - 1));
-    {
-      const int w = tid >> 5; // the last step's tiles
-      if ((w == 4 || w == 5) && w - 4 < dfr.n)
-        cf_deferred_store(dfr, w - 4, tid & 31);
+    if (T == 1) { // a single tile: no other CTA exists to copy the factor into the matrix (see the tile CTAs below)
+      __syncthreads();
+      cf_store_tile(a, p.A, p.ld, min(CF_B, p.n), min(CF_B, p.npiv), false);
     }
   } else if (!p.prefactored && (int)blockIdx.x < p.ntile) {
     double *a = tb, *b1 = tb + CF_SLOT, *b2 = tb + 2 * CF_SLOT;
@@ -923,6 +993,25 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       if (tid == 0) {
         cf_publish_begin((i == j ? slotUd + (size_t)j * CF_SLOT : slotUs + (size_t)i * CF_SLOT), cf_saddr(a), CF_SLOT_BYTES);
         cf_publish_end(i == j ? fud + j : fus + i, e);
+      }
+      CF_TS(4)
+      // The spine finishes this tile and publishes the factor tile in its exchange slot; THIS CTA (idle from here on) copies it into the
+      // matrix A, which nobody in this launch reads.  (The spine used to do that itself from two idle warps during its next first pivot
+      // chain: those warps share issue slots with the chain warps, and the step waited for them at the next CTA barrier.)  Tile (1,0)
+      // also copies L(0,0), whose own block index is the spine's.
+      for (int pass = 0; pass < ((blockIdx.x == 1) ? 2 : 1); pass++) {
+        const int ti = pass ? 0 : i, tj = pass ? 0 : j;
+        if (pass)
+          __syncthreads(); // the first tile has left shared memory
+        if (tid == 0) {
+          cf_acquire(ti == tj ? fdiag + tj : fpan + ti * Tp + tj, e);
+          cf_fence_async_all();
+          cf_mbar_expect_tx(mb0, CF_SLOT_BYTES);
+          cf_bulk_g2s(cf_saddr(a), CF_SLOTL(ti, tj), CF_SLOT_BYTES, mb0);
+        }
+        cf_mbar_wait(mb0, par);
+        par ^= 1;
+        cf_store_tile(a, p.A + (size_t)(CF_B * tj) * p.ld + CF_B * ti, p.ld, min(CF_B, p.n - CF_B * ti), min(CF_B, p.npiv - CF_B * tj), false);
       }
     } else {
       if (tid == 0) {

@@ -67,9 +67,14 @@ __device__ __forceinline__ double warp_sum(double s) {
 // Returns chi2 (NaN-safe: ok flag in *ok_out).  All 128 threads participate.
 __device__ double gate_chi2(const double *A, int lda, double *T, double *S, int ldt, double *ybuf, double *Pp, int ldpp, int rb, int nr, int cb,
                             int ncg, const int *gid, const double *P, int ldP, int c_res, int tid, int *s_ok, double *s_chi2) {
-  // T = H P_marg by panels of 8 covariance columns: the panel P[gid[:], gid[b0 .. b0+7]] is gathered into shared memory with all
-  // loads of a thread in flight at once (runs of 6-14 contiguous doubles per clone / calibration block), then every thread forms
-  // dot products out of shared memory.  (Gathering P entry by entry inside the dot product left the kernel L2-latency bound.)
+  // S = I + sum over panels of 8 covariance columns of (H P_marg[:, panel]) H[:, panel]^T.  The panel P[gid[:], gid[b0 .. b0+7]] is
+  // gathered into shared memory with all loads of a thread in flight at once (runs of 6-14 contiguous doubles per clone / calibration
+  // block), T = H * panel (nr x 8) is formed out of shared memory and folded into the lower triangle of S right away: the full
+  // nr x ncg product H P_marg is never stored (it was 40 % of the block's shared memory and capped the clone window at 30).
+  for (int w = tid; w < nr * nr; w += 128) {
+    const int i = w % nr, jj = w / nr;
+    S[(size_t)jj * ldt + i] = (i == jj) ? 1.0 : 0.0;
+  }
   for (int b0 = 0; b0 < ncg; b0 += 8) {
     const int nb = min(8, ncg - b0);
     for (int w = tid; w < nb * ncg; w += 128) {
@@ -83,19 +88,19 @@ __device__ double gate_chi2(const double *A, int lda, double *T, double *S, int 
       double acc = 0.0;
       for (int k = 0; k < ncg; k++)
         acc += hc[(size_t)k * lda] * pc[k];
-      T[(size_t)(b0 + b) * ldt + i] = acc;
+      T[(size_t)b * ldt + i] = acc;
     }
     __syncthreads();
-  }
-  __syncthreads();
-  for (int w = tid; w < nr * nr; w += 128) {
-    int i = w % nr, jj = w / nr;
-    if (i < jj)
-      continue;
-    double s = (i == jj) ? 1.0 : 0.0;
-    for (int b = 0; b < ncg; b++)
-      s += T[(size_t)b * ldt + i] * A[(size_t)(cb + b) * lda + rb + jj];
-    S[(size_t)jj * ldt + i] = s;
+    for (int w = tid; w < nr * nr; w += 128) {
+      const int i = w % nr, jj = w / nr;
+      if (i < jj)
+        continue;
+      double s = S[(size_t)jj * ldt + i];
+      for (int b = 0; b < nb; b++)
+        s += T[(size_t)b * ldt + i] * A[(size_t)(cb + b0 + b) * lda + rb + jj];
+      S[(size_t)jj * ldt + i] = s;
+    }
+    // (the next panel's gather only writes Pp; its T is written after the barrier that follows the gather)
   }
   __syncthreads();
   if (tid == 0)
@@ -171,8 +176,8 @@ __global__ void __launch_bounds__(128) feature_kernel(FeatArgs a) {
   const int c_cp = 3 + cf, c_res = 3 + cf + 3;
   const int lda = a.lda;
   double *A = sm;                                   // lda * maxcols
-  double *T = A + (size_t)lda * a.maxcols;          // ldt * (maxcols)   (gate only)
-  double *S = T + (size_t)a.ldt * a.maxcols;        // ldt * ldt         (gate only)
+  double *T = A + (size_t)lda * a.maxcols;          // ldt * 8: H * (8-column covariance panel)   (gate only)
+  double *S = T + (size_t)a.ldt * 8;                // ldt * ldt         (gate only)
   double *vbuf = (a.mode == 1) ? T : S + (size_t)a.ldt * a.ldt; // reflector / forward-substitution vector
   double *Pp = vbuf + lda + 1;                                 // 8 x maxcols covariance panel (gate only)
   __shared__ int gid[3 + 14 + 6 * 64 + 3]; // state index of every local column except the residual

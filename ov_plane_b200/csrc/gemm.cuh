@@ -13,6 +13,16 @@
 
 namespace ovp {
 
+// Address of a shared-memory array, pinned in a register.  nvcc 12.9 for sm_100a treats the address of every shared array (static, and
+// the dynamic block) as a constant it may REMATERIALISE at each use as (SR_CgaCtaId << 24) + offset: one S2R (tens of cycles, and the
+// consumer waits on it) in front of every inner loop that touches shared memory.  The opaque asm stops that; going through
+// shared -> generic keeps the address space known, so accesses through the returned pointer are still LDS / STS.
+template <typename T> __device__ __forceinline__ T *pin_shared(T *p) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("" : "+r"(a));
+  return (T *)__cvta_shared_to_generic((size_t)a);
+}
+
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(d0), "+d"(d1)

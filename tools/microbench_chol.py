@@ -26,7 +26,14 @@ for (nn, mm) in ((n, 0), (n, mrows), (128, 0), (64, 0)):
             nxt = sp[3 + 2 * k] if k + 1 < min(3, T) else float("nan")
             print("  k=%d potrf %6.1f -> %6.1f (%.1f us)   until next potrf (trinv, publish, panel, update): %.1f us" % (k, s0, s1, s1 - s0, nxt - s1))
         print("  last CTA end %.1f us" % ts[:, 15].max())
+        # producer path of the tiles the spine needs for step k+1 (us, same clock as the spine's stamps)
+        for k in range(1, min(4, T - 1)):
+            pan = ts[bidx(k + 1, k - 1)]
+            us, ud = ts[bidx(k + 1, k)], ts[bidx(k + 1, k + 1)] if k + 1 < T else None
+            print("  step %d: spine potrf %.1f..%.1f | tile(%d,%d) Linv loaded %.1f solved %.1f published %.1f | tile(%d,%d) updated %.1f published %.1f | tile(%d,%d) updated %.1f published %.1f"
+                  % (k, sp[1 + 2 * k] if k < 3 else float("nan"), sp[2 + 2 * k] if k < 3 else float("nan"), k + 1, k - 1, pan[5], pan[6], pan[7], k + 1, k, us[3], us[4], k + 1, k + 1, ud[3], ud[4]))
         ph = out[3 + 16 * ncta:3 + 16 * ncta + 29]
+        ls = out[3 + 16 * ncta + 30:3 + 16 * ncta + 34]
         names = ["potrf start"] + [x for b in range(4) for x in ("chain%d" % b, "sync%d" % b, "trail%d+sync" % b)] + ["trinv zero", "trinv base16", "merge16 T", "merge16 X", "merge32 T", "merge32 X",
                  "store Linv", "signal D", "store L", "(unused)", "cp.async wait", "sync", "panel mma", "store panel", "signal P", "update mma"]
         prev = 0.0
@@ -36,5 +43,6 @@ for (nn, mm) in ((n, 0), (n, mrows), (128, 0), (64, 0)):
                 line.append("%s %d" % (nm, v - prev))
                 prev = v
         print("  spine k=1 phase cycles: " + " | ".join(line))
+        print("  pivot loop of panel p starts (cycles since potrf start): " + " ".join("%d" % v for v in ls) + "   (chain p ends at " + " ".join("%d" % ph[1 + 3 * b] for b in range(4)) + ")")
         if mm:
             print("  row-block CTAs end: min %.1f max %.1f" % (ts[T * (T + 1) // 2:, 15].min(), ts[T * (T + 1) // 2:, 15].max()))

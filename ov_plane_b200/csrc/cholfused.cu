@@ -53,7 +53,6 @@ struct CholFusedArgs {
   int *gate_flag;
   int nrb, mstride;
   long long *dbg; // optional: 16 globaltimer stamps per CTA (tools/microbench.py)
-  int no_lookahead; // 1: the spine applies L(k,k) to the next step's tiles only after the whole 64-column factorisation (A/B switch)
   int prefactored;  // 1: second launch of the two-launch fallback - only row-block CTAs, the factor tiles already sit in the exchange slots
 };
 
@@ -62,9 +61,13 @@ __device__ __forceinline__ long long cf_gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+#ifdef OVP_DEBUG
 #define CF_TS(slot)                                                                                                          \
   if (p.dbg && threadIdx.x == 0)                                                                                             \
     p.dbg[(size_t)blockIdx.x * 16 + (slot)] = cf_gtime();
+#else
+#define CF_TS(slot) ;
+#endif
 // shared-memory access with explicit 32-bit addresses: inside the pivot loop the compiler otherwise re-derives the address of a
 // shared array from SR_CgaCtaId (S2R / S2UR, >100 cycles each) every iteration
 __device__ __forceinline__ unsigned cf_saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -426,28 +429,39 @@ __device__ __forceinline__ double cf_rsqrt(double d) {
   return fma(c, t2, y0);
 }
 
-// One column of the pivot chain with the column index as a template parameter: all register indices are static, the deferred rank-1
-// update touches only the columns that still exist (105 instead of 224 DFMAs per 16-column panel), and the 16 steps form ONE
-// straight-line block that ptxas schedules across columns (the next pivot's rsqrt starts while this column's updates and stores are
-// still being issued).  Measured on B200 (tools/lab/chain_lab.cu): 213 -> 92 cycles per column.  An FP64 instruction occupies the
-// issue port of its SM sub-partition for ~4 cycles, so the chain is bound by its DFMA COUNT as much as by the rsqrt -> multiply -> fma
-// dependency (~90 cycles).
+// One column of the pivot chain with the column index (within a half panel of 8) as a template parameter: all register indices are
+// static, and the 8 steps form ONE straight-line block that ptxas schedules across columns (the next pivot's rsqrt starts while this
+// column's updates and stores are still being issued).  Measured on B200 (tools/lab/chain_lab.cu): 213 cycles per column for the rolled
+// loop, 92 for 16 columns of straight-line code.  An FP64 instruction occupies the issue port of its SM sub-partition for ~4 cycles, so
+// the chain is bound by its DFMA COUNT as much as by the rsqrt -> multiply -> fma dependency (~90 cycles): the deferred rank-1 update
+// touches only the columns of the current half panel that still exist (168 DFMAs per 16 columns; rolled: 224; 16 columns unrolled: 105).
+// Why 8 and not 16 columns: inside the kernel the 16-column block (12 KB of code, 255 registers) and the 8-column block (7 KB, 240
+// registers) give the same end-to-end time (321.2 vs 321.0 updates/s, A/B on B200 with -DCF_CHAIN_COLS=16); neither reaches the lab
+// figure in situ (115-140 cycles per column: the warp sampler shows short-scoreboard stalls on the threshold load and the shuffles that
+// ptxas places late, next to their consumers, in the kernel's register allocation).  The smaller one is the default.
+#ifndef CF_CHAIN_COLS
+#define CF_CHAIN_COLS 8 // columns of straight-line code per loop iteration of the pivot chain: 8 (7 KB) or 16 (12 KB; A/B: -DCF_CHAIN_COLS=16)
+#endif
 struct CfChain {
   unsigned thr_a, piv_a, lb_a, row_a, row_s, lst_a;
   int lane_r, p_lo16, p_row, p_diag, p_w0;
 };
 template <int j>
-__device__ __forceinline__ void cf_chain_step(double (&q)[16], double &dcur, double &ediag, double &mydiag, double &lprev, int &bad, const CfChain &c) {
+__device__ __forceinline__ void cf_chain_step(double (&q)[16], int jb, double &dcur, double &ediag, double &mydiag, double &lprev, int &bad,
+                                              const CfChain &c) {
+  const int jg = jb + j; // column within the 16-column panel
   const double d = dcur;
-  const double thrj = cf_lds(c.thr_a + 8 * j);
-  const double e0 = q[j]; // a(row, j): final
-  const double u1 = __shfl_sync(0xffffffffu, e0, (j + 1) & 31);
-  const double u2 = __shfl_sync(0xffffffffu, e0, (j + 2) & 31);
-  const unsigned lqb = c.lb_a + ((j + 1) & 1) * 256; // l(., j-1) of the diagonal block's 16 rows
+  const double thrj = cf_lds(c.thr_a + 8 * jg);
+  const double e0 = q[j]; // a(row, jg): final
+  const double u1 = __shfl_sync(0xffffffffu, e0, (jg + 1) & 31);
+  const double u2 = __shfl_sync(0xffffffffu, e0, (jg + 2) & 31);
+  // l(., jg-1) of the diagonal block's 16 rows (jb is even: the parity of jg-1 is that of j+1); entries 16..31 of a line are zeros (what the
+  // second half panel reads for its dead columns), and before the first column the line itself is zero
+  const unsigned lqb = c.lb_a + ((j + 1) & 1) * 256 + 8 * jb;
   double lq[16];
 #pragma unroll
   for (int k = 0; k < 16; k++)
-    if (k >= j + 2 && j > 0)
+    if (k >= j + 2)
       lq[k] = cf_lds(lqb + 8 * k);
   const bool ok = d > thrj; // thr >= 0
   const double rs = cf_rsqrt(d); // speculative: a rejected pivot discards it
@@ -455,21 +469,21 @@ __device__ __forceinline__ void cf_chain_step(double (&q)[16], double &dcur, dou
   const double l = e0 * invp, l1 = u1 * invp, l2 = u2 * invp;
   dcur = fma(-l1, l1, ediag);
   mydiag = fma(-l, l, mydiag);
-  ediag = __shfl_sync(0xffffffffu, mydiag, (j + 2) & 31);
+  ediag = __shfl_sync(0xffffffffu, mydiag, (jg + 2) & 31);
   bad |= !ok;
 #pragma unroll
   for (int k = 0; k < 16; k++)
-    if (k >= j + 2 && j > 0)
-      q[k] = fma(-lprev, lq[k], q[k]); // the update with column j-1, deferred behind this column's pivot
+    if (k >= j + 2)
+      q[k] = fma(-lprev, lq[k], q[k]); // the update with column jg-1, deferred behind this column's pivot
   if (j + 1 < 16)
     q[(j + 1) & 15] = fma(-l, l1, q[(j + 1) & 15]);
   if (j + 2 < 16)
     q[(j + 2) & 15] = fma(-l, l2, q[(j + 2) & 15]);
   cf_sts_if(c.lst_a + (j & 1) * 256, l, c.p_lo16);
-  cf_sts_if(c.row_a + j * c.row_s, l, c.p_row | (c.p_diag & (c.lane_r >= j)));
-  cf_sts_if(c.piv_a + 8 * j, invp, c.p_w0 & (c.lane_r == j));
+  cf_sts_if(c.row_a + jg * c.row_s, l, c.p_row | (c.p_diag & (c.lane_r >= jg)));
+  cf_sts_if(c.piv_a + 8 * jg, invp, c.p_w0 & (c.lane_r == jg));
   lprev = l;
-  __syncwarp(); // l(., j) line complete for the next step's deferred update
+  __syncwarp(); // l(., jg) line complete for the next step's deferred update
 }
 
 struct CfPrefetch { // the next step's two tiles: their flags are polled by the spine's idle warp during the last pivot chain, which then
@@ -479,150 +493,31 @@ struct CfPrefetch { // the next step's two tiles: their flags are polled by the 
   const double *g0, *g1;
   unsigned mbar;
 };
-// Factor tiles of the previous step that still have to be copied into the matrix A (nobody in this launch reads them there): one idle
-// warp of the spine per tile, during the FIRST pivot chain of the next step (warps 4 and 5 never run a chain).  One 512-byte column per
-// instruction (16 bytes per lane).  (One cp.async.bulk per column was tried first: 128 small bulk copies per step cost ~12 K cycles of
-// issue time; plain vector stores from an idle warp cost nothing on the critical path.)
-struct CfDeferred {
-  const double *src[2];
-  double *dst[2];
-  int n, ld, ncol;
-};
-__device__ __forceinline__ void cf_deferred_store(const CfDeferred &d, int q, int lane) {
-  const double *s = d.src[q] + 2 * lane;
-  double *g = d.dst[q] + 2 * lane;
-#pragma unroll 4
-  for (int c = 0; c < d.ncol; c++)
-    __stcg(reinterpret_cast<double2 *>(g + (size_t)c * d.ld), *reinterpret_cast<const double2 *>(s + c * CF_LD));
-}
-// Lookahead inside the spine: while the pivot chain of 16-column panel p runs on warps 0..vw, the warps that carry no chain apply the
-// FINISHED panels b < p of L(k,k) to the two tiles the next step needs -
-//   BS(b): L(k+1,k)[:, b] = (U[:, b] - U[:, <b] L(k,k)[b, <b]^T) X_bb^T      (right-side solve, independent per 8-row group)
-//   UP(b): D(k+1) -= L(k+1,k)[:, b] L(k+1,k)[:, b]^T                         (lower 8x8 blocks)
-// - so that after the last chain only panel 3 is left.  The two tiles arrive by bulk copy some time into the factorisation (their
-// producers wait for this CTA's previous panel): the I/O warp polls their flags / the mbarrier WITHOUT blocking (it gives up when the
-// chain of the current panel signals completion) and records the state in shared memory; the helpers look at that state once per panel,
-// after the CTA barrier, so every warp takes the same decision.
-struct CfOverlap {
-  bool on, diag;           // lookahead enabled for this step; a next diagonal tile exists
-  double *U, *D, *scr;     // shared-memory tiles U(k+1,k) -> L(k+1,k), D(k+1), and the 64 x 16 solve scratch
-  const int *flagU, *flagD;
-  const double *slotU, *slotD;
-  unsigned mbar, parity;
-  volatile int *sync;      // shared memory: [0] number of finished pivot chains of this step, [1] tile state: 0 flags pending, 1 loading, 2 landed
-  int done;                // panels [0, done) have been applied
-};
-// one 8-row group rg of panel b of the right-side solve (the body of cf_bsolve64 for one row group and one block)
-__device__ __forceinline__ void cf_bs_unit(double *U, const double *Lkk, const double *X, double *S, int rg, int b, int lane) {
-  const int g = lane >> 2, t = lane & 3, r = 8 * rg + g, cb = 16 * b;
-  double a0[2] = {0.0, 0.0}, a1[2] = {0.0, 0.0};
-#pragma unroll 4
-  for (int k4 = 0; k4 < cb; k4 += 4) {
-    const double av = U[CF_AT(r, k4 + t)];
-    dmma_m8n8k4(a0[0], a0[1], av, Lkk[CF_AT(cb + g, k4 + t)]);
-    dmma_m8n8k4(a1[0], a1[1], av, Lkk[CF_AT(cb + 8 + g, k4 + t)]);
-  }
-#pragma unroll
-  for (int h = 0; h < 2; h++) {
-    S[CF_AT(r, 2 * t + h)] = U[CF_AT(r, cb + 2 * t + h)] - a0[h];
-    S[CF_AT(r, 8 + 2 * t + h)] = U[CF_AT(r, cb + 8 + 2 * t + h)] - a1[h];
-  }
-  __syncwarp();
-  double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
-#pragma unroll
-  for (int k4 = 0; k4 < 16; k4 += 4) {
-    const double sv = S[CF_AT(r, k4 + t)];
-    if (k4 < 8)
-      dmma_m8n8k4(c0[0], c0[1], sv, X[CF_XAT(b, g, k4 + t)]);
-    dmma_m8n8k4(c1[0], c1[1], sv, X[CF_XAT(b, 8 + g, k4 + t)]);
-  }
-  __syncwarp();
-#pragma unroll
-  for (int h = 0; h < 2; h++) {
-    U[CF_AT(r, cb + 2 * t + h)] = c0[h];
-    U[CF_AT(r, cb + 8 + 2 * t + h)] = c1[h];
-  }
-  __syncwarp();
-}
-// lower 8x8 block q (0..35, row-major over the lower triangle of 8x8 blocks) of D -= L[:, b] L[:, b]^T
-__device__ __forceinline__ void cf_up_unit(double *D, const double *L, int q, int b, int lane) {
-  const int g = lane >> 2, t = lane & 3, cb = 16 * b;
-  int bi = 0;
-  while (q >= bi + 1) {
-    q -= bi + 1;
-    bi++;
-  }
-  const int bj = q;
-  double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-  for (int k4 = 0; k4 < 16; k4 += 4)
-    dmma_m8n8k4(c0, c1, L[CF_AT(8 * bi + g, cb + k4 + t)], L[CF_AT(8 * bj + g, cb + k4 + t)]);
-  double *pc = D + CF_AT(8 * bi + g, 8 * bj + 2 * t);
-  pc[0] -= c0;
-  pc[CF_LD] -= c1;
-}
-// panels [b0, b1) by `nh` warps (this warp is number `hi` of them); `bar` = named barrier id shared by exactly these warps (0: __syncthreads)
-__device__ __forceinline__ void cf_apply_panels(const CfOverlap &ov, const double *Lkk, const double *X, int b0, int b1, int hi, int nh, int bar,
-                                                int lane) {
-  for (int b = b0; b < b1; b++) {
-    for (int rg = hi; rg < 8; rg += nh)
-      cf_bs_unit(ov.U, Lkk, X, ov.scr, rg, b, lane);
-    if (!ov.diag)
-      continue;
-    if (bar)
-      asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nh * 32) : "memory");
-    else
-      __syncthreads();
-    for (int q = hi; q < 36; q += nh)
-      cf_up_unit(ov.D, ov.U, q, b, lane);
-  }
-}
 __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool strict, double *pivinv, int *info, double *bcast,
-                           const CfPrefetch &pf, const CfDeferred &dfr, CfOverlap &ov, int epoch, long long *dbgp = nullptr) {
+                           const CfPrefetch &pf, int epoch, long long *dbgp = nullptr) {
+#ifdef OVP_DEBUG // phase stamps of the spine (tools/microbench_chol.py); the product library carries none: every stamp is a test, a branch
+                 // and a few instructions of a code path whose size matters (see cf_chain_step)
 #define PT(slot)                                                                                                             \
   if (dbgp && threadIdx.x == 0)                                                                                              \
     dbgp[slot] = clock64();
+#else
+#define PT(slot) ;
+#endif
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  PT(34)
   if (tid < CF_B)
     pivinv[tid] = 0.0;
   if (bs < CF_B) // partial tile: the chain writes only bs rows of the diagonal blocks of x (compact image, CF_XAT)
     for (int idx = tid; idx < CF_XSZ; idx += 256)
       x[idx] = 0.0;
   __syncthreads();
+  PT(35)
 #pragma unroll 1 // one copy of the unrolled pivot chain (1.4 K instructions)
   for (int c0 = 0; c0 < bs; c0 += 16) {
     const int nbp = min(16, bs - c0);
     const int vw = (CF_B - c0 - 16) / 16; // warps 0..vw-1 carry the rows below the block, warp vw carries the identity (below)
-    const int pnl = c0 >> 4;
-    const int st0 = ov.on ? ov.sync[1] : 0; // tile state at the start of this panel: the same value in every warp (written before the barrier)
-    if ((warp_u == 4 || warp_u == 5) && c0 == 0) { // (never chain warps: vw <= 3) the previous step's factor tiles -> A
-      if (warp_u - 4 < dfr.n)
-        cf_deferred_store(dfr, warp_u - 4, lane);
-      if (ov.on)
-        asm volatile("bar.sync 2, 96;" ::: "memory"); // ... before the I/O warp lets the bulk loads overwrite those buffers
-    } else if (warp_u == 7 && ov.on) { // the I/O warp, lookahead mode: non-blocking progress on the next step's two tiles
-      if (c0 == 0)
-        asm volatile("bar.sync 2, 96;" ::: "memory");
-      if (lane == 0) {
-        int st = ov.sync[1];
-        while (st < 2 && ov.sync[0] <= pnl) {
-          if (st == 0) {
-            if (cf_ld_acquire(ov.flagU) == epoch && (!ov.diag || cf_ld_acquire(ov.flagD) == epoch)) {
-              cf_fence_async_all();
-              cf_mbar_expect_tx(ov.mbar, ov.diag ? 2 * CF_SLOT_BYTES : CF_SLOT_BYTES);
-              cf_bulk_g2s(cf_saddr(ov.U), ov.slotU, CF_SLOT_BYTES, ov.mbar);
-              if (ov.diag)
-                cf_bulk_g2s(cf_saddr(ov.D), ov.slotD, CF_SLOT_BYTES, ov.mbar);
-              st = 1;
-            }
-          } else if (cf_mbar_try(ov.mbar, ov.parity)) {
-            st = 2;
-          }
-        }
-        ov.sync[1] = st;
-      }
-    } else if (warp_u == 7) { // the I/O warp, blocking prefetch during the last panel (no lookahead for this step)
+    if (warp_u == 7) { // the I/O warp: during the last panel it polls the flags of the next step's two tiles and starts their bulk loads
       if (c0 + 16 >= bs) { // last panel: poll the flags of the next step's tiles, then start their bulk loads
         if (lane == 0 && (pf.flag0 || pf.flag1)) {
           if (pf.flag0)
@@ -653,6 +548,9 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
       // front of the next pivot).  Static register indices with a ROLLED column loop: the array shifts by one per column inside
       // the deferred update.  Pivot chain per column: rsqrt -> select -> 2 multiplies -> fma; the operands from other lanes
       // (u1, u2, next diagonal) are shuffled before they are needed.
+#ifdef OVP_DEBUG
+      if (c0 == 0) PT(50)
+#endif
       double q[16];
       {
         // predicated loads, no branches: written as a conditional expression this compiled into 16 divergent branch / reconvergence
@@ -666,6 +564,9 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
         }
       }
       double e0 = q[0], e1 = q[1];
+#ifdef OVP_DEBUG
+      if (c0 == 0 && dbgp && tid == 0) dbgp[51] = clock64() + (long long)(e0 + e1 == 12345.678);
+#endif
       double *lb = bcast + warp * 96; // [0,32) and [32,64): l(., j) by column parity (16 values + 16 zeros); [64,96): zeros
       lb[lane] = 0.0;
       lb[32 + lane] = 0.0;
@@ -674,6 +575,9 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
       double dcur = __shfl_sync(0xffffffffu, mydiag, 0);
       double ediag = __shfl_sync(0xffffffffu, mydiag, 1);
       double lprev = 0.0;
+#ifdef OVP_DEBUG
+      if (c0 == 0 && dbgp && tid == 0) dbgp[52] = clock64() + (long long)(dcur + ediag == 12345.678);
+#endif
       // loop-invariant addresses and predicates, pinned in registers
       unsigned thr_a = cf_saddr(thr + c0), piv_a = cf_saddr(pivinv + c0), lb_a = cf_saddr(lb);
       // opaque to the compiler: otherwise it REMATERIALISES the address of a static shared array inside the loop as
@@ -691,13 +595,32 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
       // every chain warp has read the unfactored diagonal block (and its own rows) from the tile: only now may warp 0 start to
       // overwrite it.  Named barrier over the vw + 1 chain warps - without it the read races with warp 0's first store whenever a
       // warp is delayed by a few hundred cycles (seen only with several cooperative launches sharing the GPU).
+#ifdef OVP_DEBUG
+      if (dbgp && lane == 0 && c0 <= 16)
+        dbgp[40 + 4 * (c0 >> 4) + warp] = clock64(); // arrival of each chain warp at the named barrier (panels 0 and 1)
+#endif
       asm volatile("bar.sync 1, %0;" ::"r"((vw + 1) * 32) : "memory");
       PT(30 + (c0 >> 4))
       if (nbp == 16) {
         const CfChain cc{thr_a, piv_a, lb_a, row_a, row_s, lst_a, lane_r, p_lo16, p_row, p_diag, p_w0};
-#define CF_ST(J) cf_chain_step<J>(q, dcur, ediag, mydiag, lprev, bad, cc);
-        CF_ST(0) CF_ST(1) CF_ST(2) CF_ST(3) CF_ST(4) CF_ST(5) CF_ST(6) CF_ST(7)
-        CF_ST(8) CF_ST(9) CF_ST(10) CF_ST(11) CF_ST(12) CF_ST(13) CF_ST(14) CF_ST(15)
+#define CF_ST(J) cf_chain_step<J>(q, jb, dcur, ediag, mydiag, lprev, bad, cc);
+#if CF_CHAIN_COLS == 16
+        {
+          const int jb = 0;
+          CF_ST(0) CF_ST(1) CF_ST(2) CF_ST(3) CF_ST(4) CF_ST(5) CF_ST(6) CF_ST(7)
+          CF_ST(8) CF_ST(9) CF_ST(10) CF_ST(11) CF_ST(12) CF_ST(13) CF_ST(14) CF_ST(15)
+        }
+#else
+#pragma unroll 1
+        for (int jb = 0; jb < 16; jb += 8) {
+          CF_ST(0) CF_ST(1) CF_ST(2) CF_ST(3) CF_ST(4) CF_ST(5) CF_ST(6) CF_ST(7)
+#pragma unroll
+          for (int k = 0; k < 8; k++) { // the second half panel continues with static indices 0..7
+            q[k] = q[k + 8];
+            q[k + 8] = 0.0;
+          }
+        }
+#endif
 #undef CF_ST
       } else {
         // partial panel (the last one of a system whose size is not a multiple of 16): the rolled form of the same step; the register
@@ -739,15 +662,8 @@ __device__ void cf_potrf64(double *a, double *x, int bs, const double *thr, bool
       }
       if (strict && bad && tid == 0)
         atomicExch(info, 1);
-      if (ov.on && tid == 0)
-        ov.sync[0] = pnl + 1; // this panel's chain is finished (the I/O warp stops polling)
       PT(1 + 3 * (c0 >> 4))
-    } else if (ov.on && st0 == 2 && pnl > ov.done) {
-      // idle warps vw+1 .. 6: apply the finished panels [done, pnl) to the next step's tiles
-      cf_apply_panels(ov, a, x, ov.done, pnl, warp_u - (vw + 1), 6 - vw, 3, lane);
     }
-    if (ov.on && st0 == 2)
-      ov.done = pnl;
     __syncthreads();
     PT(2 + 3 * (c0 >> 4))
     if (CF_B - c0 - 16 > 0 && nbp == 16) // (a partial block is the last pivot block: everything to its right is never read)
@@ -801,23 +717,29 @@ __device__ __noinline__ void cf_bsolve64(double *U, const double *Lkk, const dou
   }
 }
 
-__global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
+static_assert(sizeof(CholFusedArgs) <= 32 * sizeof(double), "the shared-memory copy of the arguments has 32 doubles");
+__global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p_in) {
   extern __shared__ __align__(128) double sm_dyn[];
   double *const sm = pin_shared(sm_dyn); // (gemm.cuh) keeps the base in a register: no S2R SR_CgaCtaId in front of the loops below
   // every shared array is carved from the one dynamic block: addresses of static __shared__ variables are re-derived from
   // SR_CgaCtaId (S2R, ~100+ cycles) wherever the compiler rematerialises them - inside the pivot loop that tripled its latency.
-  // Layout (doubles): [0,16) two mbarriers (+ padding to 128 B) | tile buffers | role-specific (see the three branches)
-  double *tb = sm + 16; // tile buffers: 128-byte aligned bulk-copy targets
+  // Layout (doubles): [0,16) two mbarriers (+ padding to 128 B) | [16,48) the kernel arguments | tile buffers | role-specific
+  //
+  // The ARGUMENTS are read from this shared-memory copy, not from the constant bank: the compiler re-loads a kernel parameter with
+  // LDC / LDCU wherever it needs one (31 loads spread over the spine's step), each a potential constant-cache miss behind the
+  // instruction cache the step's code already overflows; as LDS they cannot miss.  Measured: 1.94 -> 1.90 ms of chol_fused per step.
+  double *tb = sm + 48; // tile buffers: 128-byte aligned bulk-copy targets
   const unsigned mb0 = cf_saddr(sm);
-  volatile int *csync = reinterpret_cast<volatile int *>(sm + 2); // spine: [0] finished pivot chains of the step, [1] state of the lookahead tiles
   __shared__ int s_epoch;
   const int tid = threadIdx.x;
   if (tid == 0) {
-    s_epoch = *(volatile int *)p.ctrl + 1;
+    *reinterpret_cast<CholFusedArgs *>(sm + 16) = p_in;
+    s_epoch = *(volatile int *)p_in.ctrl + 1;
     cf_mbar_init(mb0, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  const CholFusedArgs &p = *reinterpret_cast<const CholFusedArgs *>(sm + 16);
   const int e = s_epoch;
   const int Tp = p.Tp, T = p.T;
   int *fdiag = p.flags, *fpan = p.flags + Tp; // D(k): L(k,k) and Linv(k) published; P(i,k): L(i,k) published
@@ -831,8 +753,6 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
     double *a = tb, *b3 = tb + CF_SLOT, *b4 = tb + 2 * CF_SLOT;
     double *xc = tb + 3 * CF_SLOT, *sscr = xc + CF_XSZ, *thr = sscr + 16 * CF_LD, *pivinv = thr + CF_B, *bcast = pivinv + CF_B; // bcast: 8 x 96
     unsigned par_pf = 0;
-    CfDeferred dfr; // (unused since the tile CTAs copy the factor tiles into A; kept for the A/B switch of the old scheme)
-    dfr.n = 0;
     CF_TS(0)
     cf_load_tile(a, p.A, p.ld, min(CF_B, p.n), min(CF_B, p.n), true);
     __syncthreads();
@@ -847,33 +767,15 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
         CF_TS(1 + 2 * k)
       long long *dbgp = (p.dbg && k == 1) ? p.dbg + (size_t)gridDim.x * 16 : nullptr;
       PT(0)
-      CfOverlap ov; // lookahead: the idle warps apply finished panels to the next step's tiles while the pivot chains run
-      ov.on = has_panel && bs == CF_B && !p.no_lookahead;
-      ov.diag = next_diag;
-      ov.U = b3;
-      ov.D = b4;
-      ov.scr = sscr;
-      ov.flagU = fus + k + 1;
-      ov.flagD = fud + k + 1;
-      ov.slotU = slotUs + (size_t)(k + 1) * CF_SLOT;
-      ov.slotD = slotUd + (size_t)(k + 1) * CF_SLOT;
-      ov.mbar = mb0;
-      ov.parity = par_pf;
-      ov.sync = csync;
-      ov.done = 0;
-      if (tid == 0) {
-        csync[0] = 0;
-        csync[1] = 0;
-      }
       CfPrefetch pf;
-      pf.flag0 = (has_panel && !ov.on) ? fus + k + 1 : nullptr;
-      pf.flag1 = (next_diag && !ov.on) ? fud + k + 1 : nullptr;
+      pf.flag0 = has_panel ? fus + k + 1 : nullptr;
+      pf.flag1 = next_diag ? fud + k + 1 : nullptr;
       pf.s0 = b3;
       pf.s1 = b4;
-      pf.g0 = ov.slotU;
-      pf.g1 = ov.slotD;
+      pf.g0 = slotUs + (size_t)(k + 1) * CF_SLOT;
+      pf.g1 = slotUd + (size_t)(k + 1) * CF_SLOT;
       pf.mbar = mb0;
-      cf_potrf64(a, xc, bs, thr, p.tol == 0.0, pivinv, p.info, bcast, pf, dfr, ov, e, dbgp);
+      cf_potrf64(a, xc, bs, thr, p.tol == 0.0, pivinv, p.info, bcast, pf, e, dbgp);
       if (k < 3)
         CF_TS(2 + 2 * k)
       PT(13)
@@ -899,27 +801,10 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
       if (has_panel) {
         if (next_diag && tid < CF_B)
           thr[tid] = fmax(p.tol * __ldcg(p.diag0 + CF_B * (k + 1) + tid), 0.0);
-        if (ov.on) {
-          if (tid == IO && csync[1] == 0) { // the tiles' flags had not shown up while the chains ran: now wait for them
-            cf_acquire(ov.flagU, e);
-            if (next_diag)
-              cf_acquire(ov.flagD, e);
-            cf_fence_async_all();
-            cf_mbar_expect_tx(mb0, next_diag ? 2 * CF_SLOT_BYTES : CF_SLOT_BYTES);
-            cf_bulk_g2s(cf_saddr(b3), ov.slotU, CF_SLOT_BYTES, mb0);
-            if (next_diag)
-              cf_bulk_g2s(cf_saddr(b4), ov.slotD, CF_SLOT_BYTES, mb0);
-          }
-          cf_mbar_wait(mb0, par_pf);
-          par_pf ^= 1;
-          PT(24)
-          cf_apply_panels(ov, a, xc, ov.done, 4, tid >> 5, 8, 0, tid & 31); // what the lookahead has not reached (panel 3 at least)
-        } else {
-          cf_mbar_wait(mb0, par_pf); // the two tiles of the next step (bulk loads started during the last pivot chain)
-          par_pf ^= 1;
-          PT(24)
-          cf_bsolve64(b3, a, xc, sscr); // L(k+1,k) = U(k+1,k) L(k,k)^-T
-        }
+        cf_mbar_wait(mb0, par_pf); // the two tiles of the next step (bulk loads started during the last pivot chain)
+        par_pf ^= 1;
+        PT(24)
+        cf_bsolve64(b3, a, xc, sscr); // L(k+1,k) = U(k+1,k) L(k,k)^-T
         cf_fence_async_smem();
         __syncthreads();
         PT(25)
@@ -929,10 +814,8 @@ __global__ void __launch_bounds__(256, 1) chol_fused_kernel(CholFusedArgs p) {
         }
         PT(26)
         if (next_diag) {
-          if (!ov.on) {
-            cf_mma_64<2>(b4, b3, b3, -1.0, true, false); // lower triangle of the next diagonal tile
-            __syncthreads();
-          }
+          cf_mma_64<2>(b4, b3, b3, -1.0, true, false); // lower triangle of the next diagonal tile
+          __syncthreads();
           double *tmp = a;
           a = b4;
           b4 = tmp;
@@ -1223,18 +1106,11 @@ int chol_fused(Ctx *c, double *A, int ld, int n, int npiv, double tol, const dou
   p.w = w;
   p.dbg = dbg;
   p.prefactored = 0;
-  {
-    // the in-spine lookahead is OFF by default: measured on B200 the two tiles it needs arrive ~22 K cycles after this CTA's previous
-    // panel is published (their producers' acquire -> bulk load -> 64^3 update -> bulk store -> release round trip), i.e. after the last
-    // pivot chain, so the helpers never get to run and the unit-wise tail is slower than cf_bsolve64 + cf_mma_64 (170 vs 143 us at n = 474)
-    static const char *nl = getenv("OVP_CHOL_LOOKAHEAD");
-    p.no_lookahead = (nl && nl[0] == '1') ? 0 : 1;
-  }
   const int vrows = M ? (mrows + (z ? 1 : 0)) : 0;
   p.nrb = (vrows + CF_RB - 1) / CF_RB;
   p.mstride = p.Tp * CF_B + 4;
-  size_t smem_tile = ((size_t)16 + 3 * CF_SLOT + CF_XSZ + 16 * CF_LD + 2 * CF_B + 8 * 96) * sizeof(double);
-  size_t smem_rows = ((size_t)16 + CF_SLOT + CF_XSZ + (size_t)CF_RB * p.mstride + (size_t)CF_RB * CF_LD + 320) * sizeof(double);
+  size_t smem_tile = ((size_t)48 + 3 * CF_SLOT + CF_XSZ + 16 * CF_LD + 2 * CF_B + 8 * 96) * sizeof(double);
+  size_t smem_rows = ((size_t)48 + CF_SLOT + CF_XSZ + (size_t)CF_RB * p.mstride + (size_t)CF_RB * CF_LD + 320) * sizeof(double);
   size_t smem = std::max(smem_tile, p.nrb ? smem_rows : 0);
   if (smem > 220 * 1024)
     return fail(c, OVP_ERR_CAPACITY, "chol_fused: %d columns need %zu B of shared memory", npiv, smem);

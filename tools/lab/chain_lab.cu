@@ -226,20 +226,31 @@ template <int NB2> __global__ void __launch_bounds__(256, 1) labU(double *out, l
       tot += t1 - t0;
       if (lane == 0 && rep == reps - 1)
         cyc[warp] = tot / reps;
+      {
+        // filler: NB2 further instructions of straight-line code between two runs of the chain (what the trailing update, barriers and
+        // the next panel's set-up are in the kernel) - does the chain still sit in the instruction cache next time round?
+        unsigned fx = tid, fy = (unsigned)bad;
+#pragma unroll
+        for (int i = 0; i < NB2 / 2; i++) {
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(fx) : "r"(fy));
+          asm volatile("xor.b32 %0, %0, %1;" : "+r"(fy) : "r"(fx));
+        }
+        bad += (int)(fx + fy == 12345u);
+      }
       out[tid] = q[15] + dcur + bad + q[5];
     }
     __syncthreads();
   }
 }
-void runU(const char *name) {
+template <int NB2> void runU(const char *name) {
   double *out;
   long long *cyc;
   cudaMalloc(&out, 256 * 8);
   cudaMalloc(&cyc, 8 * 8);
   size_t smem = (CF_B * CF_LD + 1280 + 2 * CF_B + 8 * 96) * 8;
-  cudaFuncSetAttribute(labU<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(labU<NB2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   for (int nw : {1, 4, 5}) {
-    labU<0><<<1, 256, smem>>>(out, cyc, nw, 20);
+    labU<NB2><<<1, 256, smem>>>(out, cyc, nw, 20);
     cudaDeviceSynchronize();
     long long h[8];
     cudaMemcpy(h, cyc, 64, cudaMemcpyDeviceToHost);
@@ -265,7 +276,13 @@ template <int FL> void run(const char *name) {
 }
 int main() {
   run<F_DEFER | F_STORE | F_SHFL | F_THR>("as in cholfused.cu");
-  runU("unrolled, exact-width update, fast rsqrt");
+  runU<0>("unrolled, exact-width update, fast rsqrt");
+  runU<128>("  + 128 filler instructions between runs");
+  runU<256>("  + 256 filler instructions between runs");
+  runU<512>("  + 512 filler instructions between runs");
+  runU<1024>("  + 1024 filler instructions between runs");
+  runU<2048>("  + 2048 filler instructions between runs");
+  runU<4096>("  + 4096 filler instructions between runs");
   run<F_DEFER | F_STORE | F_SHFL | F_THR | F_FASTRSQ>("branch-free rsqrt");
   run<F_STORE | F_SHFL | F_THR>("no deferred update");
   run<F_DEFER | F_SHFL | F_THR>("no stores");

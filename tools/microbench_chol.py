@@ -33,7 +33,7 @@ for (nn, mm) in ((n, 0), (n, mrows), (128, 0), (64, 0)):
             print("  step %d: spine potrf %.1f..%.1f | tile(%d,%d) Linv loaded %.1f solved %.1f published %.1f | tile(%d,%d) updated %.1f published %.1f | tile(%d,%d) updated %.1f published %.1f"
                   % (k, sp[1 + 2 * k] if k < 3 else float("nan"), sp[2 + 2 * k] if k < 3 else float("nan"), k + 1, k - 1, pan[5], pan[6], pan[7], k + 1, k, us[3], us[4], k + 1, k + 1, ud[3], ud[4]))
         ph = out[3 + 16 * ncta:3 + 16 * ncta + 29]
-        ls = out[3 + 16 * ncta + 30:3 + 16 * ncta + 34]
+        ls = out[3 + 16 * ncta + 30:3 + 16 * ncta + 54]
         names = ["potrf start"] + [x for b in range(4) for x in ("chain%d" % b, "sync%d" % b, "trail%d+sync" % b)] + ["trinv zero", "trinv base16", "merge16 T", "merge16 X", "merge32 T", "merge32 X",
                  "store Linv", "signal D", "store L", "(unused)", "cp.async wait", "sync", "panel mma", "store panel", "signal P", "update mma"]
         prev = 0.0
@@ -43,6 +43,6 @@ for (nn, mm) in ((n, 0), (n, mrows), (128, 0), (64, 0)):
                 line.append("%s %d" % (nm, v - prev))
                 prev = v
         print("  spine k=1 phase cycles: " + " | ".join(line))
-        print("  pivot loop of panel p starts (cycles since potrf start): " + " ".join("%d" % v for v in ls) + "   (chain p ends at " + " ".join("%d" % ph[1 + 3 * b] for b in range(4)) + ")")
+        print("  pivot loop of panel p starts (cycles since potrf start): " + " ".join("%d" % v for v in ls[:4]) + "  potrf entry %d, after its first barrier %d; chain warps reach the named barrier of panel 0 at %s, of panel 1 at %s" % (ls[4], ls[5], " ".join("%d" % v for v in ls[10:14]), " ".join("%d" % v for v in ls[14:18])) + "; panel 0 set-up: branch entry %d, rows loaded %d, diagonal shuffled %d" % (ls[20], ls[21], ls[22]) + "   (chain p ends at " + " ".join("%d" % ph[1 + 3 * b] for b in range(4)) + ")")
         if mm:
             print("  row-block CTAs end: min %.1f max %.1f" % (ts[T * (T + 1) // 2:, 15].min(), ts[T * (T + 1) // 2:, 15].max()))

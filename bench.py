@@ -41,7 +41,7 @@ class ClockSampler(object):
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -49,19 +49,23 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Rows that arrived inside [t0, t1] (the timed regions).  nvidia-smi is started BEFORE the warm-up, so it is already
+        streaming when the timed region begins (started at the region's edge, its first row used to arrive after a 60 ms region
+        had ended: zero samples)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.03)]
+        for r in rows:
             p = [x.strip() for x in r.split(",")]
             if len(p) < 7:
                 continue
@@ -253,6 +257,8 @@ def main():
         with torch.cuda.stream(stream):
             flush_buf.fill_(1.0)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     # ---- warm-up through the full C-ABI path ----
     for _ in range(args.warmup):
         ctx.restore()
@@ -265,10 +271,9 @@ def main():
     ctx.restore()
     ctx.msckf_launch()
     ctx.synchronize()
-    sampler = ClockSampler(local)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    t_region0 = time.time()
     l0 = ctx.launch_count()
     for k in range(args.steps):
         flush_l2()
@@ -278,7 +283,6 @@ def main():
         ev[k][1].record(stream)
     barrier()
     launches = ctx.launch_count() - l0
-    clocks = sampler.stop()
     ctx.msckf_finish()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     per_rank_ms = gather_over_ranks(float(np.mean(step_ms)))
@@ -298,6 +302,8 @@ def main():
         ctx.var_get(ctx.handle_imu())  # device->host read of the step's result (all variable values)
         e2e_t.append(time.perf_counter() - t0)
     barrier()
+    clocks = sampler.stop(t_region0, time.time())  # nvidia-smi rows that arrived during the two timed regions (value + e2e)
+    clocks["window"] = "device-timed steps + e2e steps"
     h1, d1 = ctx.transfer_bytes()
     n_var_bytes = 0
     e2e_ms = max_over_ranks(1e3 * float(np.mean(e2e_t)))
@@ -335,7 +341,7 @@ def main():
     dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
     dname, dv = dom
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    tpath = os.path.join(ROOT, "profiles", "traffic_r2.json")
     if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get(dname)

@@ -349,8 +349,8 @@ int ovp_create(const ovp_state_options *opt, int device, int max_state, int max_
   OVP_CUDA(cudaMemset(c->dM, 0, (size_t)c->Nmax * c->Rcap * sizeof(double)));
   OVP_CUDA(cudaMemset(c->dY, 0, (size_t)c->Nmax * c->Rcap * sizeof(double)));
   OVP_CUDA(cudaMemset(c->dHT, 0, (size_t)c->Rcap * c->Rcap * sizeof(double)));
-  OVP_CUDA(cudaMalloc(&c->dvec, ((size_t)8 * c->Rcap + 2 * c->Nmax) * sizeof(double)));
-  OVP_CUDA(cudaMemset(c->dvec, 0, ((size_t)8 * c->Rcap + 2 * c->Nmax) * sizeof(double)));
+  OVP_CUDA(cudaMalloc(&c->dvec, ((size_t)8 * c->Rcap + (2 + OVP_DX_SPLIT) * c->Nmax) * sizeof(double)));
+  OVP_CUDA(cudaMemset(c->dvec, 0, ((size_t)8 * c->Rcap + (2 + OVP_DX_SPLIT) * c->Nmax) * sizeof(double)));
   OVP_CUDA(cudaMalloc(&c->dcols, (size_t)8 * c->Rcap * sizeof(int)));
   OVP_CUDA(cudaMalloc(&c->dflags, 256 * sizeof(int)));
   OVP_CUDA(cudaMemset(c->dflags, 0, 256 * sizeof(int)));

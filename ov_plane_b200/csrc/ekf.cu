@@ -40,12 +40,47 @@ __device__ __forceinline__ void quat_left_update(double *q, const double *dth) {
   q[3] = r3 / n2;
 }
 
-// Tail of EKFUpdate in one launch, one warp per variable: dx rows of the variable = Y[id : id + size, :] w (lanes over the
-// compressed rows, fixed-order shuffle tree), ov_type::update on the device (StateHelper.cpp:190-193), and the negative-diagonal
-// check of the variable's covariance rows (:176-187).  Skipped when the gate flag says the update was rejected.
+// dx = Y w, stage 1: OVP_DX_SPLIT partial sums per state row.  Y is column-major (row i of column k at Y[k * ldy + i]): 64 consecutive rows per
+// CTA are one coalesced 512-byte segment per column; the CTA's 4 thread groups take every 4th column of the chunk, so a thread has <= 16
+// independent loads (all in flight at once) and a fixed summation order.  (The one-launch version - a warp per variable striding over the
+// columns - had 2 loads in flight per lane and took 22 us per update, 6 % of the step.)
+__global__ void __launch_bounds__(256) dx_partial_kernel(const double *Y, int ldy, int N, const double *w, int rr, double *part, int ldpart,
+                                                         const int *flag) {
+  if (flag && *flag == 0)
+    return;
+  __shared__ double red[4][64];
+  const int r = threadIdx.x & 63, kl = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + r;
+  const int chunk = (rr + OVP_DX_SPLIT - 1) / OVP_DX_SPLIT;
+  const int k0 = blockIdx.y * chunk, k1 = min(rr, k0 + chunk);
+  double s = 0.0;
+  if (i < N) {
+    for (int kb = k0 + kl; kb < k1; kb += 64) { // 16 columns of this thread group per round
+      double v[16], wk[16];
+#pragma unroll
+      for (int u = 0; u < 16; u++) {
+        const int k = kb + 4 * u;
+        const bool ok = k < k1;
+        v[u] = ok ? Y[(size_t)k * ldy + i] : 0.0;
+        wk[u] = ok ? w[k] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; u++)
+        s = fma(v[u], wk[u], s);
+    }
+  }
+  red[kl][r] = s;
+  __syncthreads();
+  if (kl == 0 && i < N)
+    part[(size_t)blockIdx.y * ldpart + i] = ((red[0][r] + red[1][r]) + red[2][r]) + red[3][r];
+}
+
+// Tail of EKFUpdate, stage 2, one warp per variable: dx rows of the variable = sum of the partial sums (lane = row, fixed order),
+// ov_type::update on the device (StateHelper.cpp:190-193), and optionally the negative-diagonal check of the variable's covariance rows
+// (:176-187).  Skipped when the gate flag says the update was rejected.
 __global__ void __launch_bounds__(128) finish_update_kernel(int nh, const int *var_id, const int *var_size, const int *var_kind, double *val,
-                                                            const double *Y, int ldy, const double *w, int rr, const double *P, int ldP,
-                                                            int *neg_flag, const int *flag) {
+                                                            const double *part, int ldpart, const double *P, int ldP, int *neg_flag,
+                                                            const int *flag) {
   const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (h >= nh)
     return;
@@ -55,31 +90,20 @@ __global__ void __launch_bounds__(128) finish_update_kernel(int nh, const int *v
   if (id < 0)
     return;
   const int s = var_size[h];
-  // lanes stride over the compressed rows k (all loads of a lane are independent: 15 accumulators, one per row of the variable; the s
-  // rows of one column of Y are contiguous), then a fixed-order shuffle tree per row
+  double mine = 0.0;
+  if (lane < s) {
+    double pv[OVP_DX_SPLIT];
+#pragma unroll
+    for (int q = 0; q < OVP_DX_SPLIT; q++)
+      pv[q] = part[(size_t)q * ldpart + id + lane];
+#pragma unroll
+    for (int q = 0; q < OVP_DX_SPLIT; q++)
+      mine += pv[q];
+  }
   double acc[15];
 #pragma unroll
   for (int j = 0; j < 15; j++)
-    acc[j] = 0.0;
-  {
-    const double *y = Y + id;
-#pragma unroll 2
-    for (int k = lane; k < rr; k += 32) {
-      const double wk = w[k];
-      const double *yk = y + (size_t)k * ldy;
-#pragma unroll
-      for (int j = 0; j < 15; j++)
-        if (j < s)
-          acc[j] = fma(yk[j], wk, acc[j]);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 15; j++)
-    if (j < s) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o); // dx of row j on every lane
-    }
+    acc[j] = __shfl_sync(0xffffffffu, mine, j); // dx of row j on every lane
   if (P && lane < s && P[(size_t)(id + lane) * ldP + id + lane] < 0.0)
     atomicExch(neg_flag, 1);
   if (lane != 0)
@@ -298,9 +322,11 @@ int ekf_update_core(Ctx *c, const int *d_cols, int nc, MatView HT, int rr, const
   }
   // 7. dx = Y w and the manifold update of every variable: one launch
   int nh = (int)c->vars.size();
-  finish_update_kernel<<<(nh * 32 + 127) / 128, 128, 0, c->stream>>>(nh, c->d_var_id, c->d_var_size, c->d_var_kind, c->d_val, c->dY, c->Nmax, d_w, rr,
-                                                                      nullptr, c->ldP, c->dflags, flag);
-  c->launches++;
+  double *d_part = c->dvec + (size_t)8 * c->Rcap + 2 * (size_t)c->Nmax;
+  dx_partial_kernel<<<dim3((N + 63) / 64, OVP_DX_SPLIT), 256, 0, c->stream>>>(c->dY, c->Nmax, N, d_w, rr, d_part, c->Nmax, flag);
+  finish_update_kernel<<<(nh * 32 + 127) / 128, 128, 0, c->stream>>>(nh, c->d_var_id, c->d_var_size, c->d_var_kind, c->d_val, d_part, c->Nmax, nullptr,
+                                                                      c->ldP, c->dflags, flag);
+  c->launches += 2;
   c->host_values_stale = true;
   if (!defer_join)
     return join_side_stream(c);

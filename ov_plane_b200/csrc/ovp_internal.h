@@ -75,7 +75,7 @@ struct Ctx {
   DenseWs wsG, wsS;            // compress factor / innovation factor
   double *dM = nullptr, *dY = nullptr; // Nmax x Rcap
   double *dHT = nullptr;       // Rcap x Rcap (H^T operand for generic ekf_update)
-  double *dvec = nullptr;      // misc vectors: z, w, dx ... (8 * Rcap)
+  double *dvec = nullptr;      // misc vectors: z, w, dx ... (8 * Rcap), then 2 * Nmax, then the OVP_DX_SPLIT x Nmax partial sums of dx = Y w
   int *dcols = nullptr;        // gather index arrays (8 * Rcap ints)
   int *dflags = nullptr;       // device flags / status words (256 ints)
   double *dscal = nullptr;     // device scalars (256 doubles)
@@ -189,6 +189,7 @@ double chi2_q95(Ctx *c, int dof);
 // ---- features.cu -------------------------------------------------------------------------------------------------
 // extra: forced_cols != nullptr => point features only, x columns fixed to this list of state indices (multi-GPU shard
 // half); d_export != nullptr => write the (n+1)x(n+1) factor block [R^T ; z^T] there and skip the EKF update.
+#define OVP_DX_SPLIT 8 // dx = Y w is summed in this many fixed chunks of the compressed rows (dx_partial_kernel, ekf.cu)
 struct MsckfExtra {
   const std::vector<int> *forced_cols = nullptr;
   double *d_export = nullptr;

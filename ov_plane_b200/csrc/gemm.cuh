@@ -133,6 +133,9 @@ __device__ __forceinline__ void store_tile_smem(const double (&r)[TILE / 8], dou
   }
 }
 
+// (Round 2, measured and not kept: a 4-stage cp.async operand pipeline instead of the register prefetch of the next k-step - 0.72 vs 0.71 ms
+// per step for the 27 products.  The k-step is bound by the FP64 pipe, not by the loads: 16 DMMAs per warp x ~17 cycles of issue each per
+// sub-partition; 240 tiles of 32 x 32 on 148 SMs are 2 rounds of 30 k-steps = 17 K cycles against 13 K at perfect balance.)
 // TILE = 64: 4 warps x (32x32) ; TILE = 32: 4 warps x (16x16) — the small tile spreads mid-size problems over all 148 SMs
 template <int TILE, bool GA, bool GB> __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmBatch batch) {
   if (batch.flag && *batch.flag == 0)

@@ -381,6 +381,13 @@ class VioLoop(object):
         rec["nees_pos"] = float(ep @ np.linalg.solve(P6[3:6, 3:6], ep))
         rec["imu"] = v.copy()
         rec["N"] = be.cov_rows()
+        # what sim_save_total_state_to_file writes (ROSVisualizerHelper.cpp:152-300): estimate, 1-sigma of the marginals, simulated truth
+        calib, _ = be.var_get(be.handle_calib())
+        intr, _ = be.var_get(be.handle_intrinsics())
+        Pm = be.get_marginal_covariance([be.handle_imu(), be.handle_intrinsics(), be.handle_calib()])
+        rec["calib"], rec["intr"] = np.asarray(calib[:7]).copy(), np.asarray(intr[:8]).copy()
+        rec["std"] = np.sqrt(np.maximum(np.diag(Pm), 0.0))  # [imu 15 | intrinsics 8 | extrinsics 6]
+        rec["gt"] = np.concatenate([jpl.rot_2_quat(R), p, vel, np.zeros(3), np.zeros(3)])
         self.frames.append(rec)
 
 
@@ -414,8 +421,37 @@ TIMING_HEADER = "# timestamp (sec),tracking,propagation,plane init,msckf update,
 
 
 def timing_csv(loop):
+    """record_timing_filepath (VioManager.cpp:110-118 header, :911-928 rows: timestamp with 15 decimals, stage times with 5)"""
     lines = [TIMING_HEADER]
     for r in loop.frames:
         tot = r["propagation"] + r["plane_init"] + r["msckf"] + r["marg"]
-        lines.append("%.9f,%.6f,%.6f,%.6f,%.6f,%.6f,%.6f" % (r["t"], 0.0, r["propagation"], r["plane_init"], r["msckf"], r["marg"], tot))
+        lines.append("%.15f,%.5f,%.5f,%.5f,%.5f,%.5f,%.5f" % (r["t"], 0.0, r["propagation"], r["plane_init"], r["msckf"], r["marg"], tot))
     return "\n".join(lines) + "\n"
+
+
+def _fix(v, prec):
+    return ("%." + str(prec) + "f") % v
+
+
+def state_files(loop):
+    """The three text files of sim_save_total_state_to_file (ROSVisualizerHelper.cpp:152-300), one line per frame, fields separated and
+    terminated by a blank like the reference's stream writes:
+      estimate: t(5 decimals) q_GtoI(4) p v bg ba (6 decimals) t_off(7) num_cameras(0) [intrinsics(8) q_ItoC(4) p_IinC(3)] (6)
+      1-sigma : t(5) std of [theta p v bg ba](15) std t_off num_cameras [std intrinsics(8) std extrinsics(6)]   (zeros when not calibrated)
+      truth   : same layout as the estimate, from the simulator (biases are zero in this simulator, time offset 0)
+    Returns (est, std, gt) strings that ov_eval's error_simulation / timing tools read unchanged."""
+    sim = loop.sim
+    est, std, gt = [], [], []
+    for r in loop.frames:
+        t = _fix(r["t"], 5)
+        est.append(" ".join([t] + [_fix(x, 6) for x in r["imu"][:16]] + [_fix(0.0, 7), "1"] + [_fix(x, 6) for x in r["intr"]] +
+                            [_fix(x, 6) for x in r["calib"]]) + " ")
+        sd = r["std"]
+        n_intr = 8 if len(sd) >= 15 + 8 else 0
+        n_ext = 6 if len(sd) >= 15 + n_intr + 6 else 0
+        intr_sd = list(sd[15:15 + n_intr]) if n_intr else [0.0] * 8
+        ext_sd = list(sd[15 + n_intr:15 + n_intr + n_ext]) if n_ext else [0.0] * 6
+        std.append(" ".join([t] + [_fix(x, 6) for x in sd[:15]] + [_fix(0.0, 6), "1"] + [_fix(x, 6) for x in intr_sd] + [_fix(x, 6) for x in ext_sd]) + " ")
+        true_calib = np.concatenate([jpl.rot_2_quat(sim.R_ItoC), sim.p_IinC])
+        gt.append(" ".join([t] + [_fix(x, 6) for x in r["gt"]] + [_fix(0.0, 7), "1"] + [_fix(x, 6) for x in sim.cam] + [_fix(x, 6) for x in true_calib]) + " ")
+    return "\n".join(est) + "\n", "\n".join(std) + "\n", "\n".join(gt) + "\n"

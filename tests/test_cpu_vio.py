@@ -44,3 +44,17 @@ def test_filter_consistency_on_the_oracle():
     csv = vio_sim.timing_csv(loop)
     assert csv.splitlines()[0].startswith("# timestamp (sec),tracking,propagation,plane init,msckf update")
     assert len(csv.splitlines()) == 81
+    # on-disk formats: the timing CSV and the three state files of sim_save_total_state_to_file, as ov_eval reads them
+    row = csv.splitlines()[1].split(",")
+    assert len(row) == 7 and len(row[0].split(".")[1]) == 15 and all(len(x.split(".")[1]) == 5 for x in row[1:])
+    est, std, gt = vio_sim.state_files(loop)
+    for name, txt in (("est", est), ("std", std), ("gt", gt)):
+        ls = txt.splitlines()
+        assert len(ls) == 80, name
+        tok = ls[-1].split()
+        # t | 16 state values (15 sigmas) | time offset | number of cameras | 8 intrinsics | 7 extrinsics (6 sigmas)
+        assert len(tok) == (1 + 15 + 1 + 1 + 8 + 6 if name == "std" else 1 + 16 + 1 + 1 + 8 + 7), (name, len(tok))
+        assert len(tok[0].split(".")[1]) == 5 and len(tok[1].split(".")[1]) == 6 and tok[18 if name != "std" else 17] == "1"
+    e, g, sd = (np.array([[float(x) for x in l.split()] for l in t.splitlines()]) for t in (est, gt, std))
+    assert np.allclose(e[:, 0], g[:, 0]) and np.abs(e[-1, 5:8] - g[-1, 5:8]).max() < 0.3  # same clock, estimate near the truth
+    assert (sd[:, 1:16] > 0).all() and (sd[-1, 4:7] < 0.5).all()

@@ -254,6 +254,41 @@ typedef struct ovp_triangulation_options {
 int ovp_triangulate_features(ovp_ctx *ctx, int F, const int *meas_offset, const int *meas_clone, const float *uv_norm,
                              const ovp_triangulation_options *opt, double *p_FinG, int *status);
 
+/* ---- PlaneFitting (track_plane/PlaneFitting.cpp): plane hypothesis + refinement, the step right before the plane Jacobians ----------- */
+/* Call sites: UpdaterMSCKF.cpp:267-360, UpdaterPlane.cpp:230-267, UpdaterSLAM.cpp:171.  Both entry points take a BATCH of candidate planes
+ * (feat_offset: n_planes + 1 prefix offsets into the per-feature arrays) and run them concurrently. */
+typedef struct ovp_plane_fit_options {
+  int min_inlier_num;     /* StateOptions::plane_msckf_min_feat / plane_init_min_feat */
+  double max_cond_number; /* StateOptions::plane_msckf_max_cond / plane_init_max_cond */
+  int shuffle_kind;       /* draws of std::shuffle(std::mt19937(8888)) as produced by 0: libstdc++ of GCC 7..10 (the reference's Docker
+                             images), 1: libstdc++ of GCC >= 11 (std::uniform_int_distribution changed) */
+} ovp_plane_fit_options;
+/* PlaneFitting::plane_fitting (:83-195): RANSAC over 200 five-point sets (points >= 0.05 m apart, condition number of the 5 x 3 system
+ * <= max_cond_number), inliers within 0.05 m, winner = most inliers then smallest mean error, refit on its inliers.  status[p] = 1:
+ * abcd[4p..] is the plane (unit normal, offset) and inlier[f] flags the features the reference keeps in `feats`; 0: the reference returns
+ * false (too few points, a draw with fewer than five separated points, no valid set). */
+int ovp_plane_fitting(ovp_ctx *ctx, int n_planes, const int *feat_offset, const double *p_FinG, const ovp_plane_fit_options *opt, int *status,
+                      double *abcd, int *inlier);
+/* The n_shuffles successive permutations of 0..n-1 the reference's RANSAC loop draws (context-free host helper; needs no GPU). */
+int ovp_plane_shuffle(int n, int n_shuffles, int shuffle_kind, int *out);
+typedef struct ovp_plane_refine_options {
+  double sigma_px_norm;   /* sigma_pix / focal length (UpdaterMSCKF.cpp:271-272) */
+  double sigma_c;         /* StateOptions::sigma_constraint */
+  int max_num_iterations; /* 0 = the reference's 12 (PlaneFitting.cpp:396) */
+} ovp_plane_refine_options;
+/* PlaneFitting::optimize_plane (:197-514): joint refinement of the features of each plane (and of the plane unless fix_plane[p]) over
+ * reprojection + point-on-plane factors with the Cauchy loss, Ceres' dogleg trust-region iteration restated on the device (one launch for
+ * the whole batch).  Measurements as in ovp_triangulate_features (clone handles, undistorted normalised coordinates); a feature without
+ * measurements is a SLAM feature: constant, one constraint with 2 sigma_c.  Camera poses, the current IMU pose and the extrinsics come from
+ * the context.  status[p] = 1: success; p_FinG_out holds the refined positions of the inliers (others unchanged), cp_out the refined plane,
+ * inlier[f] the kept features.  status[p] = 0 with cp_out == cp_inG: the solver did not converge within the iteration limit (nothing
+ * changed); status[p] = 0 otherwise: too few inliers (positions / plane were already updated, like the reference's side effects).
+ * info (optional, 5 doubles per plane): converged, iterations, initial cost, final cost, termination reason (1 gradient, 2 parameter,
+ * 3 function tolerance, 4 no free parameter, -1 iteration limit, -2 invalid steps). */
+int ovp_optimize_plane(ovp_ctx *ctx, int n_planes, const int *feat_offset, const int *meas_offset, const int *meas_clone, const float *uv_norm,
+                       const double *p_FinG, const double *cp_inG, const int *fix_plane, const ovp_plane_refine_options *opt, double *p_FinG_out,
+                       double *cp_out, int *inlier, int *status, double *info);
+
 /* ---- UpdaterZeroVelocity (update/UpdaterZeroVelocity.cpp:68-318) ------------------------------------------------------- */
 typedef struct ovp_zupt_options {
   double gravity_mag;           /* VioManagerOptions.h:206 */

@@ -2,6 +2,7 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs can drive it through ctypes.
 // Nothing under ov_plane_b200/ or include/ may link or load this library.
 #include "oracle.hpp"
+#include "oracle_planefit.hpp"
 #include <string>
 
 using namespace orc;
@@ -723,6 +724,113 @@ int orc_triangulate_features(void *p, int F, const int *meas_offset, const int *
       for (int i = 0; i < 3; i++)
         p_FinG[3 * f + i] = status[f] ? pf(i, 0) : 0.0;
     }
+  });
+}
+// ---- PlaneFitting (track_plane/PlaneFitting.cpp) ----
+// shuffle_kind: 0 libstdc++ GCC 7..10 (the reference's documented toolchains), 1 libstdc++ GCC >= 11, 2 this build's std::shuffle
+int orc_plane_shuffle(int n, int n_shuffles, int shuffle_kind, int *out) { // n_shuffles successive shuffles of 0..n-1 from std::mt19937(8888)
+  std::mt19937 g(8888);
+  for (int k = 0; k < n_shuffles; k++) {
+    std::vector<int> v(n);
+    for (int i = 0; i < n; i++)
+      v[i] = i;
+    PlaneFitting::shuffle(v, g, (ShuffleKind)shuffle_kind);
+    for (int i = 0; i < n; i++)
+      out[(size_t)k * n + i] = v[i];
+  }
+  return 0;
+}
+int orc_fit_plane(int K, const double *pts, double cond_thresh, int cond_check, double *abcd, int *ok) {
+  std::vector<int> idx(K);
+  for (int i = 0; i < K; i++)
+    idx[i] = i;
+  *ok = PlaneFitting::fit_plane(pts, idx, abcd, cond_thresh, cond_check != 0) ? 1 : 0;
+  return 0;
+}
+int orc_plane_fitting(int F, const double *pts, int min_inlier_num, double max_cond, int shuffle_kind, double *abcd, int *inlier, int *ok) {
+  std::vector<int> inl;
+  *ok = PlaneFitting::plane_fitting(F, pts, abcd, min_inlier_num, max_cond, inl, (ShuffleKind)shuffle_kind) ? 1 : 0;
+  for (int f = 0; f < F; f++)
+    inlier[f] = inl[f];
+  return 0;
+}
+// optimize_plane against the clone / extrinsics / IMU values of the oracle state.  info[4] = {converged, iterations, initial cost, final cost}
+int orc_optimize_plane(void *p, int F, const int *meas_offset, const int *meas_clone, const float *uv_norm, const double *p_FinG,
+                       const double *cp_inG, double sigma_px_norm, double sigma_c, int fix_plane, int max_num_iterations, double *p_out,
+                       double *cp_out, int *inlier, int *ok, double *info) {
+  Ctx *c = (Ctx *)p;
+  return guarded(c, [&] {
+    PlaneFitting::Problem P;
+    P.F = F;
+    P.meas_offset.assign(meas_offset, meas_offset + F + 1);
+    VarP calib = c->state->_calib_IMUtoCAM;
+    for (int k = 0; k < meas_offset[F]; k++) {
+      VarP cl = c->state->by_handle.at(meas_clone[k]);
+      FeatureInitializer::ClonePose cp;
+      cp.R = calib->Rot() * cl->Rot(); // UpdaterMSCKF.cpp:131-132
+      cp.p = cl->pos() - cp.R.T() * calib->pos();
+      P.cam.push_back(cp);
+      P.uvn.push_back((double)uv_norm[2 * k]);
+      P.uvn.push_back((double)uv_norm[2 * k + 1]);
+    }
+    P.p0.assign(p_FinG, p_FinG + 3 * F);
+    for (int i = 0; i < 3; i++)
+      P.cp0[i] = cp_inG[i];
+    P.sigma_px_norm = sigma_px_norm;
+    P.sigma_c = sigma_c;
+    P.fix_plane = fix_plane != 0;
+    std::vector<double> pv;
+    std::vector<int> inl;
+    PlaneFitting::Summary S;
+    VarP imu = c->state->_imu;
+    *ok = PlaneFitting::optimize_plane(P, imu->Rot(), imu->pos(), calib->Rot(), calib->pos(), pv, cp_out, inl, &S, max_num_iterations > 0 ? max_num_iterations : 12) ? 1 : 0;
+    for (int i = 0; i < 3 * F; i++)
+      p_out[i] = pv[i];
+    for (int f = 0; f < F; f++)
+      inlier[f] = inl[f];
+    if (info) {
+      info[0] = S.converged ? 1.0 : 0.0;
+      info[1] = S.iterations;
+      info[2] = S.initial_cost;
+      info[3] = S.final_cost;
+      info[4] = S.reason;
+    }
+  });
+}
+// robustified cost 1/2 sum rho(s) of the refinement problem at given feature positions / plane (for the optimality checks of the tests)
+int orc_optimize_plane_cost(void *p, int F, const int *meas_offset, const int *meas_clone, const float *uv_norm, const double *p_FinG,
+                            const double *cp_inG, double sigma_px_norm, double sigma_c, int fix_plane, double *cost) {
+  Ctx *c = (Ctx *)p;
+  return guarded(c, [&] {
+    PlaneFitting::Problem P;
+    P.F = F;
+    P.meas_offset.assign(meas_offset, meas_offset + F + 1);
+    VarP calib = c->state->_calib_IMUtoCAM;
+    for (int k = 0; k < meas_offset[F]; k++) {
+      VarP cl = c->state->by_handle.at(meas_clone[k]);
+      FeatureInitializer::ClonePose cp;
+      cp.R = calib->Rot() * cl->Rot();
+      cp.p = cl->pos() - cp.R.T() * calib->pos();
+      P.cam.push_back(cp);
+      P.uvn.push_back((double)uv_norm[2 * k]);
+      P.uvn.push_back((double)uv_norm[2 * k + 1]);
+    }
+    P.p0.assign(p_FinG, p_FinG + 3 * F);
+    for (int i = 0; i < 3; i++)
+      P.cp0[i] = cp_inG[i];
+    P.sigma_px_norm = sigma_px_norm;
+    P.sigma_c = sigma_c;
+    P.fix_plane = fix_plane != 0;
+    PlaneFitting::layout(P);
+    std::vector<double> x(P.n, 0.0);
+    for (int f = 0; f < F; f++)
+      if (P.feat_col[f] >= 0)
+        for (int i = 0; i < 3; i++)
+          x[P.feat_col[f] + i] = p_FinG[3 * f + i];
+    if (P.cp_col >= 0)
+      for (int i = 0; i < 3; i++)
+        x[P.cp_col + i] = cp_inG[i];
+    *cost = PlaneFitting::evaluate(P, x, nullptr, nullptr);
   });
 }
 } // extern "C"

@@ -38,6 +38,14 @@ class UpdaterOptions(C.Structure):
     _fields_ = [("sigma_pix", C.c_double), ("chi2_multipler", C.c_double)]
 
 
+class PlaneFitOptions(C.Structure):
+    _fields_ = [("min_inlier_num", C.c_int), ("max_cond_number", C.c_double), ("shuffle_kind", C.c_int)]
+
+
+class PlaneRefineOptions(C.Structure):
+    _fields_ = [("sigma_px_norm", C.c_double), ("sigma_c", C.c_double), ("max_num_iterations", C.c_int)]
+
+
 DEBUG_LIB_PATH = os.path.join(_HERE, "lib", "libovp_debug.so")  # product sources + include/ovp_debug.h hooks (tools/, kernel unit tests)
 
 
@@ -432,6 +440,27 @@ class Context(object):
         pf, st = np.zeros((max(1, F), 3)), np.zeros(max(1, F), dtype=np.int32)
         self._ck(self.lib.ovp_triangulate_features(self.h, F, _p(mo), _p(mc), _p(uvn), None, _p(pf), _p(st)))
         return pf[:F], st[:F]
+
+    # ---- PlaneFitting (plane hypothesis + refinement, the step before the plane Jacobians) ----
+    def plane_fitting(self, feat_offset, p_FinG, min_inlier_num, max_cond, shuffle_kind=0):
+        fo, pf = _i32(feat_offset), _f64(p_FinG).reshape(-1, 3)
+        nP, Ft = len(fo) - 1, int(fo[-1])
+        opt = PlaneFitOptions(int(min_inlier_num), float(max_cond), int(shuffle_kind))
+        st, ab, inl = np.zeros(max(1, nP), dtype=np.int32), np.zeros((max(1, nP), 4)), np.zeros(max(1, Ft), dtype=np.int32)
+        self._ck(self.lib.ovp_plane_fitting(self.h, nP, _p(fo), _p(pf), C.byref(opt), _p(st), _p(ab), _p(inl)))
+        return st[:nP], ab[:nP], inl[:Ft]
+
+    def optimize_plane(self, feat_offset, meas_offset, meas_clone, uv_norm, p_FinG, cp_inG, fix_plane, sigma_px_norm, sigma_c, max_num_iterations=0):
+        fo, mo, mc = _i32(feat_offset), _i32(meas_offset), _i32(meas_clone)
+        uvn = np.ascontiguousarray(uv_norm, dtype=np.float32)
+        pf, cp, fx = _f64(p_FinG).reshape(-1, 3), _f64(cp_inG).reshape(-1, 3), _i32(fix_plane)
+        nP, Ft = len(fo) - 1, int(fo[-1])
+        opt = PlaneRefineOptions(float(sigma_px_norm), float(sigma_c), int(max_num_iterations))
+        po, co = np.zeros((max(1, Ft), 3)), np.zeros((max(1, nP), 3))
+        inl, st, info = np.zeros(max(1, Ft), dtype=np.int32), np.zeros(max(1, nP), dtype=np.int32), np.zeros((max(1, nP), 5))
+        self._ck(self.lib.ovp_optimize_plane(self.h, nP, _p(fo), _p(mo), _p(mc), _p(uvn), _p(pf), _p(cp), _p(fx), C.byref(opt), _p(po), _p(co),
+                                             _p(inl), _p(st), _p(info)))
+        return st[:nP], po[:Ft], co[:nP], inl[:Ft], info[:nP]
 
     # ---- UpdaterZeroVelocity ----
     def zupt_feed_imu(self, t, wm, am):

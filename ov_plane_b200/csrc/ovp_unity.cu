@@ -5,6 +5,7 @@
 #include "features.cu"
 #include "capi.cu"
 #include "capi2.cu"
+#include "planefit.cu"
 #ifdef OVP_DEBUG // libovp_debug.so only: micro-benchmarks and kernel-level test hooks (include/ovp_debug.h)
 #include "debug_hooks.cu"
 #include "debug_potrf.cu"

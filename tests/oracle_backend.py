@@ -13,7 +13,7 @@ KIND_VEC, KIND_POSE, KIND_IMU, KIND_LANDMARK = 0, 1, 2, 3
 
 
 def _load():
-    srcs = [os.path.join(_ODIR, "oracle.hpp"), os.path.join(_ODIR, "oracle_capi.cpp")]
+    srcs = [os.path.join(_ODIR, f) for f in ("oracle.hpp", "oracle_planefit.hpp", "oracle_capi.cpp")]
     if (not os.path.exists(_LIB)) or any(os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
         subprocess.check_call(["make", "-C", _ODIR, "CXX=g++"])
     lib = C.CDLL(_LIB)
@@ -357,6 +357,51 @@ class OracleContext(object):
         pf, st = np.zeros((max(1, F), 3)), np.zeros(max(1, F), dtype=np.int32)
         self._ck(self.lib.orc_triangulate_features(self.h, F, _p(mo), _p(mc), _p(uvn), _p(pf), _p(st)))
         return pf[:F], st[:F]
+
+    # ---- PlaneFitting ----
+    def plane_fitting(self, feat_offset, p_FinG, min_inlier_num, max_cond, shuffle_kind=0):
+        fo, pf = _i32(feat_offset), _f64(p_FinG).reshape(-1, 3)
+        nP, Ft = len(fo) - 1, int(fo[-1])
+        st, ab, inl = np.zeros(nP, dtype=np.int32), np.zeros((nP, 4)), np.zeros(max(1, Ft), dtype=np.int32)
+        for p in range(nP):
+            a, b = int(fo[p]), int(fo[p + 1])
+            pts, il, ok, abcd = np.ascontiguousarray(pf[a:b]), np.zeros(max(1, b - a), dtype=np.int32), C.c_int(0), np.zeros(4)
+            self.lib.orc_plane_fitting(b - a, _p(pts), int(min_inlier_num), C.c_double(max_cond), int(shuffle_kind), _p(abcd), _p(il), C.byref(ok))
+            st[p] = ok.value
+            ab[p] = abcd if ok.value else 0.0
+            inl[a:b] = il[:b - a] if ok.value else 0
+        return st, ab, inl[:Ft]
+
+    def optimize_plane(self, feat_offset, meas_offset, meas_clone, uv_norm, p_FinG, cp_inG, fix_plane, sigma_px_norm, sigma_c, max_num_iterations=0):
+        fo, mo, mc = _i32(feat_offset), _i32(meas_offset), _i32(meas_clone)
+        uvn = np.ascontiguousarray(uv_norm, dtype=np.float32).reshape(-1, 2)
+        pf, cp, fx = _f64(p_FinG).reshape(-1, 3), _f64(cp_inG).reshape(-1, 3), _i32(fix_plane)
+        nP, Ft = len(fo) - 1, int(fo[-1])
+        po, co = pf.copy(), cp.copy()
+        inl, st, info = np.zeros(max(1, Ft), dtype=np.int32), np.zeros(nP, dtype=np.int32), np.zeros((nP, 5))
+        for p in range(nP):
+            a, b = int(fo[p]), int(fo[p + 1])
+            F = b - a
+            m0, m1 = int(mo[a]), int(mo[b])
+            lmo = np.ascontiguousarray(mo[a:b + 1] - m0, dtype=np.int32)
+            lmc, luv = np.ascontiguousarray(mc[m0:m1]), np.ascontiguousarray(uvn[m0:m1])
+            lp, lcp = np.ascontiguousarray(pf[a:b]), np.ascontiguousarray(cp[p])
+            op, oc, il, ok, inf = np.zeros((max(1, F), 3)), np.zeros(3), np.zeros(max(1, F), dtype=np.int32), C.c_int(0), np.zeros(5)
+            self._ck(self.lib.orc_optimize_plane(self.h, F, _p(lmo), _p(lmc), _p(luv), _p(lp), _p(lcp), C.c_double(sigma_px_norm),
+                                                 C.c_double(sigma_c), int(fx[p]), int(max_num_iterations), _p(op), _p(oc), _p(il), C.byref(ok), _p(inf)))
+            st[p], info[p] = ok.value, inf
+            po[a:b], co[p], inl[a:b] = op[:F], oc, il[:F]
+        return st, po, co, inl[:Ft], info
+
+    def optimize_plane_cost(self, meas_offset, meas_clone, uv_norm, p_FinG, cp_inG, fix_plane, sigma_px_norm, sigma_c):
+        """robustified cost 1/2 sum rho(s) of ONE plane's refinement problem at the given point"""
+        mo, mc = _i32(meas_offset), _i32(meas_clone)
+        uvn = np.ascontiguousarray(uv_norm, dtype=np.float32)
+        pf, cp = _f64(p_FinG).reshape(-1, 3), _f64(cp_inG)
+        cost = C.c_double(0.0)
+        self._ck(self.lib.orc_optimize_plane_cost(self.h, len(mo) - 1, _p(mo), _p(mc), _p(uvn), _p(pf), _p(cp), C.c_double(sigma_px_norm),
+                                                  C.c_double(sigma_c), int(fix_plane), C.byref(cost)))
+        return cost.value
 
     # ---- UpdaterZeroVelocity ----
     def zupt_feed_imu(self, t, wm, am):

@@ -1,0 +1,221 @@
+"""CPU checks of the oracle's PlaneFitting restatement (oracle/oracle_planefit.hpp): the std::shuffle restatements, fit_plane against
+NumPy's SVD / lstsq, the RANSAC loop against an independent Python transcription of PlaneFitting.cpp:83-195, and the restated Ceres
+dogleg against a generic quasi-Newton minimisation of the same robustified cost.  Also the product library's context-free shuffle helper
+(a host function: no GPU needed)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_backend
+import planefit_cases
+from ov_plane_b200 import api, synth
+
+
+def _orc_shuffles(n, k, kind):
+    out = np.zeros((k, n), dtype=np.int32)
+    oracle_backend.lib().orc_plane_shuffle(n, k, kind, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 6, 37, 64, 150, 1000])
+def test_shuffle_restatements(n):
+    lemire, std = _orc_shuffles(n, 20, 1), _orc_shuffles(n, 20, 2)
+    # this container's libstdc++ (GCC >= 11) is the Lemire variant: pins the restated std::shuffle + uniform_int_distribution
+    assert np.array_equal(lemire, std)
+    classic = _orc_shuffles(n, 20, 0)
+    for P in (lemire, classic):
+        assert all(np.array_equal(np.sort(r), np.arange(n)) for r in P)
+    # the two libstdc++ generations map a 32-bit draw g to floor(g * r / 2^32) (Lemire) or floor(g / floor((2^32 - 1) / r)) (classic): the same
+    # integer except with probability ~ r / 2^32 per draw, so short sequences coincide; both stay selectable (ovp_plane_fit_options)
+    # product library: own Mersenne twister + the same two restatements
+    lib = api.load_library()
+    for kind, ref in ((0, classic), (1, lemire)):
+        out = np.zeros((20, n), dtype=np.int32)
+        assert lib.ovp_plane_shuffle(n, 20, kind, out.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(out, ref)
+
+
+def _fit_plane_np(P, cond_thresh, cond_check=True):
+    if len(P) < 3:
+        return False, None
+    if cond_check:
+        s = np.linalg.svd(P, compute_uv=False)
+        if s[0] / s[-1] > cond_thresh:
+            return False, None
+    n = np.linalg.lstsq(P, -np.ones(len(P)), rcond=None)[0]
+    abcd = np.append(n, 1.0) / np.linalg.norm(n)
+    return np.linalg.norm(abcd[:3] * abcd[3]) > 0.02, abcd
+
+
+def test_fit_plane_matches_numpy():
+    rng = np.random.RandomState(3)
+    L = oracle_backend.lib()
+    n_ok = 0
+    for trial in range(200):
+        K = rng.choice([3, 5, 5, 5, 12, 40])
+        nrm = rng.randn(3)
+        nrm /= np.linalg.norm(nrm)
+        d = rng.uniform(0.01, 4.0)
+        B = np.linalg.svd(nrm[None, :])[2][1:]
+        P = (rng.uniform(-2, 2, size=(K, 2)) * rng.choice([1.0, 0.05, 0.01])) @ B + d * nrm + 0.003 * rng.randn(K, 3)
+        P = np.ascontiguousarray(P)
+        abcd, ok = np.zeros(4), C.c_int(0)
+        thr = rng.choice([50.0, 200.0])
+        L.orc_fit_plane(int(K), P.ctypes.data_as(C.c_void_p), C.c_double(thr), 1, abcd.ctypes.data_as(C.c_void_p), C.byref(ok))
+        ok_np, abcd_np = _fit_plane_np(P, thr)
+        s = np.linalg.svd(P, compute_uv=False)
+        if abs(s[0] / s[-1] - thr) < 1e-6 * thr:
+            continue
+        assert bool(ok.value) == bool(ok_np), (trial, K)
+        if ok_np:
+            n_ok += 1
+            assert np.abs(abcd - abcd_np).max() < 1e-9 * max(1.0, s[0] / s[-1])
+    assert n_ok > 40
+
+
+def _plane_fitting_py(P, min_inlier_num, max_cond, perms):
+    """PlaneFitting.cpp:83-195 transcribed with NumPy linear algebra; perms = the 200 shuffles of range(F)"""
+    F = len(P)
+    thr = max(min_inlier_num, int(F * 0.80))
+    if F < min_inlier_num:
+        return False, None, None
+    best, best_err = [], -1.0
+    for n in range(200):
+        sel = []
+        for c in perms[n]:
+            if len(sel) == 5:
+                break
+            if all(np.linalg.norm(P[q] - P[c]) >= 0.05 for q in sel):
+                sel.append(c)
+        if len(sel) != 5:
+            return False, None, None
+        ok, abcd = _fit_plane_np(P[sel], max_cond)
+        if not ok:
+            continue
+        e = np.abs(P @ abcd[:3] + abcd[3])
+        inl = np.nonzero(e < 0.05)[0]
+        avg = e[inl].sum() / len(inl) if len(inl) else np.nan
+        if len(inl) > thr and avg < 0.05 and (len(best) < len(inl) or (len(best) == len(inl) and avg < best_err)):
+            best, best_err = inl, avg
+    if len(best):
+        ok, abcd = _fit_plane_np(P[best], max_cond, cond_check=False)
+        if ok:
+            return True, abcd, best
+    return False, None, None
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("name,seed", [("small_planes", 0), ("small_planes", 1), ("cfg3_n512_f600_p8", 0)])
+def test_plane_fitting_matches_python_transcription(name, seed, kind):
+    S = synth.make_scenario(name, seed=seed)
+    fo, pts = planefit_cases.plane_point_sets(S, seed=seed)
+    orc = oracle_backend.OracleContext(S.options)
+    st, ab, inl = orc.plane_fitting(fo, pts, 5, 200.0, shuffle_kind=kind)
+    n_ok = 0
+    for p in range(len(fo) - 1):
+        P = pts[fo[p]:fo[p + 1]]
+        ok, abcd, best = _plane_fitting_py(P, 5, 200.0, _orc_shuffles(len(P), 200, kind))
+        assert bool(st[p]) == bool(ok), p
+        if ok:
+            n_ok += 1
+            flags = np.zeros(len(P), dtype=np.int32)
+            flags[best] = 1
+            assert np.array_equal(flags, inl[fo[p]:fo[p + 1]]), p
+            assert np.abs(ab[p] - abcd).max() < 1e-9
+            assert flags.sum() < len(P)  # the outliers were rejected
+    assert n_ok >= len(fo) - 2
+
+
+def test_plane_fitting_failure_modes():
+    orc = oracle_backend.OracleContext(synth.make_scenario("tiny_planes").options)
+    rng = np.random.RandomState(0)
+    few = rng.randn(4, 3)
+    assert orc.plane_fitting([0, 4], few, 5, 200.0)[0][0] == 0                       # fewer points than min_inlier_num
+    clustered = np.array([1.0, 2.0, 3.0]) + 0.004 * rng.randn(30, 3)
+    assert orc.plane_fitting([0, 30], clustered, 5, 200.0)[0][0] == 0                # no five points 0.05 m apart (:133-136)
+    cloud = rng.uniform(-2, 2, size=(40, 3))
+    assert orc.plane_fitting([0, 40], cloud, 5, 200.0)[0][0] == 0                    # no plane: never > 80 % inliers
+
+
+@pytest.mark.parametrize("fix_plane", [0, 1])
+def test_restated_dogleg_minimises_the_robust_cost(fix_plane):
+    """Run to convergence (iteration limit lifted), the restated Ceres iteration ends at a cost that a generic quasi-Newton minimiser of the same
+    robustified cost (SciPy's L-BFGS-B with numerical derivatives on the oracle's cost function) approaches from above and does not undercut."""
+    from scipy.optimize import minimize
+    S = synth.make_scenario("small_planes", seed=2)
+    orc = oracle_backend.OracleContext(S.options)
+    ch = synth.load_scenario_into(orc, S)
+    pr = planefit_cases.refine_problem(S, ch, seed=2, consistent=True)
+    sig_px, sig_c = 1.0 / 458.0, 0.01
+    fx = np.full(len(pr["feat_offset"]) - 1, fix_plane, dtype=np.int32)
+    args = (pr["feat_offset"], pr["meas_offset"], pr["meas_clone"], pr["uv_norm"], pr["p_FinG"], pr["cp_inG"], fx, sig_px, sig_c)
+    st, po, co, inl, info = orc.optimize_plane(*args, max_num_iterations=200)
+    assert (info[:, 0] == 1).all() and (info[:, 3] < info[:, 2]).all()
+    fo, mo = pr["feat_offset"], pr["meas_offset"]
+    for p in range(len(fo) - 1):
+        a, b = fo[p], fo[p + 1]
+        lmo = mo[a:b + 1] - mo[a]
+        lmc, luv = pr["meas_clone"][mo[a]:mo[b]], pr["uv_norm"][mo[a]:mo[b]]
+        free = np.nonzero(np.diff(lmo) > 0)[0]
+
+        def cost(x):
+            pf = pr["p_FinG"][a:b].copy()
+            pf[free] = x[:3 * len(free)].reshape(-1, 3)
+            cp = pr["cp_inG"][p] if fix_plane else x[3 * len(free):]
+            return orc.optimize_plane_cost(lmo, lmc, luv, pf, cp, fix_plane, sig_px, sig_c)
+
+        x0 = np.concatenate([pr["p_FinG"][a:b][free].ravel(), [] if fix_plane else pr["cp_inG"][p]])
+        assert abs(cost(x0) - info[p, 2]) < 1e-9 * info[p, 2]
+        best = minimize(cost, x0, method="L-BFGS-B", options=dict(maxiter=150, maxfun=20000, ftol=1e-12, gtol=1e-9, eps=1e-7))
+        print("plane %d fix %d: cost %.4f -> dogleg %.6f (%d iterations, reason %d) | L-BFGS-B %.6f" % (p, fix_plane, info[p, 2], info[p, 3], info[p, 1],
+                                                                                                  info[p, 4], best.fun))
+        # the generic minimiser (numerical derivatives, badly scaled variables) approaches the same minimum from above and never gets below it
+        assert info[p, 3] <= best.fun * (1.0 + 2e-5)  # (function tolerance 1e-6 per iteration at the stop)
+
+
+def test_noise_free_refinement_recovers_the_true_plane():
+    S = synth.make_scenario("small_planes", seed=2)
+    orc = oracle_backend.OracleContext(S.options)
+    ch = synth.load_scenario_into(orc, S)
+    pr = planefit_cases.refine_problem(S, ch, seed=2, noise=0.0, consistent=True, px_noise=0.0, slam_share=0.0)
+    fx = np.zeros(len(pr["feat_offset"]) - 1, dtype=np.int32)
+    st, po, co, inl, info = orc.optimize_plane(pr["feat_offset"], pr["meas_offset"], pr["meas_clone"], pr["uv_norm"], pr["p_FinG"], pr["cp_inG"], fx,
+                                                1.0 / 458.0, 0.01)
+    assert (st == 1).all() and (info[:, 1] <= 5).all() and (info[:, 3] < 1e-6).all() and inl.all()
+    for k, pid in enumerate(S.plane_ids):
+        P = S.pf_true[S.planeid == pid]
+        n = np.linalg.lstsq(P, -np.ones(len(P)), rcond=None)[0]
+        cp_true = -n / (n @ n)
+        assert np.linalg.norm(pr["cp_inG"][k] - cp_true) > 5e-3 and np.linalg.norm(co[k] - cp_true) < 5e-6
+    assert np.abs(po - pr["p_FinG"]).max() < 1e-5  # single precision normalised coordinates: 6e-8 x 5 m
+
+
+def test_optimize_plane_reference_semantics():
+    """12 iterations (PlaneFitting.cpp:396): no CONVERGENCE => false and nothing is touched (:431-438); converged but fewer than 80 % inliers => false
+    with the side effects already applied (:441-487); too few features => false outright (:211-214)."""
+    S = synth.make_scenario("small_planes", seed=2)
+    orc = oracle_backend.OracleContext(S.options)
+    ch = synth.load_scenario_into(orc, S)
+    hard = planefit_cases.refine_problem(S, ch, seed=2)  # pixels inconsistent with the state's poses: slow robust convergence
+    fx = np.zeros(len(hard["feat_offset"]) - 1, dtype=np.int32)
+    st, po, co, inl, info = orc.optimize_plane(hard["feat_offset"], hard["meas_offset"], hard["meas_clone"], hard["uv_norm"], hard["p_FinG"], hard["cp_inG"],
+                                                fx, 1.0 / 458.0, 0.01)
+    assert (info[:, 0] == 0).all() and (info[:, 1] == 12).all() and (info[:, 4] == -1).all() and (st == 0).all()
+    assert np.array_equal(po, hard["p_FinG"]) and np.array_equal(co, hard["cp_inG"]) and inl.sum() == 0
+    easy = planefit_cases.refine_problem(S, ch, seed=2, consistent=True, noise=0.004)
+    st, po, co, inl, info = orc.optimize_plane(easy["feat_offset"], easy["meas_offset"], easy["meas_clone"], easy["uv_norm"], easy["p_FinG"], easy["cp_inG"],
+                                                fx, 1.0 / 458.0, 0.01)
+    conv = info[:, 0] == 1
+    assert conv.sum() >= 2 and (st[~conv] == 0).all()
+    for p in np.nonzero(conv)[0]:
+        a, b = easy["feat_offset"][p], easy["feat_offset"][p + 1]
+        moved = np.abs(po[a:b] - easy["p_FinG"][a:b]).max(axis=1) > 0
+        has_meas = np.diff(easy["meas_offset"][a:b + 1]) > 0
+        assert np.array_equal(moved, (inl[a:b] == 1) & has_meas)           # only measured inliers receive their refined position
+        assert not np.array_equal(co[p], easy["cp_inG"][p])
+        assert bool(st[p]) == (inl[a:b].sum() >= max(4, int(0.8 * (b - a))))
+    # three features, free plane: refused before anything is built
+    st, po, co, inl, info = orc.optimize_plane([0, 3], easy["meas_offset"][:4], easy["meas_clone"], easy["uv_norm"], easy["p_FinG"][:3], easy["cp_inG"][:1],
+                                                [0], 1.0 / 458.0, 0.01)
+    assert st[0] == 0 and info[0, 1] == 0

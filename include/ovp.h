@@ -205,6 +205,27 @@ int ovp_slam_handle(ovp_ctx *ctx, int64_t featid);       /* State::_features_SLA
 int ovp_slam_should_marg(ovp_ctx *ctx, int64_t featid);  /* Landmark::should_marg (1/0), -1 = absent */
 int64_t ovp_slam_plane_of(ovp_ctx *ctx, int64_t featid); /* State::_features_SLAM_to_PLANE entry, -1 = no entry */
 
+/* ---- Anchored landmark representations (UpdaterHelper.cpp:35-193, UpdaterSLAM.cpp:684-850) -------------------------------------------- */
+/* get_feature_jacobian_full (UpdaterHelper.cpp:195-449) for any ov_type::LandmarkRepresentation (numbering as in
+ * ovp_feature_jacobian_representation).  p_F / p_F_fej: p_FinG and its first estimate for the global forms (0, 1), p_FinA for the anchored
+ * forms (the first-estimate argument is then unused, :297-301).  The anchor clone is appended to x_order when no measurement was taken
+ * from it (:245-264).  No plane rows: the reference's plane constraint asserts GLOBAL_3D (:455-456).  Same output layout as
+ * ovp_feature_jacobian_full; H_f has 3 columns (1 for ANCHORED_INVERSE_DEPTH_SINGLE). */
+int ovp_feature_jacobian_full_rep(ovp_ctx *ctx, int m, const int *clone_handles, const float *uv, int representation, int anchor_clone_handle,
+                                  const double *p_F, const double *p_F_fej, double sigma_px, double *H_f, int *hf_cols, double *H_x, int *hx_cols,
+                                  double *res, int *rows_out, int *x_order, int *x_order_n);
+/* Landmark::_feat_representation / _anchor_clone_timestamp of a landmark that is in the state: declares how its 3-vector value is read
+ * (0 / 2 position, 1 / 3 [theta, phi, rho], 4 [x/z, y/z, 1/z]).  The fused update entry points (ovp_slam_update, ...) are GLOBAL_3D and
+ * refuse landmarks declared otherwise. */
+int ovp_slam_set_representation(ovp_ctx *ctx, int64_t featid, int representation, int anchor_clone_handle);
+int ovp_slam_get_representation(ovp_ctx *ctx, int64_t featid, int *representation, int *anchor_clone_handle);
+/* UpdaterSLAM::perform_anchor_change (:706-850): re-express an anchored landmark in another clone's camera frame; covariance through
+ * StateHelper::EKFPropagation with the anchor-change Jacobian, value and first estimate re-anchored. */
+int ovp_slam_perform_anchor_change(ovp_ctx *ctx, int64_t featid, int new_anchor_clone_handle);
+/* UpdaterSLAM::change_anchors (:684-704): when the clone window is over its limit, every landmark anchored in the clone about to be
+ * marginalised (the oldest) moves to the clone at the state time.  *n_changed (optional): how many landmarks moved. */
+int ovp_slam_change_anchors(ovp_ctx *ctx, int *n_changed);
+
 /* ---- Multi-GPU sharding of one large update ----------------------------------------------------------- */
 /* Rank-local half: Jacobians, nullspace, chi2 gates and compression of THIS rank's point features against the replicated
  * state; writes the (n+1) x (n+1) lower-triangular factor block [R^T ; z^T] in the canonical column order of the FULL batch

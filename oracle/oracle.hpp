@@ -324,6 +324,9 @@ struct Var {
   // Landmark extras
   size_t featid = 0;
   bool should_marg = false;
+  int feat_representation = 0;        // Landmark::_feat_representation
+  double anchor_clone_timestamp = -1; // Landmark::_anchor_clone_timestamp
+  bool has_had_anchor_change = false;
   int handle = -1; // stable external identifier (tests use it to address variables)
 
   int size() const { return sz; }
@@ -1064,6 +1067,12 @@ struct Feature {
   Mat cp_FinG = Mat(3, 1);
   Mat cp_FinG_fej = Mat(3, 1);
   bool to_delete = false;
+  // ov_type::LandmarkRepresentation (0 GLOBAL_3D ... 5 ANCHORED_INVERSE_DEPTH_SINGLE) and, for the anchored forms, the anchor clone and the
+  // feature in its camera frame (UpdaterHelper.h:61-99)
+  int feat_representation = 0;
+  double anchor_clone_timestamp = -1;
+  Mat p_FinA = Mat(3, 1);
+  Mat p_FinA_fej = Mat(3, 1);
 };
 
 struct UpdaterHelper {
@@ -1169,6 +1178,21 @@ struct UpdaterHelper {
         }
       }
     }
+    const bool relative = feature.feat_representation >= 2; // LandmarkRepresentation::is_relative_representation
+    VarP clone_Ai;
+    if (relative) { // :245-264: the anchor clone (and its extrinsics) take part even without a measurement from it
+      clone_Ai = state->_clones_IMU.at(feature.anchor_clone_timestamp);
+      if (map_hx.find(clone_Ai.get()) == map_hx.end()) {
+        map_hx.insert({clone_Ai.get(), total_hx});
+        x_order.push_back(clone_Ai);
+        total_hx += clone_Ai->size();
+      }
+      if (state->_options.do_calib_camera_pose && map_hx.find(calibration.get()) == map_hx.end()) {
+        map_hx.insert({calibration.get(), total_hx});
+        x_order.push_back(calibration);
+        total_hx += calibration->size();
+      }
+    }
     bool plane_in_state = (state->_features_PLANE.find(feature.planeid) != state->_features_PLANE.end());
     if (feature.planeid != 0 && plane_in_state) {
       VarP planecp = state->_features_PLANE.at(feature.planeid);
@@ -1179,10 +1203,29 @@ struct UpdaterHelper {
       }
     }
     Mat p_FinG = feature.p_FinG;
+    if (relative) // :281-293
+      p_FinG = clone_Ai->Rot().T() * calibration->Rot().T() * (feature.p_FinA - calibration->pos()) + clone_Ai->pos();
     Mat p_FinG_fej = feature.p_FinG_fej;
+    if (relative) // :297-301
+      p_FinG_fej = p_FinG;
+    // :318-323 derivative of p_FinG in the feature representation, computed once
+    Mat dpfg_dlambda = Mat::Identity(3), dpfg_danchor, dpfg_dcalib;
+    bool has_anchor_jac = false;
+    if (feature.feat_representation != 0) {
+      Mat anchor(7, 1), anchor_fej(7, 1), calib7(7, 1);
+      for (int i = 0; i < 7; i++) {
+        anchor(i, 0) = relative ? clone_Ai->value[i] : 0.0;
+        anchor_fej(i, 0) = relative ? clone_Ai->fej[i] : 0.0;
+        calib7(i, 0) = calibration->value[i];
+      }
+      has_anchor_jac = get_feature_jacobian_representation(feature.feat_representation, state->_options.do_fej, p_FinG, p_FinG_fej, feature.p_FinA,
+                                                            anchor, anchor_fej, calib7, dpfg_dlambda, dpfg_danchor, dpfg_dcalib);
+      if (feature.planeid != 0)
+        ref_exit("the point-on-plane rows require GLOBAL_3D (assert, UpdaterHelper.cpp:455-456)");
+    }
 
     int c = 0;
-    int jacobsize = 3;
+    int jacobsize = (feature.feat_representation != 5) ? 3 : 1;
     jacobsize += (feature.planeid != 0 && !plane_in_state) ? 3 : 0;
     int meassize = (feature.planeid != 0) ? (3 * total_meas) : (2 * total_meas);
     if (total_meas == 0 && feature.planeid != 0)
@@ -1228,8 +1271,13 @@ struct UpdaterHelper {
       dpfc_dclone.setBlock(0, 3, -1.0 * dpfc_dpfg);
       Mat dz_dpfc = dz_dzn * dzn_dpfc;
       Mat dz_dpfg = dz_dpfc * dpfc_dpfg;
-      H_f.setBlock(c, 0, white_px * dz_dpfg);
+      H_f.setBlock(c, 0, (white_px * dz_dpfg) * dpfg_dlambda); // :411
       H_x.setBlock(c, map_hx[clone_Ii.get()], (white_px * dz_dpfc) * dpfc_dclone);
+      if (has_anchor_jac) { // :418-420: we might be in the anchoring pose for this measurement, hence +=
+        H_x.addBlock(c, map_hx[clone_Ai.get()], (white_px * dz_dpfg) * dpfg_danchor);
+        if (state->_options.do_calib_camera_pose)
+          H_x.addBlock(c, map_hx[calibration.get()], (white_px * dz_dpfg) * dpfg_dcalib);
+      }
       if (state->_options.do_calib_camera_pose) {
         Mat dpfc_dcalib(3, 6);
         dpfc_dcalib.setBlock(0, 0, skew_x(p_FinCi - p_IinC));
@@ -1700,6 +1748,126 @@ struct SlamOptions {
   double sigma_pix = 1.0, chi2_multipler = 1.0;
   bool use_plane_constraint_slamu = true, use_plane_constraint_slamd = true;
 };
+// ---------------------------------------------------------------------------------------------------------------
+// ov_type::Landmark::get_xyz / set_from_xyz (ov_core @74a63cf, not in the tree: restated) and UpdaterSLAM::change_anchors /
+// perform_anchor_change (update/UpdaterSLAM.cpp:684-850).  Landmark forms 0..4 (the single-depth form needs the initial bearing).
+// ---------------------------------------------------------------------------------------------------------------
+struct LandmarkOps {
+  static Mat get_xyz(const Var &lm, bool isfej) {
+    const std::vector<double> &v = isfej ? lm.fej : lm.value;
+    const int rep = lm.feat_representation;
+    if (rep == 0 || rep == 2)
+      return vec3(v[0], v[1], v[2]);
+    if (rep == 4)
+      return vec3(v[0] / v[2], v[1] / v[2], 1.0 / v[2]);
+    if (rep == 1 || rep == 3)
+      return (1.0 / v[2]) * vec3(std::cos(v[0]) * std::sin(v[1]), std::sin(v[0]) * std::sin(v[1]), std::cos(v[1]));
+    ref_exit("Landmark::get_xyz: representation not carried");
+    return Mat(3, 1);
+  }
+  static void set_from_xyz(Var &lm, const Mat &p, bool isfej) {
+    std::vector<double> &v = isfej ? lm.fej : lm.value;
+    const int rep = lm.feat_representation;
+    if (rep == 0 || rep == 2) {
+      v[0] = p(0, 0), v[1] = p(1, 0), v[2] = p(2, 0);
+    } else if (rep == 4) {
+      v[0] = p(0, 0) / p(2, 0), v[1] = p(1, 0) / p(2, 0), v[2] = 1.0 / p(2, 0);
+    } else if (rep == 1 || rep == 3) {
+      double g_rho = 1.0 / p.norm();
+      v[0] = std::atan2(p(1, 0), p(0, 0));
+      v[1] = std::acos(g_rho * p(2, 0));
+      v[2] = g_rho;
+    } else {
+      ref_exit("Landmark::set_from_xyz: representation not carried");
+    }
+  }
+  // UpdaterSLAM::perform_anchor_change (:706-850), mono camera (anchor_cam_id = 0)
+  static void perform_anchor_change(StateP state, VarP landmark, double new_anchor_timestamp) {
+    const int rep = landmark->feat_representation;
+    if (rep < 2)
+      ref_exit("perform_anchor_change: not an anchored representation (assert, :710)");
+    VarP calibv = state->_calib_IMUtoCAM;
+    VarP cl_old = state->_clones_IMU.at(landmark->anchor_clone_timestamp), cl_new = state->_clones_IMU.at(new_anchor_timestamp);
+    auto pose7 = [](const VarP &v, bool fej) {
+      Mat m(7, 1);
+      for (int i = 0; i < 7; i++)
+        m(i, 0) = fej ? v->fej[i] : v->value[i];
+      return m;
+    };
+    Mat p_FinA = get_xyz(*landmark, false), p_FinA_fej = get_xyz(*landmark, true);
+    Mat H_f_old, Ha_old, Hc_old, H_f_new, Ha_new, Hc_new, zero3(3, 1);
+    UpdaterHelper::get_feature_jacobian_representation(rep, state->_options.do_fej, zero3, zero3, p_FinA, pose7(cl_old, false), pose7(cl_old, true),
+                                                       pose7(calibv, false), H_f_old, Ha_old, Hc_old);
+    // :739-777 the landmark in the new anchor camera, best and first estimates (the extrinsics have no first estimate)
+    auto reanchor = [&](bool fej, const Mat &p_in) {
+      Mat R_GtoOLD = calibv->Rot() * (fej ? cl_old->Rot_fej() : cl_old->Rot());
+      Mat p_OLDinG = (fej ? cl_old->pos_fej() : cl_old->pos()) - R_GtoOLD.T() * calibv->pos();
+      Mat R_GtoNEW = calibv->Rot() * (fej ? cl_new->Rot_fej() : cl_new->Rot());
+      Mat p_NEWinG = (fej ? cl_new->pos_fej() : cl_new->pos()) - R_GtoNEW.T() * calibv->pos();
+      Mat R_OLDtoNEW = R_GtoNEW * R_GtoOLD.T();
+      Mat p_OLDinNEW = R_GtoNEW * (p_OLDinG - p_NEWinG);
+      return R_OLDtoNEW * p_in + p_OLDinNEW;
+    };
+    Mat p_FinA_new = reanchor(false, p_FinA), p_FinA_new_fej = reanchor(true, p_FinA_fej);
+    UpdaterHelper::get_feature_jacobian_representation(rep, state->_options.do_fej, zero3, zero3, p_FinA_new, pose7(cl_new, false), pose7(cl_new, true),
+                                                       pose7(calibv, false), H_f_new, Ha_new, Hc_new);
+    std::vector<VarP> x_order_old = {cl_old}, x_order_new = {cl_new};
+    std::vector<Mat> H_x_old = {Ha_old}, H_x_new = {Ha_new};
+    if (state->_options.do_calib_camera_pose) {
+      x_order_old.push_back(calibv);
+      H_x_old.push_back(Hc_old);
+      x_order_new.push_back(calibv);
+      H_x_new.push_back(Hc_new);
+    }
+    std::vector<VarP> phi_order_NEW = {landmark}, phi_order_OLD;
+    int current_it = 0;
+    std::map<Var *, int> Phi_id_map;
+    for (auto &var : x_order_old)
+      if (Phi_id_map.find(var.get()) == Phi_id_map.end()) {
+        Phi_id_map.insert({var.get(), current_it});
+        phi_order_OLD.push_back(var);
+        current_it += var->size();
+      }
+    for (auto &var : x_order_new)
+      if (Phi_id_map.find(var.get()) == Phi_id_map.end()) {
+        Phi_id_map.insert({var.get(), current_it});
+        phi_order_OLD.push_back(var);
+        current_it += var->size();
+      }
+    Phi_id_map.insert({landmark.get(), current_it});
+    phi_order_OLD.push_back(landmark);
+    current_it += landmark->size();
+    Mat Phi(3, current_it), Q(3, 3);
+    Mat H_f_new_inv = inverse_small(H_f_new);
+    for (size_t i = 0; i < H_x_old.size(); i++)
+      Phi.addBlock(0, Phi_id_map.at(x_order_old[i].get()), H_f_new_inv * H_x_old[i]);
+    Phi.setBlock(0, Phi_id_map.at(landmark.get()), H_f_new_inv * H_f_old);
+    for (size_t i = 0; i < H_x_new.size(); i++)
+      Phi.addBlock(0, Phi_id_map.at(x_order_new[i].get()), (-1.0) * (H_f_new_inv * H_x_new[i]));
+    StateHelper::EKFPropagation(state, phi_order_NEW, phi_order_OLD, Phi, Q);
+    landmark->anchor_clone_timestamp = new_anchor_timestamp;
+    set_from_xyz(*landmark, p_FinA_new, false);
+    set_from_xyz(*landmark, p_FinA_new_fej, true);
+    landmark->has_had_anchor_change = true;
+  }
+  // UpdaterSLAM::change_anchors (:684-704)
+  static int change_anchors(StateP state) {
+    if ((int)state->_clones_IMU.size() <= state->_options.max_clone_size)
+      return 0;
+    int n = 0;
+    double marg_timestep = state->margtimestep();
+    for (auto &f : state->_features_SLAM) {
+      if (f.second->feat_representation < 2)
+        continue;
+      if (f.second->anchor_clone_timestamp == marg_timestep) {
+        perform_anchor_change(state, f.second, state->_timestamp);
+        n++;
+      }
+    }
+    return n;
+  }
+};
+
 struct UpdaterSLAM {
   SlamOptions opt;
   Chi2Table chi2tab;

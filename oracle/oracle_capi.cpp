@@ -585,6 +585,73 @@ int orc_slam_should_marg(void *p, long long featid) {
   return it == c->state->_features_SLAM.end() ? -1 : (it->second->should_marg ? 1 : 0);
 }
 
+// ---- anchored representations: get_feature_jacobian_full with a representation, Landmark bookkeeping, anchor change ----
+static double clone_time_of(Ctx *c, int handle) {
+  VarP cl = c->state->by_handle.at(handle);
+  for (auto &kv : c->state->_clones_IMU)
+    if (kv.second == cl)
+      return kv.first;
+  throw std::runtime_error("handle is not a clone");
+}
+int orc_feature_jacobian_full_rep(void *p, int m, const int *clone_handles, const float *uv, int representation, int anchor_clone_handle,
+                                  const double *p_F, const double *p_F_fej, double sigma_px, double *H_f, int *hf_cols, double *H_x, int *hx_cols,
+                                  double *res, int *rows_out, int *x_order, int *x_order_n) {
+  Ctx *c = (Ctx *)p;
+  return guarded(c, [&] {
+    Feature f;
+    for (int i = 0; i < m; i++) {
+      f.timestamps.push_back(clone_time_of(c, clone_handles[i]));
+      f.uvs.push_back(uv[2 * i]);
+      f.uvs.push_back(uv[2 * i + 1]);
+    }
+    f.feat_representation = representation;
+    if (representation >= 2) {
+      f.anchor_clone_timestamp = clone_time_of(c, anchor_clone_handle);
+      f.p_FinA = vec3(p_F[0], p_F[1], p_F[2]);
+      f.p_FinA_fej = vec3(p_F_fej[0], p_F_fej[1], p_F_fej[2]);
+    } else {
+      f.p_FinG = vec3(p_F[0], p_F[1], p_F[2]);
+      f.p_FinG_fej = vec3(p_F_fej[0], p_F_fej[1], p_F_fej[2]);
+    }
+    Mat Hf, Hx, r;
+    std::vector<VarP> order;
+    UpdaterHelper::get_feature_jacobian_full(c->state, f, sigma_px, 1.0, Hf, Hx, r, order);
+    *hf_cols = Hf.cols();
+    *hx_cols = Hx.cols();
+    *rows_out = r.rows();
+    std::memcpy(H_f, Hf.a.data(), sizeof(double) * Hf.a.size());
+    std::memcpy(H_x, Hx.a.data(), sizeof(double) * Hx.a.size());
+    std::memcpy(res, r.a.data(), sizeof(double) * r.a.size());
+    *x_order_n = (int)order.size();
+    for (size_t i = 0; i < order.size(); i++)
+      x_order[i] = order[i]->handle;
+  });
+}
+int orc_slam_set_representation(void *p, long long featid, int representation, int anchor_clone_handle) {
+  Ctx *c = (Ctx *)p;
+  return guarded(c, [&] {
+    VarP lm = c->state->_features_SLAM.at((size_t)featid);
+    lm->feat_representation = representation;
+    lm->anchor_clone_timestamp = representation >= 2 ? clone_time_of(c, anchor_clone_handle) : -1;
+  });
+}
+int orc_slam_get_representation(void *p, long long featid, int *representation, int *anchor_clone_handle) {
+  Ctx *c = (Ctx *)p;
+  return guarded(c, [&] {
+    VarP lm = c->state->_features_SLAM.at((size_t)featid);
+    *representation = lm->feat_representation;
+    *anchor_clone_handle = lm->feat_representation >= 2 ? c->state->_clones_IMU.at(lm->anchor_clone_timestamp)->handle : -1;
+  });
+}
+int orc_slam_perform_anchor_change(void *p, long long featid, int new_anchor_clone_handle) {
+  Ctx *c = (Ctx *)p;
+  return guarded(c, [&] { LandmarkOps::perform_anchor_change(c->state, c->state->_features_SLAM.at((size_t)featid), clone_time_of(c, new_anchor_clone_handle)); });
+}
+int orc_slam_change_anchors(void *p, int *n_changed) {
+  Ctx *c = (Ctx *)p;
+  return guarded(c, [&] { *n_changed = LandmarkOps::change_anchors(c->state); });
+}
+
 // ---- Propagator -----------------------------------------------------------------------------------------------
 void orc_prop_set(void *p, double sigma_w, double sigma_wb, double sigma_a, double sigma_ab, double gravity_mag) {
   Ctx *c = (Ctx *)p;

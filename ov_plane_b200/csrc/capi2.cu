@@ -531,7 +531,7 @@ namespace ovp {
 // plane_handle >= 0: plane in the state (its values come from the device tables); otherwise cp / cp_fej (may be null: no plane).
 static int stage_feature_jacobian(Ctx *c, int m, const int *clone_handles, const float *uv, const double *p_FinG, const double *p_FinG_fej,
                                   bool has_plane, int plane_handle, const double *cp, const double *cp_fej, double sigma_px, double sigma_c,
-                                  int *rows_out, int *hfc_out, int *hxc_out) {
+                                  int *rows_out, int *hfc_out, int *hxc_out, int extra_hx_cols = 0) {
   if (m < 1 || m > 64)
     return fail(c, OVP_ERR_BAD_ARGS, "feature_jacobian_full: m=%d not in 1..64", m);
   for (int i = 0; i < m; i++) {
@@ -545,7 +545,7 @@ static int stage_feature_jacobian(Ctx *c, int m, const int *clone_handles, const
   const int ncal = (c->opt.do_calib_camera_pose ? 6 : 0) + (c->opt.do_calib_camera_intrinsics ? 8 : 0);
   const int rows = has_plane ? 3 * m : 2 * m;
   const int hfc = 3 + ((has_plane && !in_state) ? 3 : 0);
-  const int hxc = ncal + 6 * m + (in_state ? 3 : 0);
+  const int hxc = ncal + 6 * m + (in_state ? 3 : 0) + extra_hx_cols; // extra: zero columns appended for an anchor clone (anchors.cu)
   size_t e = (size_t)rows * (hfc + hxc + 1) + 256;
   int st = ensure_stage(c, e);
   if (st)

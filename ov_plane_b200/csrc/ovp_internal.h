@@ -20,6 +20,8 @@ struct Var {
   int64_t tag = 0;
   bool should_marg = false;
   bool alive = true;
+  int rep = 0;     // ov_type::LandmarkRepresentation of a SLAM landmark (0 = GLOBAL_3D)
+  int anchor = -1; // handle of its anchor clone (anchored representations), anchors.cu
 };
 
 struct ImuSample {

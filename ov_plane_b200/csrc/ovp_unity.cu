@@ -6,6 +6,7 @@
 #include "capi.cu"
 #include "capi2.cu"
 #include "planefit.cu"
+#include "anchors.cu"
 #ifdef OVP_DEBUG // libovp_debug.so only: micro-benchmarks and kernel-level test hooks (include/ovp_debug.h)
 #include "debug_hooks.cu"
 #include "debug_potrf.cu"

@@ -266,6 +266,37 @@ class OracleContext(object):
         return (Hf[:r * hfc.value].reshape((r, hfc.value), order="F").copy(), Hx[:r * hxc.value].reshape((r, hxc.value), order="F").copy(),
                 res[:r].copy(), xo[:xon.value].tolist())
 
+    def feature_jacobian_full_rep(self, clone_handles, uv, representation, anchor_clone_handle, p_F, p_F_fej, sigma_px):
+        ch, uv = _i32(clone_handles), np.ascontiguousarray(uv, dtype=np.float32)
+        m = len(ch)
+        rows_cap, cols_cap = 2 * m, 14 + 6 * (m + 1)
+        Hf, Hx, res = np.zeros(rows_cap * 3), np.zeros(rows_cap * cols_cap), np.zeros(rows_cap)
+        xo = np.zeros(m + 4, dtype=np.int32)
+        hfc, hxc, rows, xon = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        pf, pff = _f64(p_F), _f64(p_F_fej)
+        self._ck(self.lib.orc_feature_jacobian_full_rep(self.h, m, _p(ch), _p(uv), int(representation), int(anchor_clone_handle), _p(pf), _p(pff),
+                                                        C.c_double(sigma_px), _p(Hf), C.byref(hfc), _p(Hx), C.byref(hxc), _p(res), C.byref(rows),
+                                                        _p(xo), C.byref(xon)))
+        r = rows.value
+        return (Hf[:r * hfc.value].reshape((r, hfc.value), order="F").copy(), Hx[:r * hxc.value].reshape((r, hxc.value), order="F").copy(),
+                res[:r].copy(), xo[:xon.value].tolist())
+
+    def slam_set_representation(self, featid, representation, anchor_clone_handle=-1):
+        self._ck(self.lib.orc_slam_set_representation(self.h, C.c_longlong(int(featid)), int(representation), int(anchor_clone_handle)))
+
+    def slam_get_representation(self, featid):
+        rep, anc = C.c_int(-1), C.c_int(-1)
+        self._ck(self.lib.orc_slam_get_representation(self.h, C.c_longlong(int(featid)), C.byref(rep), C.byref(anc)))
+        return rep.value, anc.value
+
+    def slam_perform_anchor_change(self, featid, new_anchor_clone_handle):
+        self._ck(self.lib.orc_slam_perform_anchor_change(self.h, C.c_longlong(int(featid)), int(new_anchor_clone_handle)))
+
+    def slam_change_anchors(self):
+        n = C.c_int(0)
+        self._ck(self.lib.orc_slam_change_anchors(self.h, C.byref(n)))
+        return n.value
+
     def nullspace_project_inplace(self, H_f, H_x, res, H_cp=None):
         H_f, H_x, res = _cm(H_f).copy(order="F"), _cm(H_x).copy(order="F"), _f64(res).copy()
         rows, ro = H_f.shape[0], C.c_int()

@@ -1,0 +1,14 @@
+// MINIMAL STAND-IN for ov_core feat/Feature.h (OpenVINS @74a63cf): the members PlaneFitting reads.  Syntax check only.
+#pragma once
+#include <Eigen/Dense>
+#include <unordered_map>
+#include <vector>
+namespace ov_core {
+class Feature {
+public:
+  size_t featid;
+  std::unordered_map<size_t, std::vector<Eigen::Vector2f>> uvs_norm; // the reference holds Eigen::VectorXf of size 2
+  std::unordered_map<size_t, std::vector<double>> timestamps;
+  Eigen::Vector3d p_FinG;
+};
+} // namespace ov_core

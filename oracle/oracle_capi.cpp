@@ -266,6 +266,29 @@ int orc_initialize(void *p, int kind, int s, const double *value, const double *
     }
   });
 }
+// StateHelper::initialize_invertible called directly: H_L square (rows == size of the new variable), no chi2 test, no update
+int orc_initialize_invertible(void *p, int kind, int s, const double *value, const double *fej, long long tag, const int *handles, int k,
+                              const double *H_R, const double *H_L, const double *res, double sigma2, int *new_handle) {
+  Ctx *c = (Ctx *)p;
+  return guarded(c, [&] {
+    auto order = handles_to_vars(c, handles, k);
+    int n = 0;
+    for (auto &v : order)
+      n += v->sz;
+    VarP nv = (kind == KIND_LANDMARK) ? Var::makeLandmark(s) : Var::makeVec(s);
+    std::copy(value, value + s, nv->value.begin());
+    std::copy(fej, fej + s, nv->fej.begin());
+    nv->featid = (size_t)tag;
+    StateHelper::initialize_invertible(c->state, nv, order, from_colmajor(H_R, s, n), from_colmajor(H_L, s, s), sigma2 * Mat::Identity(s),
+                                       from_colmajor(res, s, 1));
+    c->state->reg(nv);
+    *new_handle = nv->handle;
+    if (kind == KIND_LANDMARK)
+      c->state->_features_SLAM[(size_t)tag] = nv;
+    else
+      c->state->_features_PLANE[(size_t)tag] = nv;
+  });
+}
 int orc_merge_planes_and_marginalize(void *p, const long long *f2p_feat, const long long *f2p_plane, int nf, const long long *merge_new,
                                      const long long *merge_old, int nm) {
   Ctx *c = (Ctx *)p;

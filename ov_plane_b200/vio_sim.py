@@ -187,11 +187,15 @@ class VioLoop(object):
     updater calls (a parity run wraps the CPU checker's calls so that its plane gates use the well-defined chi2, see tests/)."""
 
     def __init__(self, backend, sim, max_clones=30, min_clones_for_update=5, plane_init_min_feat=8, chi2_mult=1.0, gate_ctx=None,
-                 use_planes=True):
+                 use_planes=True, fit_planes=False, sigma_c=0.01):
         self.be, self.sim = backend, sim
         self.max_clones, self.min_clones = max_clones, min_clones_for_update
         self.plane_init_min_feat, self.chi2_mult, self.use_planes = plane_init_min_feat, chi2_mult, use_planes
         self.gate_ctx = gate_ctx
+        # fit_planes: plane estimates and refined feature positions come from PlaneFitting::plane_fitting / optimize_plane through the backend
+        # (UpdaterPlane.cpp:224-270, UpdaterMSCKF.cpp:262-360) instead of the simulator's stand-in
+        self.fit_planes, self.sigma_c = fit_planes, sigma_c
+        self.fit_stats = dict(ransac_ok=0, ransac_fail=0, refine_ok=0, refine_fail=0)
         self.tracks = {}   # featid -> list of (t, uv)
         self.planeof = {}  # featid -> planeid
         self.clone_times = []
@@ -328,6 +332,8 @@ class VioLoop(object):
             return None, []
         pfs = np.array(pfs)
         pids = np.array(pids, dtype=np.int64)
+        if self.fit_planes:
+            return self._finish_batch_with_plane_fitting(offs, mcl, uvs, pfs, fids, pids, cam)
         # plane estimates: in-state planes come from the state; new planes get a least-squares fit through their triangulated points
         plane_ids, plane_cp = [], []
         for pid in sorted(set(int(x) for x in pids if x > 0)):
@@ -366,6 +372,72 @@ class VioLoop(object):
                      plane_ids=np.array(plane_ids, dtype=np.int64), plane_cp=np.ascontiguousarray(np.array(plane_cp, dtype=np.float64).reshape(-1, 3)))
         return batch, fids
 
+    def _finish_batch_with_plane_fitting(self, offs, mcl, uvs, pfs, fids, pids, cam):
+        """The reference's order of business for the planes of a frame: a plane that is NOT in the state gets a RANSAC hypothesis from its
+        triangulated points (plane_fitting) and a joint refinement of plane + points (optimize_plane, free plane); a plane that IS in the state
+        only refines its points against the state's estimate (fixed plane).  Whatever fails falls back to plain point features this frame."""
+        be = self.be
+        pids = pids.copy()
+        offs = np.asarray(offs, dtype=np.int32)
+        uvn = np.array([undistort(cam, np.asarray(uv, dtype=np.float64)) for uv in uvs], dtype=np.float32).reshape(-1, 2)
+        groups = {int(pid): np.nonzero(pids == pid)[0] for pid in sorted(set(int(x) for x in pids if x > 0))}
+        new = [pid for pid, idx in groups.items() if be.plane_handle(pid) < 0 and len(idx) >= self.plane_init_min_feat]
+        for pid, idx in groups.items():
+            if be.plane_handle(pid) < 0 and pid not in new:
+                pids[idx] = 0
+        cp_of = {}
+        if new:
+            fo = np.cumsum([0] + [len(groups[pid]) for pid in new]).astype(np.int32)
+            st, ab, inl = be.plane_fitting(fo, np.vstack([pfs[groups[pid]] for pid in new]), self.plane_init_min_feat, 200.0)
+            for k, pid in enumerate(new):
+                idx = groups[pid]
+                if not st[k]:
+                    self.fit_stats["ransac_fail"] += 1
+                    pids[idx] = 0
+                    continue
+                self.fit_stats["ransac_ok"] += 1
+                keep = inl[fo[k]:fo[k + 1]] == 1
+                pids[idx[~keep]] = 0
+                groups[pid] = idx[keep]
+                cp_of[pid] = -ab[k, :3] * ab[k, 3]
+        cand = [pid for pid in groups if (pids[groups[pid]] == pid).any() and (pid in cp_of or be.plane_handle(pid) >= 0)]
+        pref = pfs.copy()
+        plane_ids, plane_cp = [], []
+        if cand:
+            fo, mo, mc, uv2, p0, cp0, fx = [0], [0], [], [], [], [], []
+            for pid in cand:
+                idx = groups[pid]
+                for i in idx:
+                    a, b = offs[i], offs[i + 1]
+                    mc.extend(mcl[a:b])
+                    uv2.append(uvn[a:b])
+                    mo.append(mo[-1] + (b - a))
+                    p0.append(pfs[i])
+                fo.append(fo[-1] + len(idx))
+                in_state = be.plane_handle(pid) >= 0
+                cp0.append(be.var_get(be.plane_handle(pid))[0][:3] if in_state else cp_of[pid])
+                fx.append(1 if in_state else 0)
+            st, po, co, inl, _ = be.optimize_plane(np.array(fo, dtype=np.int32), np.array(mo, dtype=np.int32), np.array(mc, dtype=np.int32),
+                                                   np.vstack(uv2), np.array(p0), np.array(cp0), np.array(fx, dtype=np.int32),
+                                                   self.sim.sigma_px / cam[0], self.sigma_c)
+            for k, pid in enumerate(cand):
+                idx = groups[pid]
+                if not st[k]:  # the reference skips the plane for this frame (`continue`, UpdaterMSCKF.cpp:279-280, 353-354)
+                    self.fit_stats["refine_fail"] += 1
+                    pids[idx] = 0
+                    continue
+                self.fit_stats["refine_ok"] += 1
+                keep = inl[fo[k]:fo[k + 1]] == 1
+                pref[idx[keep]] = po[fo[k]:fo[k + 1]][keep]
+                pids[idx[~keep]] = 0
+                plane_ids.append(pid)
+                plane_cp.append(co[k] if not fx[k] else np.asarray(cp0[k]))
+        batch = dict(F=len(fids), meas_offset=offs, meas_clone=np.array(mcl, dtype=np.int32),
+                     uv=np.ascontiguousarray(np.array(uvs, dtype=np.float32).reshape(-1, 2)), p_FinG=np.ascontiguousarray(pref),
+                     p_FinG_original=np.ascontiguousarray(pfs), featid=np.array(fids, dtype=np.int64), planeid=pids,
+                     plane_ids=np.array(plane_ids, dtype=np.int64), plane_cp=np.ascontiguousarray(np.array(plane_cp, dtype=np.float64).reshape(-1, 3)))
+        return batch, fids
+
     def _record(self, rec):
         be, sim = self.be, self.sim
         v, _ = be.var_get(be.handle_imu())
@@ -399,10 +471,10 @@ class _null(object):
         return False
 
 
-def run(backend, n_frames=100, seed=0, max_clones=30, n_feats=60, use_planes=True, gate_ctx=None, keep_cov_every=0, t0=0.5):
+def run(backend, n_frames=100, seed=0, max_clones=30, n_feats=60, use_planes=True, gate_ctx=None, keep_cov_every=0, t0=0.5, fit_planes=False):
     """Run the loop for n_frames camera frames; returns (loop, list of (frame index, covariance) snapshots)."""
     sim = RoomSimulator(seed=seed, n_feats=n_feats)
-    loop = VioLoop(backend, sim, max_clones=max_clones, gate_ctx=gate_ctx, use_planes=use_planes)
+    loop = VioLoop(backend, sim, max_clones=max_clones, gate_ctx=gate_ctx, use_planes=use_planes, fit_planes=fit_planes)
     loop.initialize_with_gt(t0)
     for (ti, wm, am) in sim.imu_until(t0):
         backend.feed_imu(ti, wm, am)

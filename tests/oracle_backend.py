@@ -237,6 +237,14 @@ class OracleContext(object):
                                          C.byref(nh)))
         return bool(acc.value), nh.value
 
+    def initialize_invertible(self, kind, value, fej, tag, handles, H_R, H_L, res, sigma2):
+        v, f, hs = _f64(value), _f64(fej), _i32(handles)
+        H_R, H_L, res = _cm(H_R), _cm(H_L), _f64(res)
+        nh = C.c_int(-1)
+        self._ck(self.lib.orc_initialize_invertible(self.h, kind, len(v), _p(v), _p(f), C.c_longlong(int(tag)), _p(hs), len(hs), _p(H_R), _p(H_L),
+                                                    _p(res), C.c_double(sigma2), C.byref(nh)))
+        return nh.value
+
     def merge_planes_and_marginalize(self, feat2plane, plane2oldplane):
         ff = np.array(list(feat2plane.keys()), dtype=np.int64)
         fp = np.array(list(feat2plane.values()), dtype=np.int64)

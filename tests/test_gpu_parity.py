@@ -272,6 +272,30 @@ def test_initialize_plane_and_landmark(chi2_table):
     assert ctx.cov_rows() == orc.cov_rows()
 
 
+def test_initialize_invertible_direct(chi2_table):
+    """StateHelper::initialize_invertible (StateHelper.cpp:489-586) called on its own: square H_L, new variable appended with its cross terms"""
+    S = synth.make_scenario("tiny_points", seed=4)
+    ctx, orc, chg, cho = make_pair(S, chi2_table)
+    rng = np.random.RandomState(5)
+    sel = [0, 2, 6]
+    hg = [ctx.handle_calib()] + [chg[i] for i in sel]
+    ho = [orc.handle_calib()] + [cho[i] for i in sel]
+    H_R, H_L, res = rng.randn(3, 24) * 5, rng.randn(3, 3) + 3 * np.eye(3), rng.randn(3) * 0.1
+    val = np.array([0.5, -1.0, 2.0])
+    N0 = ctx.cov_rows()
+    for kind, tag in ((0, 41), (3, 90001)):  # a plane (Vec) then a landmark
+        hn_g = ctx.initialize_invertible(kind, val, val, tag, hg, H_R, H_L, res, 0.25)
+        hn_o = orc.initialize_invertible(kind, val, val, tag, ho, H_R, H_L, res, 0.25)
+        assert ctx.var_id(hn_g) == orc.var_id(hn_o)
+        assert np.allclose(ctx.var_get(hn_g)[0][:3], orc.var_get(hn_o)[0][:3], rtol=1e-12, atol=1e-14)
+    assert ctx.cov_rows() == orc.cov_rows() == N0 + 6
+    e = relerr(ctx.cov(), orc.cov())
+    print("initialize_invertible direct: cov rel err %.3e" % e)
+    assert e < 1e-11
+    assert ctx.plane_handle(41) >= 0 and ctx.slam_handle(90001) >= 0
+    ctx.close()
+
+
 def test_propagate_and_clone(chi2_table):
     S = synth.make_scenario("tiny_points", seed=2)
     ctx, orc, chg, cho = make_pair(S, chi2_table)

@@ -15,7 +15,7 @@ from ov_plane_b200 import api, synth, vio_sim
 pytestmark = pytest.mark.gpu
 
 
-def _pair(max_clones, chi2_table, seed, n_feats=60):
+def _pair(max_clones, chi2_table, seed, n_feats=60, fit_planes=False):
     opts = vio_sim.state_options(max_clones=max_clones)
     g = api.Context(opts, device=0, max_state=384, max_meas_rows=20000)
     g.set_chi2_table(chi2_table)
@@ -24,7 +24,7 @@ def _pair(max_clones, chi2_table, seed, n_feats=60):
     loops = []
     for be, gate in ((g, None), (o, lambda: oracle_backend.GaugeProbe(gate_without=True))):
         sim = vio_sim.RoomSimulator(seed=seed, n_feats=n_feats)
-        lp = vio_sim.VioLoop(be, sim, max_clones=max_clones, gate_ctx=gate)
+        lp = vio_sim.VioLoop(be, sim, max_clones=max_clones, gate_ctx=gate, fit_planes=fit_planes)
         lp.initialize_with_gt(0.5)
         for (ti, wm, am) in sim.imu_until(0.5):
             be.feed_imu(ti, wm, am)
@@ -46,9 +46,10 @@ def _copy_state(src, dst):
     dst.be.cov_upload(src.be.cov())
 
 
-@pytest.mark.parametrize("frames,max_clones", [(120, 11), (300, 30)])
-def test_vio_loop_per_frame_parity(frames, max_clones, chi2_table):
-    g, o, lg, lo = _pair(max_clones, chi2_table, seed=3)
+@pytest.mark.parametrize("frames,max_clones,fit_planes", [(120, 11, False), (300, 30, False), (140, 30, True)])
+def test_vio_loop_per_frame_parity(frames, max_clones, fit_planes, chi2_table):
+    """fit_planes: plane hypotheses and refined positions come from ovp_plane_fitting / ovp_optimize_plane inside the loop"""
+    g, o, lg, lo = _pair(max_clones, chi2_table, seed=3, fit_planes=fit_planes)
     worst_v = worst_P = 0.0
     nupd = ninit = 0
     for k in range(1, frames + 1):
@@ -71,6 +72,9 @@ def test_vio_loop_per_frame_parity(frames, max_clones, chi2_table):
         worst_v, worst_P = max(worst_v, dv), max(worst_P, dP)
         assert dv < 1e-6 and dP < 1e-6, (t, dv, dP)
         _copy_state(lo, lg)
+    if fit_planes:
+        assert lg.fit_stats == lo.fit_stats and lo.fit_stats["ransac_ok"] >= 1 and lo.fit_stats["refine_ok"] >= 1, (lg.fit_stats, lo.fit_stats)
+        print("plane fitting in the loop (identical on both sides):", lo.fit_stats)
     print("cfg4 per-frame parity: %d frames, window %d, N %d, %d feature updates, %d plane initialisations | worst single-frame IMU state rel diff "
           "%.2e, covariance rel diff %.2e | gates identical in every frame" % (frames, max_clones, lo.frames[-1]["N"], nupd, ninit, worst_v, worst_P))
     g.close()

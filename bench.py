@@ -461,6 +461,7 @@ def main():
                             "frames": len(fr4), "state_N": int(fr4[-1]["N"]), "ms_per_frame_estimator": float(1e3 * est.mean()),
                             "ms_per_frame_estimator_p95": float(1e3 * np.percentile(est, 95)), "frames_per_s": float(1.0 / est.mean()),
                             "stage_ms": {k: float(1e3 * np.mean([r[k] for r in fr4])) for k in ("propagation", "plane_init", "msckf", "marg")},
+                            "front_end_ms_python": float(1e3 * np.mean([r["front_end"] for r in fr4])),
                             "nees_ori": float(np.mean([r["nees_ori"] for r in fr4])), "nees_pos": float(np.mean([r["nees_pos"] for r in fr4])),
                             "final_err_deg_m": [float(fr4[-1]["err_ori_deg"]), float(fr4[-1]["err_pos"])],
                             "note": "wall clock of the estimator calls through the C ABI (the reference's timing-CSV columns, VioManager.cpp:911-928); "
@@ -474,6 +475,7 @@ def main():
         try:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import planefit_cases
+            ctx.restore()  # the clone poses the refinement problem was generated against
             fo8, pts8 = planefit_cases.plane_point_sets(S, seed=0)
             pr8 = planefit_cases.refine_problem(S, ch, seed=0, consistent=True, noise=0.006)
             fx8 = np.zeros(len(pr8["feat_offset"]) - 1, dtype=np.int32)

@@ -74,7 +74,7 @@ static void register_new(Ctx *c, int h, int kind, int64_t tag) {
 
 // StateHelper::initialize_invertible on device-staged operands (W = [H_L | H_R | res], top s rows), StateHelper.cpp:489-586
 static int init_invertible_core(Ctx *c, int kind, int s, const double *value, const double *fej, int64_t tag, const int *d_cols, int n,
-                                const double *W, int ldW, double sigma2, int *new_handle) {
+                                const double *W, int ldW, double sigma2, int *new_handle, bool hl_is_upper = true) {
   const int N = c->N;
   if (N + s > c->Nmax)
     return fail(c, OVP_ERR_CAPACITY, "state capacity %d exceeded", c->Nmax);
@@ -97,9 +97,10 @@ static int init_invertible_core(Ctx *c, int kind, int s, const double *value, co
   OVP_CUDA(cudaMemcpyAsync(hres, W + (size_t)(s + n) * ldW, s * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   OVP_CUDA(cudaStreamSynchronize(c->stream));
   (void)hW;
-  for (int j = 0; j < s; j++)
-    for (int i = j + 1; i < s; i++)
-      hHL[j * s + i] = 0.0; // below-diagonal entries were annihilated by the reflectors
+  if (hl_is_upper) // called from initialize(): the reflectors annihilated the below-diagonal entries (the storage holds reflector data there);
+    for (int j = 0; j < s; j++) // a direct ovp_initialize_invertible call hands over a general square H_L (StateHelper.cpp:564)
+      for (int i = j + 1; i < s; i++)
+        hHL[j * s + i] = 0.0;
   double Hinv[9];
   if (small_inverse(hHL, s, Hinv))
     return fail(c, OVP_ERR_BAD_ARGS, "initialize: H_L is singular");
@@ -291,7 +292,7 @@ int ovp_initialize_invertible(ovp_ctx *h, int kind, int s, const double *value, 
   st = stage_init_system(c, H_R, H_L, res, s, n, s, &W);
   if (st)
     return st;
-  return init_invertible_core(c, kind, s, value, fej, tag, c->dcols, n, W, s, sigma2, new_handle);
+  return init_invertible_core(c, kind, s, value, fej, tag, c->dcols, n, W, s, sigma2, new_handle, false);
 }
 
 } // extern "C"
@@ -856,7 +857,7 @@ int ovp_msckf_update_gathered(ovp_ctx *h, const double *d_blocks, int G, const i
   st = chol_partial(c, c->wsG.S, c->wsG.cap, nc1, n, c->gram_tol);
   if (st)
     return st;
-  st = ekf_update_core(c, c->dcols, n, mv(c->wsG.S, c->wsG.cap), n, c->wsG.S + (nc1 - 1), nullptr, -1.0, nullptr, nullptr, true, c->wsG.cap);
+  st = ekf_update_core(c, c->dcols, n, mv(c->wsG.S, c->wsG.cap), n, c->wsG.S + (nc1 - 1), nullptr, -1.0, nullptr, nullptr, true, c->wsG.cap, false, true);
   if (st)
     return st;
   return check_status_flags(c);

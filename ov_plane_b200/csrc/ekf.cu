@@ -256,7 +256,7 @@ int join_side_stream(Ctx *c) {
 }
 
 int ekf_update_core(Ctx *c, const int *d_cols, int nc, MatView HT, int rr, const double *d_z, const double *d_Rdiag, double gate_thresh,
-                    int *d_gate_flag, double *d_chi2, bool apply, int zstride, bool defer_join) {
+                    int *d_gate_flag, double *d_chi2, bool apply, int zstride, bool defer_join, bool ht_lower) {
   if (rr <= 0 || nc <= 0)
     return OVP_OK;
   {
@@ -275,6 +275,7 @@ int ekf_update_core(Ctx *c, const int *d_cols, int nc, MatView HT, int rr, const
   // 1. M = P[:, cols] * HT        (N x rr)
   {
     GemmProblem p = make_problem(N, rr, nc, mv(c->dP, c->ldP, 0, nullptr, d_cols), HT, c->dM, c->Nmax);
+    p.ktri = ht_lower ? 1 : 0; // H^T = L (the compression's Cholesky factor): column j is zero above row j
     launch_gemm1(c, p);
   }
   // 2. S = HT^T * M[cols, :] + R  (lower part)
@@ -285,6 +286,7 @@ int ekf_update_core(Ctx *c, const int *d_cols, int nc, MatView HT, int rr, const
     p.diag_add = d_Rdiag;
     p.diag_const = 1.0;
     p.tri = TRI_LOWER;
+    p.ktri = ht_lower ? 2 : 0; // row i of H = L^T is zero left of column i
     launch_gemm1(c, p);
   }
   double *d_w = c->dvec; // [0, Rcap)

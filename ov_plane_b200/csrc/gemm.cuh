@@ -79,6 +79,9 @@ struct GemmProblem {
   int tri;     // TRI_*: LOWER computes tiles with tile_row >= tile_col only; MIRROR additionally writes C(j,i)
   int a_kfast; // 1: A is contiguous along k in memory (tile loader walks k fastest)
   int b_kfast;
+  int ktri;    // structural zeros along k: 1 = B(k, j) == 0 for k < j (B lower trapezoidal: a Cholesky factor used as H^T), 2 = A(i, k) == 0
+               // for k < i (its transpose on the left).  A tile starts its k loop at its own first column / row instead of 0: the skipped
+               // products are exact zeros, so the result is bit-identical and M = P[:, ids] L, S = L^T M[ids, :] cost half / a third.
 };
 #define OVP_GEMM_MAX_BATCH 8
 struct GemmBatch {
@@ -166,8 +169,9 @@ template <int TILE, bool GA, bool GB> __global__ void __launch_bounds__(128) gem
     for (int j = 0; j < NM; j++)
       acc[i][j][0] = acc[i][j][1] = 0.0;
   double ra[TILE / 8], rb[TILE / 8];
-  load_tile_regs<TILE, GA>(ra, va, m0, M, 0, K, akf, tid);
-  load_tile_regs<TILE, GB>(rb, vb, n0, N, 0, K, bkf, tid);
+  const int kbeg = (pb.ktri == 1) ? (n0 & ~(OVP_GK - 1)) : ((pb.ktri == 2) ? (m0 & ~(OVP_GK - 1)) : 0);
+  load_tile_regs<TILE, GA>(ra, va, m0, M, kbeg, K, akf, tid);
+  load_tile_regs<TILE, GB>(rb, vb, n0, N, kbeg, K, bkf, tid);
   // epilogue operands that do not depend on the product are fetched now, off the critical path
   const double alpha = pb.alpha, beta = pb.beta;
   double *Cp = pb.C;
@@ -185,7 +189,7 @@ template <int TILE, bool GA, bool GB> __global__ void __launch_bounds__(128) gem
         cin[i][j][h] = (beta != 0.0 && gi < M && gj < N) ? Cp[(size_t)gj * ldc + gi] : 0.0;
       }
   }
-  for (int k0 = 0; k0 < K; k0 += OVP_GK) {
+  for (int k0 = kbeg; k0 < K; k0 += OVP_GK) {
     store_tile_smem<TILE>(ra, As, akf, tid);
     store_tile_smem<TILE>(rb, Bs, bkf, tid);
     __syncthreads();
@@ -290,6 +294,7 @@ inline GemmProblem make_problem(int M, int N, int K, MatView A, MatView B, doubl
   p.diag_add = nullptr;
   p.diag_const = 0.0;
   p.tri = TRI_FULL;
+  p.ktri = 0;
   // loader walk: along whichever logical direction is contiguous in memory
   p.a_kfast = (p.A.sk == 1) ? 1 : 0;
   p.b_kfast = (p.B.sk == 1) ? 1 : 0;

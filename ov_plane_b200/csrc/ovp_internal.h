@@ -176,9 +176,10 @@ void launch_fill(Ctx *c, double *p, size_t n, double v);
 // ---- ekf.cu ------------------------------------------------------------------------------------------------------
 // Generic EKF update core.  HT: nc x rr (column-major, ld ldHT) = H^T in the column order given by d_cols (device array of
 // nc state indices).  z: rr.  Rdiag: rr or nullptr (identity).  If gate_thresh >= 0, chi2 = z^T S^-1 z is compared with
-// it on the device and the update is skipped when larger (flag written to d_gate_flag, chi2 to d_chi2).
+// it on the device and the update is skipped when larger (flag written to d_gate_flag, chi2 to d_chi2).  ht_lower: HT(k, j) == 0 for k < j
+// (HT is the lower Cholesky factor of the compression) - the two products skip the structural zeros.
 int ekf_update_core(Ctx *c, const int *d_cols, int nc, MatView HT, int rr, const double *d_z, const double *d_Rdiag, double gate_thresh,
-                    int *d_gate_flag, double *d_chi2, bool apply = true, int zstride = 1, bool defer_join = false);
+                    int *d_gate_flag, double *d_chi2, bool apply = true, int zstride = 1, bool defer_join = false, bool ht_lower = false);
 int join_side_stream(Ctx *c); // make the main stream wait for the side stream's covariance downdate (no-op when nothing is pending)
 int upload_var_table(Ctx *c);
 int sync_host_values(Ctx *c);

@@ -94,7 +94,7 @@ static void pf_shuffle(int *v, int n, Mt19937 &g, int kind) { // libstdc++ std::
 
 #define PF_HYP 200            // max_iter_num (PlaneFitting.cpp:88)
 #define PF_SET 5              // ransac_solver_feat_num (:87)
-#define PF_MAX_POINTS 2000    // points of one candidate plane (shared-memory staging: 24 bytes each)
+#define PF_MAX_POINTS 1900    // points of one candidate plane (shared-memory staging: 24 bytes each + the warps' work rows <= 48 KB)
 #define PF_WARPS 8
 
 struct PfHyp { // result of one draw

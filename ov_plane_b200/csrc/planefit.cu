@@ -8,7 +8,7 @@
 //     picks the winner exactly like the sequential loop (more inliers, then smaller mean error, then the earlier draw) and refits it.
 //   ovp_optimize_plane  = PlaneFitting::optimize_plane (:197-514).  The reference hands the problem to Ceres (DENSE_SCHUR + DOGLEG, Cauchy loss,
 //     12 iterations).  Ceres is not part of the reference tree (libceres-dev 1.14, package.xml:47); the algorithm of its TrustRegionMinimizer +
-//     DoglegStrategy is restated here as ONE kernel launch per batch of planes: a CTA per plane, a thread per feature.  Every free feature is a
+//     DoglegStrategy is restated here as ONE kernel launch per batch of planes: a CTA per plane; the residual / Jacobian pass runs a warp per feature (lane = measurement), the 3 x 3 algebra a thread per feature.  Every free feature is a
 //     3 x 3 block that only couples to the 3 plane parameters, so the whole iteration (Jacobi scaling, gradient, Cauchy point, regularised
 //     Gauss-Newton step through the Schur complement on the plane, dogleg interpolation, model / true cost change, radius and mu updates,
 //     the three convergence tests) runs on per-feature normal-equation blocks plus a handful of block reductions - no Jacobian rows are stored,
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(32) plane_ransac_select_kernel(const int *feat
 }
 
 // ---- optimize_plane: restated Ceres dogleg on per-feature normal blocks -----------------------------------------------------------------
-#define PO_THREADS 128
+#define PO_THREADS 256
 #define PO_FIELDS 42 // per-feature scratch doubles: x 3, cand 3, Uu 6, Wu 9, bu 3, sc 3, D 3, g 3, gn 3, st 3 + 3 spare
 enum { PO_X = 0, PO_CAND = 3, PO_U = 6, PO_W = 12, PO_B = 21, PO_SC = 24, PO_D = 27, PO_G = 30, PO_GN = 33, PO_ST = 36 };
 
@@ -426,39 +426,57 @@ struct PoArgs {
   int *inlier, *status;
 };
 
-// cost contribution and (optionally) the UNSCALED normal-equation blocks of one feature at position p with plane cp (n, d precomputed).
+// Cost contribution and (optionally) the UNSCALED normal-equation blocks of one feature at position p with plane cp (n, d precomputed), computed
+// by ONE WARP: lane = measurement (strided when a track is longer than 32), per-lane partial sums combined by an xor butterfly (every lane ends
+// with the same bits), the point-on-plane block evaluated redundantly by every lane.  Outputs are SET, not accumulated, and identical in all
+// lanes: U (6, packed lower), W (9), bf (3): feature blocks; Vf (6), bcf (3): this feature's share of the plane block.
 // Loss: Cauchy a = 1 on every residual block (PlaneFitting.cpp:252,363): rho = log(1 + s); corrector.cc with rho'' <= 0: residual and
 // Jacobian are scaled by sqrt(rho') = 1 / sqrt(1 + s).
-__device__ double po_feature(const PoArgs &A, int fg, const double *p, const double *nrm, double d, bool cp_free, bool feat_free, bool want,
-                             double *U, double *W, double *bf, double *V, double *bc) {
+__device__ double po_feature_warp(const PoArgs &A, int fg, const double *p, const double *nrm, double d, bool cp_free, bool feat_free, bool want,
+                                  double *U, double *W, double *bf, double *Vf, double *bcf) {
+  const int lane = threadIdx.x & 31;
   const int m0 = A.meas_offset[fg], m = A.meas_offset[fg + 1] - m0;
-  double cost = 0.0;
-  if (m > 0) {
-    const double w = 1.0 / A.sigma_px_norm;
-    for (int k = 0; k < m; k++) {
-      const int hc = A.meas_clone[m0 + k];
-      const double *R = A.Rc + 9 * (size_t)hc, *pc = A.pc + 3 * (size_t)hc;
-      const double dx = p[0] - pc[0], dy = p[1] - pc[1], dz = p[2] - pc[2];
-      const double X = R[0] * dx + R[1] * dy + R[2] * dz, Y = R[3] * dx + R[4] * dy + R[5] * dz, Z = R[6] * dx + R[7] * dy + R[8] * dz;
-      const double r0 = w * (X / Z - (double)A.uvn[2 * (size_t)(m0 + k)]), r1 = w * (Y / Z - (double)A.uvn[2 * (size_t)(m0 + k) + 1]);
-      const double s = r0 * r0 + r1 * r1;
-      cost += 0.5 * log(1.0 + s);
-      if (want) {
-        const double rho1 = fmax(DBL_MIN, 1.0 / (1.0 + s)), sc = sqrt(rho1) * w;
-        const double iz = 1.0 / Z, xz = -X / (Z * Z), yz = -Y / (Z * Z);
-        double J0[3], J1[3];
-        for (int i = 0; i < 3; i++) {
-          J0[i] = sc * (iz * R[i] + xz * R[6 + i]);
-          J1[i] = sc * (iz * R[3 + i] + yz * R[6 + i]);
-        }
-        const double q0 = sqrt(rho1) * r0, q1 = sqrt(rho1) * r1;
-        for (int i = 0; i < 3; i++) {
-          for (int j = 0; j <= i; j++)
-            U[i * (i + 1) / 2 + j] += J0[i] * J0[j] + J1[i] * J1[j];
-          bf[i] += J0[i] * q0 + J1[i] * q1;
-        }
+  double part[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // cost, U (6), bf (3) of this lane's measurements
+  const double w = 1.0 / A.sigma_px_norm;
+  for (int k = lane; k < m; k += 32) {
+    const int hc = A.meas_clone[m0 + k];
+    const double *R = A.Rc + 9 * (size_t)hc, *pc = A.pc + 3 * (size_t)hc;
+    const double dx = p[0] - pc[0], dy = p[1] - pc[1], dz = p[2] - pc[2];
+    const double X = R[0] * dx + R[1] * dy + R[2] * dz, Y = R[3] * dx + R[4] * dy + R[5] * dz, Z = R[6] * dx + R[7] * dy + R[8] * dz;
+    const double r0 = w * (X / Z - (double)A.uvn[2 * (size_t)(m0 + k)]), r1 = w * (Y / Z - (double)A.uvn[2 * (size_t)(m0 + k) + 1]);
+    const double s = r0 * r0 + r1 * r1;
+    part[0] += 0.5 * log(1.0 + s);
+    if (want) {
+      const double rho1 = fmax(DBL_MIN, 1.0 / (1.0 + s)), sq = sqrt(rho1), sc = sq * w;
+      const double iz = 1.0 / Z, xz = -X / (Z * Z), yz = -Y / (Z * Z);
+      double J0[3], J1[3];
+      for (int i = 0; i < 3; i++) {
+        J0[i] = sc * (iz * R[i] + xz * R[6 + i]);
+        J1[i] = sc * (iz * R[3 + i] + yz * R[6 + i]);
+      }
+      const double q0 = sq * r0, q1 = sq * r1;
+      for (int i = 0; i < 3; i++) {
+        for (int j = 0; j <= i; j++)
+          part[1 + i * (i + 1) / 2 + j] += J0[i] * J0[j] + J1[i] * J1[j];
+        part[7 + i] += J0[i] * q0 + J1[i] * q1;
       }
     }
+  }
+  const int nred = want ? 10 : 1;
+  for (int k = 0; k < nred; k++)
+    part[k] = pf_warp_sum(part[k]);
+  double cost = part[0];
+  if (want) {
+    for (int i = 0; i < 6; i++)
+      U[i] = part[1 + i];
+    for (int i = 0; i < 3; i++)
+      bf[i] = part[7 + i];
+    for (int i = 0; i < 9; i++)
+      W[i] = 0.0;
+    for (int i = 0; i < 6; i++)
+      Vf[i] = 0.0;
+    for (int i = 0; i < 3; i++)
+      bcf[i] = 0.0;
   }
   // point-on-plane block (Factor_PointOnPlane.cpp:39-70): m identical copies for a measured feature (:367-369), one inflated copy for a
   // constant (SLAM) feature (:274-277) - and none at all when neither the feature nor the plane is free (Ceres drops constant blocks)
@@ -483,8 +501,8 @@ __device__ double po_feature(const PoArgs &A, int fg, const double *p, const dou
       }
       if (cp_free) {
         for (int j = 0; j <= i; j++)
-          V[i * (i + 1) / 2 + j] += mult * Jc[i] * Jc[j];
-        bc[i] += mult * Jc[i] * q;
+          Vf[i * (i + 1) / 2 + j] += mult * Jc[i] * Jc[j];
+        bcf[i] += mult * Jc[i] * q;
         if (feat_free)
           for (int j = 0; j < 3; j++)
             W[3 * i + j] += mult * Jp[i] * Jc[j];
@@ -534,26 +552,36 @@ __global__ void __launch_bounds__(PO_THREADS) optimize_plane_kernel(PoArgs A) {
   double x_cost = 0.0, initial_cost = 0.0, gmax = 0.0, x_norm = 0.0;
   double Vu[6], bcu[3], scc[3] = {0, 0, 0}, Dc[3] = {1, 1, 1}, gc[3] = {0, 0, 0}, gnc[3] = {0, 0, 0}, stc[3] = {0, 0, 0};
 
-  // evaluation with Jacobian at (x, cp): per-feature blocks to scratch, plane blocks + cost + gradient max norm + |x| reduced
+  // evaluation with Jacobian at (x, cp): a warp per feature (lane = measurement); per-feature blocks to scratch, plane blocks + cost + gradient
+  // max norm + |x| reduced over the block.  The other phases of an iteration are 3 x 3 algebra per feature and stay one thread per feature:
+  // the two mappings meet in the scratch arrays, with a block barrier in between.
+  const int lane = tid & 31, warp = tid >> 5, nwarps = PO_THREADS / 32;
   auto evaluate_full = [&]() {
     const double d = sqrt(cp[0] * cp[0] + cp[1] * cp[1] + cp[2] * cp[2]);
     const double nrm[3] = {cp[0] / d, cp[1] / d, cp[2] / d};
-    double acc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // cost, V(6), bc(3), |x|^2
+    double acc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // cost, V(6), bc(3), |x|^2   (lane 0 of every warp accumulates)
     double gm = 0.0;
-    for (int f = tid; f < F; f += PO_THREADS) {
+    __syncthreads();
+    for (int f = warp; f < F; f += nwarps) {
       const bool ff = A.meas_offset[f0 + f + 1] > A.meas_offset[f0 + f];
-      double p[3] = {FLD(PO_X, f, 0), FLD(PO_X, f, 1), FLD(PO_X, f, 2)};
-      double U[6] = {0, 0, 0, 0, 0, 0}, W[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, bf[3] = {0, 0, 0};
-      acc[0] += po_feature(A, f0 + f, p, nrm, d, cp_free, ff, true, U, W, bf, acc + 1, acc + 7);
-      for (int i = 0; i < 6; i++)
-        FLD(PO_U, f, i) = U[i];
-      for (int i = 0; i < 9; i++)
-        FLD(PO_W, f, i) = W[i];
-      for (int i = 0; i < 3; i++) {
-        FLD(PO_B, f, i) = bf[i];
-        if (ff) {
-          gm = fmax(gm, fabs(bf[i]));
-          acc[10] += p[i] * p[i];
+      const double p[3] = {FLD(PO_X, f, 0), FLD(PO_X, f, 1), FLD(PO_X, f, 2)};
+      double U[6], W[9], bf[3], Vf[6], bcf[3];
+      const double cf = po_feature_warp(A, f0 + f, p, nrm, d, cp_free, ff, true, U, W, bf, Vf, bcf);
+      if (lane == 0) {
+        acc[0] += cf;
+        for (int i = 0; i < 6; i++) {
+          FLD(PO_U, f, i) = U[i];
+          acc[1 + i] += Vf[i];
+        }
+        for (int i = 0; i < 9; i++)
+          FLD(PO_W, f, i) = W[i];
+        for (int i = 0; i < 3; i++) {
+          FLD(PO_B, f, i) = bf[i];
+          acc[7 + i] += bcf[i];
+          if (ff) {
+            gm = fmax(gm, fabs(bf[i]));
+            acc[10] += p[i] * p[i];
+          }
         }
       }
     }
@@ -867,10 +895,13 @@ __global__ void __launch_bounds__(PO_THREADS) optimize_plane_kernel(PoArgs A) {
       {
         const double d = sqrt(ccp[0] * ccp[0] + ccp[1] * ccp[1] + ccp[2] * ccp[2]);
         const double nrm[3] = {ccp[0] / d, ccp[1] / d, ccp[2] / d};
-        for (int f = tid; f < F; f += PO_THREADS) {
+        __syncthreads(); // the candidate positions were written one thread per feature
+        for (int f = warp; f < F; f += nwarps) {
           const bool ff = A.meas_offset[f0 + f + 1] > A.meas_offset[f0 + f];
           const double p[3] = {FLD(PO_CAND, f, 0), FLD(PO_CAND, f, 1), FLD(PO_CAND, f, 2)};
-          cc[0] += po_feature(A, f0 + f, p, nrm, d, cp_free, ff, false, nullptr, nullptr, nullptr, nullptr, nullptr);
+          const double cf = po_feature_warp(A, f0 + f, p, nrm, d, cp_free, ff, false, nullptr, nullptr, nullptr, nullptr, nullptr);
+          if (lane == 0)
+            cc[0] += cf;
         }
       }
       po_block_sum<1>(cc, red);

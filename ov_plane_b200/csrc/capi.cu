@@ -225,6 +225,10 @@ static int do_marginalize(Ctx *c, int h) {
   if (!valid_handle(c, h) || c->vars[h].id < 0)
     return fail(c, OVP_ERR_NOT_IN_STATE, "marginalize: variable %d not in the state (reference: std::exit, StateHelper.cpp:279-283)", h);
   Var &v = c->vars[h];
+  if (v.kind == OVP_KIND_POSE) // a clone that still anchors a landmark: the reference asserts change_anchors ran first (UpdaterSLAM.cpp:699)
+    for (auto &kv : c->slam)
+      if (c->vars[kv.second].id >= 0 && c->vars[kv.second].rep >= 2 && c->vars[kv.second].anchor == h)
+        return fail(c, OVP_ERR_BAD_ARGS, "marginalize: clone %d is the anchor of landmark %lld - call ovp_slam_change_anchors first", h, (long long)kv.first);
   int mid = v.id, ms = v.size, N = c->N;
   // compaction into the scratch covariance, then swap (StateHelper.cpp:302-318)
   double *dst = c->dM; // Nmax x Rcap >= Nmax x Nmax scratch

@@ -981,21 +981,27 @@ __global__ void __launch_bounds__(PO_THREADS) optimize_plane_kernel(PoArgs A) {
 
 static std::map<long long, std::vector<int>> g_perm_cache; // (shuffle_kind, F) -> 200 x F draws; depends on nothing else
 static std::mutex g_perm_mutex;
-static const std::vector<int> &pf_permutations(int F, int kind) {
+// copies the 200 draws for F points into dst (200 x F ints); generated once per (kind, F) and kept, under the lock
+static void pf_permutations_copy(int F, int kind, int *dst) {
+  if (F <= 0)
+    return;
   std::lock_guard<std::mutex> lock(g_perm_mutex);
   const long long key = ((long long)kind << 32) | (unsigned)F;
   auto it = g_perm_cache.find(key);
-  if (it != g_perm_cache.end())
-    return it->second;
-  std::vector<int> out((size_t)PF_HYP * F);
-  Mt19937 g(8888u); // std::mt19937 rand_gen(8888), PlaneFitting.cpp:93
-  for (int h = 0; h < PF_HYP; h++) {
-    int *v = out.data() + (size_t)h * F;
-    for (int i = 0; i < F; i++)
-      v[i] = i;
-    pf_shuffle(v, F, g, kind);
+  if (it == g_perm_cache.end()) {
+    if (g_perm_cache.size() >= 64) // a tracker sees a handful of sizes per frame; bound the table anyway
+      g_perm_cache.clear();
+    std::vector<int> out((size_t)PF_HYP * F);
+    Mt19937 g(8888u); // std::mt19937 rand_gen(8888), PlaneFitting.cpp:93
+    for (int h = 0; h < PF_HYP; h++) {
+      int *v = out.data() + (size_t)h * F;
+      for (int i = 0; i < F; i++)
+        v[i] = i;
+      pf_shuffle(v, F, g, kind);
+    }
+    it = g_perm_cache.emplace(key, std::move(out)).first;
   }
-  return g_perm_cache.emplace(key, std::move(out)).first->second;
+  std::memcpy(dst, it->second.data(), it->second.size() * sizeof(int));
 }
 
 } // namespace ovp
@@ -1062,11 +1068,8 @@ int ovp_plane_fitting(ovp_ctx *h, int n_planes, const int *feat_offset, const do
   std::vector<char> hbuf(b_in_end);
   std::memcpy(hbuf.data() + b_fo, feat_offset, (size_t)(n_planes + 1) * 4);
   std::memcpy(hbuf.data() + b_po, h_perm_off.data(), (size_t)n_planes * 4);
-  for (auto &kv : perm_off) {
-    const std::vector<int> &pm = pf_permutations(kv.first, opt->shuffle_kind);
-    if (!pm.empty())
-      std::memcpy(hbuf.data() + b_pm + (size_t)kv.second * 4, pm.data(), pm.size() * 4);
-  }
+  for (auto &kv : perm_off)
+    pf_permutations_copy(kv.first, opt->shuffle_kind, (int *)(hbuf.data() + b_pm + (size_t)kv.second * 4));
   std::memcpy(hbuf.data() + b_pt, p_FinG, (size_t)Ftot * 24);
   char *d = (char *)c->d_stage;
   OVP_CUDA(cudaMemcpyAsync(d, hbuf.data(), b_in_end, cudaMemcpyHostToDevice, c->stream));

@@ -139,6 +139,9 @@ __device__ __forceinline__ void store_tile_smem(const double (&r)[TILE / 8], dou
 // (Round 2, measured and not kept: gather indices of the tile's k range in shared memory + a second register stage (loads two k-steps ahead):
 // ncu attributes 40 % of the gathered products' stall samples to the long scoreboard of the prefetch (index load, then element load), yet the
 // variant measured 0.703 vs 0.685 ms per step for the 27 products and 22.8 vs 24.7 TFLOP/s on the 2048^3 self-test (240 registers on the 64-tile).)
+// (Round 2, measured and not kept: per-thread tile map hoisted out of the k loop and pinned (row pointers, shared-memory slots), all loads of a
+// k-step unconditional with clamped indices: 350 -> 210 SASS instructions per k-step, no branch regions, 126 registers - and 1.03 instead of
+// 0.675 ms per step for the 27 products.  The loop is not bound by its instruction count.)
 // (Round 2, measured and not kept: a 4-stage cp.async operand pipeline instead of the register prefetch of the next k-step - 0.72 vs 0.71 ms
 // per step for the 27 products.  The k-step is bound by the FP64 pipe, not by the loads: 16 DMMAs per warp x ~17 cycles of issue each per
 // sub-partition; 240 tiles of 32 x 32 on 148 SMs are 2 rounds of 30 k-steps = 17 K cycles against 13 K at perfect balance.)

@@ -65,6 +65,9 @@ def test_anchor_change_matches_the_oracle(rep, do_fej, chi2_table):
     print("rep %d do_fej %d: cov rel err after perform_anchor_change %.2e, after change_anchors %.2e, landmark value / fej max diff %.2e" % (
         rep, do_fej, e1, e2, dv))
     assert e1 < 1e-9 and e2 < 1e-9 and dv < 1e-10
+    # a clone that still anchors a landmark cannot be marginalised (the reference asserts change_anchors ran first, UpdaterSLAM.cpp:699)
+    with pytest.raises(api.OvpError):
+        ctx.marginalize(chg[-1])
     # the fused GLOBAL_3D update path refuses the anchored landmark instead of misreading its value
     with pytest.raises(api.OvpError):
         ctx.slam_update(dict(F=1, meas_offset=np.array([0, 2], dtype=np.int32), meas_clone=np.array(chg[:2], dtype=np.int32),

@@ -76,6 +76,17 @@ def test_optimize_plane_edge_cases(chi2_table):
     so, po, co, io, no = orc.optimize_plane(*args)
     assert (sg == 1).all() and np.array_equal(sg, so) and np.array_equal(ng[:, 1], no[:, 1]) and ig.all()
     assert np.abs(cg - co).max() < 1e-8 and (ng[:, 3] < 1e-6).all()
+    # tracks longer than a warp (every measurement listed twice: 40 per feature): the residual pass strides the lanes over the measurements
+    mo2 = (2 * pr["meas_offset"]).astype(np.int32)
+    mc2 = np.concatenate([np.tile(pr["meas_clone"][a:b], 2) for a, b in zip(pr["meas_offset"][:-1], pr["meas_offset"][1:])]).astype(np.int32)
+    uv2 = np.concatenate([np.tile(pr["uv_norm"][a:b], (2, 1)) for a, b in zip(pr["meas_offset"][:-1], pr["meas_offset"][1:])]).astype(np.float32)
+    noisy = pr["p_FinG"] + 0.004 * np.random.RandomState(3).randn(*pr["p_FinG"].shape)
+    a3 = (pr["feat_offset"], mo2, mc2, uv2, noisy, pr["cp_inG"], fx, 1.0 / 458.0, 0.01)
+    sg, pg, cg, ig, ng = ctx.optimize_plane(*a3)
+    so, po, co, io, no = orc.optimize_plane(*a3)
+    assert int(np.diff(mo2).max()) > 32
+    assert np.array_equal(sg, so) and np.array_equal(ig, io) and np.array_equal(ng[:, 1], no[:, 1]) and np.array_equal(ng[:, 4], no[:, 4])
+    assert np.abs(pg - po).max() < 1e-7 and np.abs(cg - co).max() < 1e-7
     # one SLAM-only feature against a fixed plane (UpdaterSLAM.cpp:171 style), three features with a free plane (refused), an empty candidate
     fo = np.array([0, 1, 4, 4], dtype=np.int32)
     mo = np.concatenate([[0, 0], pr["meas_offset"][1:4]]).astype(np.int32)

@@ -1031,6 +1031,8 @@ int ovp_plane_fitting(ovp_ctx *h, int n_planes, const int *feat_offset, const do
     return fail(c, OVP_ERR_BAD_ARGS, "plane_fitting: null argument");
   if (opt->shuffle_kind != 0 && opt->shuffle_kind != 1)
     return fail(c, OVP_ERR_BAD_ARGS, "plane_fitting: shuffle_kind %d (0 = libstdc++ GCC <= 10, 1 = GCC >= 11)", opt->shuffle_kind);
+  if (feat_offset[0] != 0)
+    return fail(c, OVP_ERR_BAD_ARGS, "plane_fitting: feat_offset must start at 0");
   const int Ftot = feat_offset[n_planes];
   int Fmax = 0;
   std::map<int, int> perm_off; // F -> offset (ints) into the permutation block of this call
@@ -1098,7 +1100,16 @@ int ovp_optimize_plane(ovp_ctx *h, int n_planes, const int *feat_offset, const i
     return OVP_OK;
   if (!feat_offset || !meas_offset || !p_FinG || !cp_inG || !fix_plane || !opt || !p_FinG_out || !cp_out || !inlier || !status)
     return fail(c, OVP_ERR_BAD_ARGS, "optimize_plane: null argument");
-  const int Ftot = feat_offset[n_planes], M = (Ftot > 0) ? meas_offset[Ftot] : 0;
+  if (feat_offset[0] != 0 || meas_offset[0] != 0)
+    return fail(c, OVP_ERR_BAD_ARGS, "optimize_plane: offset arrays must start at 0");
+  for (int p = 0; p < n_planes; p++)
+    if (feat_offset[p + 1] < feat_offset[p])
+      return fail(c, OVP_ERR_BAD_ARGS, "optimize_plane: feat_offset is not non-decreasing at plane %d", p);
+  const int Ftot = feat_offset[n_planes];
+  for (int f = 0; f < Ftot; f++)
+    if (meas_offset[f + 1] < meas_offset[f])
+      return fail(c, OVP_ERR_BAD_ARGS, "optimize_plane: meas_offset is not non-decreasing at feature %d", f);
+  const int M = (Ftot > 0) ? meas_offset[Ftot] : 0;
   if (M > 0 && (!meas_clone || !uv_norm))
     return fail(c, OVP_ERR_BAD_ARGS, "optimize_plane: null measurement arrays");
   if (!(opt->sigma_px_norm > 0.0) || !(opt->sigma_c > 0.0))

@@ -76,10 +76,10 @@ def test_optimize_plane_edge_cases(chi2_table):
     so, po, co, io, no = orc.optimize_plane(*args)
     assert (sg == 1).all() and np.array_equal(sg, so) and np.array_equal(ng[:, 1], no[:, 1]) and ig.all()
     assert np.abs(cg - co).max() < 1e-8 and (ng[:, 3] < 1e-6).all()
-    # tracks longer than a warp (every measurement listed twice: 40 per feature): the residual pass strides the lanes over the measurements
-    mo2 = (2 * pr["meas_offset"]).astype(np.int32)
-    mc2 = np.concatenate([np.tile(pr["meas_clone"][a:b], 2) for a, b in zip(pr["meas_offset"][:-1], pr["meas_offset"][1:])]).astype(np.int32)
-    uv2 = np.concatenate([np.tile(pr["uv_norm"][a:b], (2, 1)) for a, b in zip(pr["meas_offset"][:-1], pr["meas_offset"][1:])]).astype(np.float32)
+    # tracks longer than a warp (every measurement listed three times: up to 36 per feature): the residual pass strides the lanes over the measurements
+    mo2 = (3 * pr["meas_offset"]).astype(np.int32)
+    mc2 = np.concatenate([np.tile(pr["meas_clone"][a:b], 3) for a, b in zip(pr["meas_offset"][:-1], pr["meas_offset"][1:])]).astype(np.int32)
+    uv2 = np.concatenate([np.tile(pr["uv_norm"][a:b], (3, 1)) for a, b in zip(pr["meas_offset"][:-1], pr["meas_offset"][1:])]).astype(np.float32)
     noisy = pr["p_FinG"] + 0.004 * np.random.RandomState(3).randn(*pr["p_FinG"].shape)
     a3 = (pr["feat_offset"], mo2, mc2, uv2, noisy, pr["cp_inG"], fx, 1.0 / 458.0, 0.01)
     sg, pg, cg, ig, ng = ctx.optimize_plane(*a3)

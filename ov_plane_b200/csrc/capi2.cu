@@ -1495,7 +1495,7 @@ extern "C" int ovp_triangulate_features(ovp_ctx *h, int F, const int *meas_offse
   const int M = meas_offset[F];
   for (int k = 0; k < M; k++) {
     const int hh = meas_clone[k];
-    if (hh < 0 || hh >= (int)c->vars.size() || !c->vars[hh].alive || c->vars[hh].kind != OVP_KIND_POSE || c->vars[hh].id < 0)
+    if (hh < 0 || hh >= (int)c->vars.size() || !c->vars[hh].alive || c->vars[hh].kind != OVP_KIND_POSE || c->vars[hh].id < 0 || hh == c->h_calib)
       return fail(c, OVP_ERR_BAD_ARGS, "triangulate_features: measurement %d: handle %d is not a clone in the state", k, hh);
   }
   if (c->var_table_dirty) {

@@ -1116,7 +1116,7 @@ int ovp_optimize_plane(ovp_ctx *h, int n_planes, const int *feat_offset, const i
     return fail(c, OVP_ERR_BAD_ARGS, "optimize_plane: sigma_px_norm / sigma_c must be positive");
   for (int k = 0; k < M; k++) {
     const int hh = meas_clone[k];
-    if (hh < 0 || hh >= (int)c->vars.size() || !c->vars[hh].alive || c->vars[hh].kind != OVP_KIND_POSE || c->vars[hh].id < 0)
+    if (hh < 0 || hh >= (int)c->vars.size() || !c->vars[hh].alive || c->vars[hh].kind != OVP_KIND_POSE || c->vars[hh].id < 0 || hh == c->h_calib)
       return fail(c, OVP_ERR_BAD_ARGS, "optimize_plane: measurement %d: handle %d is not a clone in the state", k, hh);
   }
   if (Ftot == 0) {

@@ -14,9 +14,11 @@
 // TrustRegionMinimizer + DoglegStrategy(TRADITIONAL_DOGLEG) with the solver defaults (Jacobi scaling, function_tolerance 1e-6,
 // gradient_tolerance 1e-10, parameter_tolerance 1e-8, initial radius 1e4, min_relative_decrease 1e-3, mu in [1e-8, 1] x10,
 // min_lm_diagonal 1e-6) and the loss correction of corrector.cc (rho'' <= 0 for Cauchy: residual and Jacobian scaled by sqrt(rho')).
-// PARITY UNPINNED: there is no Ceres here to run; the tests pin the restatement by (i) the first-order optimality of its result
-// for the robustified cost, (ii) an independent SciPy trust-region solve of the same cost, (iii) the CUDA path, which forms the
-// same iteration through a Schur complement instead of the dense normal equations used here.
+// PARITY UNPINNED: there is no Ceres here to run; tests/test_cpu_planefit.py pins the restatement by (i) the recovery of the true plane on
+// noise-free data, (ii) an independent NumPy transcription of the objective from the factor definitions (equal to evaluate() to 1e-10) and
+// generic minimisers of it (SciPy L-BFGS-B / trust-region least squares) that approach the end point from above and never undercut it,
+// (iii) the CUDA path, which forms the same iteration through per-feature blocks and a Schur complement instead of the dense normal
+// equations used here (identical iteration counts and termination reasons, results to 1e-14).
 //
 // std::shuffle / std::uniform_int_distribution are implementation-defined: libstdc++ changed uniform_int_distribution in GCC 11
 // (Lemire's method for 32-bit generators).  The reference's documented toolchains (Ubuntu 18.04 / 20.04: GCC 7 / 9) use the older
@@ -607,7 +609,7 @@ struct PlaneFitting {
         break;
       }
       const double relative_decrease = (x_cost - cand_cost) / model_cost_change;
-      if (getenv("ORC_PF_TRACE"))
+      if (getenv("ORC_PF_TRACE")) // per-iteration trace of the checker (tools / debugging)
         fprintf(stderr, "it %d cost %.6e cand %.6e model %.3e rel %.3f radius %.3e step %.3e dogleg %.3e mu %.1e\n", iteration, x_cost, cand_cost, model_cost_change,
                 relative_decrease, radius, step_norm, dogleg_step_norm, mu);
       if (relative_decrease > min_relative_decrease) { // HandleSuccessfulStep

@@ -219,3 +219,64 @@ def test_optimize_plane_reference_semantics():
     st, po, co, inl, info = orc.optimize_plane([0, 3], easy["meas_offset"][:4], easy["meas_clone"], easy["uv_norm"], easy["p_FinG"][:3], easy["cp_inG"][:1],
                                                 [0], 1.0 / 458.0, 0.01)
     assert st[0] == 0 and info[0, 1] == 0
+
+
+def test_cost_function_and_minimum_against_an_independent_numpy_scipy_solve():
+    """The refinement objective transcribed independently in NumPy from the factor definitions (Factor_PointOnPlane.cpp:39-70; the pinhole
+    reprojection factor with camera-frame poses, PlaneFitting.cpp:330-363; Cauchy loss on every BLOCK) equals the oracle's cost, and SciPy's
+    trust-region least squares on the same objective (one scalar residual per block = the block's norm, loss='cauchy') ends at the cost the
+    restated Ceres dogleg ends at (or stays above it)."""
+    from scipy.optimize import least_squares
+    from ov_plane_b200 import jpl
+    S = synth.make_scenario("small_planes", seed=2)
+    orc = oracle_backend.OracleContext(S.options)
+    ch = synth.load_scenario_into(orc, S)
+    pr = planefit_cases.refine_problem(S, ch, seed=2, consistent=True, slam_share=0.15)
+    sig_px, sig_c = 1.0 / 458.0, 0.01
+    calib = orc.var_get(orc.handle_calib())[0]
+    R_ItoC, p_IinC = jpl.quat_2_Rot(calib[:4]), calib[4:7]
+    cam = {}
+    for h in set(int(x) for x in pr["meas_clone"]):
+        v = orc.var_get(h)[0]
+        Rg = R_ItoC @ jpl.quat_2_Rot(v[:4])
+        cam[h] = (Rg, v[4:7] - Rg.T @ p_IinC)
+    fo, mo = pr["feat_offset"], pr["meas_offset"]
+    fx = np.zeros(len(fo) - 1, dtype=np.int32)
+    st, po, co, inl, info = orc.optimize_plane(fo, mo, pr["meas_clone"], pr["uv_norm"], pr["p_FinG"], pr["cp_inG"], fx, sig_px, sig_c, max_num_iterations=300)
+    assert (info[:, 0] == 1).all()
+    for p in range(len(fo) - 1):
+        a, b = fo[p], fo[p + 1]
+        free = [f for f in range(a, b) if mo[f + 1] > mo[f]]
+
+        ks = np.arange(mo[a], mo[b])
+        Rm = np.array([cam[int(pr["meas_clone"][k])][0] for k in ks]).reshape(-1, 3, 3)
+        pcm = np.array([cam[int(pr["meas_clone"][k])][1] for k in ks]).reshape(-1, 3)
+        uvm = pr["uv_norm"][ks].astype(np.float64)
+        fidx = np.repeat(np.arange(a, b), np.diff(mo[a:b + 1])) - a      # feature (within the plane) of every measurement
+        slam = np.array([f - a for f in range(a, b) if mo[f + 1] == mo[f]], dtype=int)
+        free_loc = np.array([f - a for f in free], dtype=int)
+
+        def blocks(x):
+            """block norms of the problem at x = [free features, cp] (vectorised over the measurements)"""
+            pf = pr["p_FinG"][a:b].copy()
+            pf[free_loc] = x[:3 * len(free)].reshape(-1, 3)
+            cp = x[3 * len(free):]
+            d = np.linalg.norm(cp)
+            n = cp / d
+            c = np.einsum("kij,kj->ki", Rm, pf[fidx] - pcm)
+            rep = np.linalg.norm((c[:, :2] / c[:, 2:3] - uvm) / sig_px, axis=1)      # one reprojection block per measurement
+            pl = np.abs(pf @ n - d)
+            return np.concatenate([rep, pl[fidx] / sig_c, pl[slam] / (2.0 * sig_c)])  # + one plane block per measurement, one inflated per SLAM feature
+
+        x0 = np.concatenate([pr["p_FinG"][f] for f in free] + [pr["cp_inG"][p]])
+        cost_np = 0.5 * np.log1p(blocks(x0) ** 2).sum()
+        assert abs(cost_np - info[p, 2]) < 1e-10 * info[p, 2], (cost_np, info[p, 2])          # the same objective at the start
+        if p != 1:
+            continue  # the objective is pinned on every plane; the independent minimisation runs on one (numerical derivatives are slow)
+        sol = least_squares(blocks, x0, loss="cauchy", f_scale=1.0, method="trf", x_scale="jac", xtol=1e-12, ftol=1e-12, gtol=1e-12, max_nfev=2500)
+        cost_sp = 0.5 * np.log1p(blocks(sol.x) ** 2).sum()
+        print("plane %d: cost %.4f -> restated Ceres dogleg %.6f (%d it) | SciPy trf on the NumPy transcription %.6f (%d evaluations)" % (
+            p, info[p, 2], info[p, 3], info[p, 1], cost_sp, sol.nfev))
+        # SciPy differentiates the block NORMS numerically (not smooth where a block vanishes) and creeps towards the dogleg's end point from above
+        # (66.62 after 30000 evaluations against 66.53): it never gets below it
+        assert info[p, 3] <= cost_sp * (1.0 + 3e-5) and cost_sp < 0.5 * info[p, 2]

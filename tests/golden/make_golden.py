@@ -35,8 +35,48 @@ def slam_case(name, seed, nslam, backend_factory, chi2):
 
 SLAM_CASES = [("tiny_planes", 0, 6), ("tiny_points", 0, 8)]
 
+
+def planefit_case(name, seed, backend_factory, chi2):
+    """PlaneFitting on the planes of a scenario (RANSAC batch with extra degenerate candidates, refinement batch with a mixed fix_plane vector)
+    and one anchor change - shared by the golden writer, the CPU regression test and the GPU test."""
+    import planefit_cases
+    S = synth.make_scenario(name, seed=seed)
+    S.options = dict(S.options, max_clone_size=S.cfg["n_clones"] - 1)
+    be = backend_factory(S)
+    be.set_chi2_table(chi2)
+    ch = synth.load_scenario_into(be, S)
+    fo, pts = planefit_cases.plane_point_sets(S, seed=seed)
+    rng = np.random.RandomState(5)
+    for e in (rng.randn(4, 3), np.array([1.0, 2.0, 3.0]) + 0.004 * rng.randn(30, 3)):
+        fo = np.append(fo, fo[-1] + len(e)).astype(np.int32)
+        pts = np.vstack([pts, e])
+    st, ab, inl = be.plane_fitting(fo, pts, 5, 200.0)
+    pr = planefit_cases.refine_problem(S, ch, seed=seed, consistent=True, noise=0.006)
+    fx = np.zeros(len(pr["feat_offset"]) - 1, dtype=np.int32)
+    fx[1::2] = 1
+    rs, rp, rc, ri, rinfo = be.optimize_plane(pr["feat_offset"], pr["meas_offset"], pr["meas_clone"], pr["uv_norm"], pr["p_FinG"], pr["cp_inG"], fx,
+                                              1.0 / 458.0, 0.01)
+    # anchor change of the scenario's landmark: MSCKF inverse depth anchored in clone 5, moved to clone 9, then through change_anchors
+    from test_cpu_anchors import _anchored_landmark
+    fid, hl, _ = _anchored_landmark(be, S, ch, 4, ch[5])
+    be.slam_perform_anchor_change(fid, ch[9])
+    be.slam_perform_anchor_change(fid, ch[0])
+    n_changed = be.slam_change_anchors()
+    v, f = be.var_get(hl)
+    return dict(fit_status=st, fit_abcd=ab, fit_inlier=inl, ref_status=rs, ref_p=rp, ref_cp=rc, ref_inlier=ri, ref_info=rinfo,
+                anchor_value=np.asarray(v[:3]), anchor_fej=np.asarray(f[:3]), anchor_changed=np.array([n_changed]), P_anchor=be.cov())
+
+
+PLANEFIT_CASES = [("small_planes", 1), ("cfg3_n512_f600_p8", 0)]
+
 if __name__ == "__main__":
     chi2 = synth.chi2_table()
+    for name, seed in PLANEFIT_CASES:
+        g = planefit_case(name, seed, lambda S: ob.OracleContext(S.options), chi2)
+        np.savez_compressed(os.path.join(HERE, "planefit_%s_s%d.npz" % (name, seed)), **g)
+        print("planefit", name, seed, "fitted", g["fit_status"], "refined", g["ref_status"], "iterations", g["ref_info"][:, 1].astype(int), "written")
+    if len(sys.argv) > 1 and sys.argv[1] == "planefit":
+        sys.exit(0)
     for name, seed, nslam in SLAM_CASES:
         g = slam_case(name, seed, nslam, lambda S: ob.OracleContext(S.options), chi2)
         np.savez_compressed(os.path.join(HERE, "slam_%s_s%d.npz" % (name, seed)), **g)

@@ -280,3 +280,21 @@ def test_cost_function_and_minimum_against_an_independent_numpy_scipy_solve():
         # SciPy differentiates the block NORMS numerically (not smooth where a block vanishes) and creeps towards the dogleg's end point from above
         # (66.62 after 30000 evaluations against 66.53): it never gets below it
         assert info[p, 3] <= cost_sp * (1.0 + 3e-5) and cost_sp < 0.5 * info[p, 2]
+
+
+@pytest.mark.parametrize("name,seed", [("small_planes", 1), ("cfg3_n512_f600_p8", 0)])
+def test_oracle_reproduces_planefit_golden_vectors(name, seed):
+    """regression pin of the oracle's PlaneFitting / anchor-change restatement against the committed fixtures (tests/golden/planefit_*.npz,
+    written by tests/golden/make_golden.py; the `-m gpu` suite checks the CUDA path against the same files without the oracle)"""
+    import os
+    import sys
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold)
+    import make_golden
+    g = np.load(os.path.join(gold, "planefit_%s_s%d.npz" % (name, seed)))
+    r = make_golden.planefit_case(name, seed, lambda S: oracle_backend.OracleContext(S.options), synth.chi2_table())
+    for k in ("fit_status", "fit_inlier", "ref_status", "ref_inlier", "anchor_changed"):
+        assert np.array_equal(r[k], g[k]), k
+    assert np.array_equal(r["ref_info"][:, [0, 1, 4]], g["ref_info"][:, [0, 1, 4]])
+    for k in ("fit_abcd", "ref_p", "ref_cp", "anchor_value", "anchor_fej", "P_anchor"):
+        assert np.allclose(r[k], g[k], rtol=1e-9, atol=1e-12), k

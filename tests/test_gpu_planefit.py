@@ -98,3 +98,23 @@ def test_optimize_plane_edge_cases(chi2_table):
     assert np.array_equal(sg, so) and np.array_equal(ig, io) and np.array_equal(ng[:, 4], no[:, 4]), (sg, so, ng, no)
     assert ng[0, 4] == 4 and sg[1] == 0 and sg[2] == 0
     ctx.close()
+
+
+@pytest.mark.parametrize("name,seed", [("small_planes", 1), ("cfg3_n512_f600_p8", 0)])
+def test_planefit_and_anchor_change_against_committed_golden_vectors(name, seed, chi2_table):
+    """the CUDA path against the committed fixtures (tests/golden/planefit_*.npz, written by the oracle): no oracle at run time"""
+    import os
+    import sys
+    from ov_plane_b200 import api
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold)
+    import make_golden
+    g = np.load(os.path.join(gold, "planefit_%s_s%d.npz" % (name, seed)))
+    r = make_golden.planefit_case(name, seed, lambda S: api.Context(S.options, device=0, max_state=S.N + 64, max_meas_rows=60000), chi2_table)
+    for k in ("fit_status", "fit_inlier", "ref_status", "ref_inlier", "anchor_changed"):
+        assert np.array_equal(r[k], g[k]), k
+    assert np.array_equal(r["ref_info"][:, [0, 1, 4]], g["ref_info"][:, [0, 1, 4]])   # converged, iterations, termination reason
+    assert np.abs(r["fit_abcd"] - g["fit_abcd"]).max() < 1e-9
+    assert np.abs(r["ref_p"] - g["ref_p"]).max() < 1e-7 and np.abs(r["ref_cp"] - g["ref_cp"]).max() < 1e-7
+    assert np.abs(r["anchor_value"] - g["anchor_value"]).max() < 1e-10 and np.abs(r["anchor_fej"] - g["anchor_fej"]).max() < 1e-10
+    assert np.linalg.norm(r["P_anchor"] - g["P_anchor"]) / np.linalg.norm(g["P_anchor"]) < 1e-9

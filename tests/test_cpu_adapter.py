@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import pytest
 
 
-@pytest.mark.parametrize("src", ["StateHelperB200.cpp", "PlaneFittingB200.cpp", "UpdaterMSCKFB200.cpp"])
+@pytest.mark.parametrize("src", ["StateHelperB200.cpp", "PlaneFittingB200.cpp", "UpdaterMSCKFB200.cpp", "UpdatersB200.cpp"])
 def test_adapter_syntax_check(src):
     cmd = ["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "adapter", "stubs"), "-I", os.path.join(ROOT, "include"),
            os.path.join(ROOT, "adapter", src)]

@@ -364,3 +364,31 @@ def test_error_codes(chi2_table):
     with pytest.raises(api.OvpError) as e:
         ctx.ekf_propagation([ctx.handle_imu()], [ctx.handle_imu()], np.eye(15), np.zeros((15, 15)))
     assert e.value.status == 2
+
+
+@pytest.mark.parametrize("name,seed", [("tiny_points", 0), ("tiny_planes", 0), ("small_planes", 1), ("cfg1_euroc_n96", 0), ("cfg2_n256_f200", 0)])
+def test_msckf_update_against_committed_golden_vectors(name, seed, chi2_table):
+    """the CUDA path against the committed MSCKF fixtures (tests/golden/<scenario>.npz, written by the oracle): no oracle at run time.
+    Gates and Hx_order index-exact, posterior at the north-star 1e-6; the stacked-plane chi2 of the fixtures contains the reference's
+    round-off rows and is not compared."""
+    import os
+    from ov_plane_b200 import api
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "%s_s%d.npz" % (name, seed)))
+    S = synth.make_scenario(name, seed=seed)
+    assert np.array_equal(S.P0, g["P0"]) and np.array_equal(S.uv, g["uv"]), "scenario generator changed: regenerate the goldens"
+    ctx = api.Context(S.options, device=0, max_state=max(128, S.N + 64), max_meas_rows=60000)
+    ctx.set_chi2_table(chi2_table)
+    ch = synth.load_scenario_into(ctx, S)
+    r = ctx.msckf_update(synth.feature_batch(S, ch), 1.0, 1.0)
+    assert np.array_equal(r["feat_status"], g["feat_status"]) and np.array_equal(r["plane_status"], g["plane_status"])
+    hx = np.array([ch.index(h) if h in ch else -1 - h for h in r["hx_order"]])
+    assert np.array_equal(hx, g["hx_order_clone_idx"])
+    both = np.isfinite(g["feat_chi2"]) & np.isfinite(r["feat_chi2"])
+    assert np.array_equal(np.isfinite(g["feat_chi2"]), np.isfinite(r["feat_chi2"]))
+    assert np.allclose(r["feat_chi2"][both], g["feat_chi2"][both], rtol=1e-5, atol=1e-9)
+    e = relerr(ctx.cov(), g["P1"])
+    dv = np.abs(ctx.var_get(ctx.handle_imu())[0] - g["imu1"]).max() / max(1.0, np.abs(g["imu1"]).max())
+    dc = max(np.abs(ctx.var_get(h)[0][:7] - g["clones1"][i][:7]).max() for i, h in enumerate(ch))
+    print("%s %d vs golden: cov rel err %.3e, IMU state rel diff %.2e, clone values max diff %.2e" % (name, seed, e, dv, dc))
+    assert e < 1e-6 and dv < 1e-6 and dc < 1e-6
+    ctx.close()

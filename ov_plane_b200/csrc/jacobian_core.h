@@ -1,6 +1,6 @@
 // Per-measurement arithmetic of UpdaterHelper::get_feature_jacobian_full (UpdaterHelper.cpp:350-441, :447-512), mono camera,
 // GLOBAL_3D representation, radtan distortion (ov_core::CamRadtan — every shipped config, config/*/kalibr_imucam_chain.yaml).
-// Shared by the CUDA feature kernel and by a host-compiled unit test (tests/test_jacobian_core_cpu.py), hence __host__ __device__.
+// Shared by the CUDA feature kernels and by host code of the library (camera poses in planefit.cu / anchors.cu), hence __host__ __device__.
 #pragma once
 #include <math.h>
 
